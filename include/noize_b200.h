@@ -1,0 +1,258 @@
+/*
+ * noize_b200.h — C ABI of the B200-native heightmap hot path (libnoize_b200.so).
+ *
+ * This is the drop-in boundary for xshazwar/noize-job's per-cell pipeline.  Every entry
+ * point below replaces one of the reference's *static job delegates* (the table entries a
+ * PipelineStage binds), so a C# `[DllImport("noize_b200")]` stub with the same argument
+ * order can be swapped into the stage's delegate table.
+ *
+ * Reference paths are relative to the upstream repo (xshazwar/noize-job).
+ *
+ * Conventions
+ *   - every function returns int32_t: NZ_OK (0) or a negative NZ_E* code; nothing throws or
+ *     aborts.  `nz_last_error()` returns a thread-local message for the last failure
+ *     (reference convention: exceptions at schedule time, Pipeline/Stage/PipelineStage.cs:37).
+ *   - grids are row-major float32, idx = z*width + x   (Pipeline/Tiles/TileData.cs:135-138)
+ *   - reads outside the grid clamp to the edge cell     (Pipeline/Tiles/TileData.cs:72-77)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     NZ_E_CUDA.
+ *
+ * Two layers:
+ *   nz_*      host layer   — takes NativeSlice<float>-shaped HOST buffers (ptr,stride,length),
+ *                            moves them to the GPU, runs the stage, moves the result back.
+ *                            Between nz_pipeline_begin/nz_pipeline_end the device copy stays
+ *                            resident (keyed by host pointer) and the D2H is deferred.
+ *   nz_dev_*  device layer — operates on caller-owned DEVICE buffers on a caller stream, on
+ *                            rectangular (width x rows) grids so one rank can own a row band
+ *                            of a larger heightmap.  No synchronisation, no copies.
+ */
+#ifndef NOIZE_B200_H
+#define NOIZE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NZ_API __attribute__((visibility("default")))
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define NZ_OK              0
+#define NZ_E_INVALID      -1   /* bad argument (null slice, length != res*res, bad enum, ...) */
+#define NZ_E_CUDA         -2   /* CUDA runtime error or no device */
+#define NZ_E_NOMEM        -3   /* device/host allocation failed */
+#define NZ_E_STATE        -4   /* call not legal in the current pipeline state */
+#define NZ_E_UNSUPPORTED  -5   /* parameter combination not implemented */
+
+/* ---- enums: numeric values ARE the reference's C# enum order ------------------------- */
+
+/* NoiseStage.FractalNoise, Noise/NoiseStage.cs:15-24 (index into the delegate table :26-35) */
+typedef enum {
+    NZ_NOISE_SIN = 0,
+    NZ_NOISE_PERLIN = 1,
+    NZ_NOISE_PERIODIC_PERLIN = 2,
+    NZ_NOISE_SIMPLEX = 3,
+    NZ_NOISE_ROTATED_SIMPLEX = 4,
+    NZ_NOISE_CELLULAR = 5,
+    NZ_NOISE_DOMAIN_ROTATED_PERLIN = 6,
+    NZ_NOISE_DOMAIN_ROTATED_SIMPLEX = 7,
+    NZ_NOISE__COUNT = 8
+} nz_noise_type;
+
+/* KernelFilterType, Filter/Kernel/KernelJob.cs:79-94 */
+typedef enum {
+    NZ_FILTER_GAUSS9_S1 = 0,
+    NZ_FILTER_GAUSS7_S1 = 1,
+    NZ_FILTER_GAUSS5_S1 = 2,
+    NZ_FILTER_GAUSS3_S1 = 3,
+    NZ_FILTER_GAUSS9_S2 = 4,
+    NZ_FILTER_GAUSS7_S2 = 5,
+    NZ_FILTER_GAUSS5_S2 = 6,
+    NZ_FILTER_GAUSS3_S2 = 7,
+    NZ_FILTER_SMOOTH3 = 8,
+    NZ_FILTER_SOBEL3_HORIZONTAL = 9,
+    NZ_FILTER_SOBEL3_VERTICAL = 10,
+    NZ_FILTER_SOBEL3_2D = 11,
+    NZ_FILTER_PREWITT3_HORIZONTAL = 12,
+    NZ_FILTER_PREWITT3_VERTICAL = 13,
+    NZ_FILTER__COUNT = 14
+} nz_kernel_filter_type;
+
+/* GaussSigma, Filter/Kernel/Blur/BlurKernels.cs:8-25: sigma = 0.5 * (index + 1) */
+typedef enum {
+    NZ_SIGMA_0D50 = 0, NZ_SIGMA_1D00, NZ_SIGMA_1D50, NZ_SIGMA_2D00, NZ_SIGMA_2D50, NZ_SIGMA_3D00,
+    NZ_SIGMA_3D50, NZ_SIGMA_4D00, NZ_SIGMA_4D50, NZ_SIGMA_5D00, NZ_SIGMA_5D50, NZ_SIGMA_6D00,
+    NZ_SIGMA_6D50, NZ_SIGMA_7D00, NZ_SIGMA_7D50, NZ_SIGMA_8D00, NZ_SIGMA__COUNT
+} nz_gauss_sigma;
+
+/* MeshType, Mesh/Stage/MeshTileStage.cs:22-25 (index into the delegate table :30-33) */
+typedef enum {
+    NZ_MESH_SQUARE_GRID = 0,
+    NZ_MESH_OVERSHOOT_SQUARE_GRID = 1,
+    NZ_MESH__COUNT = 2
+} nz_mesh_type;
+
+#define NZ_MAX_KERNEL_WIDTH 25          /* BlurHelper.max_width, BlurKernels.cs:29 */
+#define NZ_MESH_VERTEX_BYTES 48         /* PositionStream32.Stream0, Mesh/Streams/PositionStream.cs:77-82 */
+
+/* NativeSlice<float> as Unity lays it out: base pointer, byte stride between elements, element
+ * count.  stride_bytes may be != 4 (Scripts/Editor/VisualizePipeline.cs:141 passes one channel of
+ * an RGBAFloat texture, stride 16). */
+typedef struct {
+    float*  ptr;
+    int32_t stride_bytes;
+    int32_t length;
+} nz_slice_f32;
+
+/* One vertex as the GPU writes it: {float3 position; float3 normal; float4 tangent; float2 uv}
+ * (Mesh/Job/Vertex.cs:5-10, StructLayout.Sequential in PositionStream.cs:77-82). */
+typedef struct {
+    float position[3];
+    float normal[3];
+    float tangent[4];
+    float uv[2];
+} nz_mesh_vertex;
+
+/* per-call timing of the LAST host-layer call made by the calling thread (milliseconds) */
+typedef struct {
+    float ms_h2d;
+    float ms_kernel;
+    float ms_d2h;
+    int32_t kernel_launches;
+} nz_timing;
+
+/* ---- lifecycle / introspection ------------------------------------------------------ */
+
+/* Select the CUDA device(s) this process drives; devices==NULL or n==0 -> device 0.  Optional:
+ * the first compute call initialises device 0 lazily.  Safe to call again (re-initialises). */
+NZ_API int32_t nz_init(const int32_t* devices, int32_t n);
+NZ_API int32_t nz_shutdown(void);
+NZ_API const char* nz_last_error(void);
+NZ_API const char* nz_version(void);
+/* number of kernels this library has launched since nz_init (monotonic, all threads) */
+NZ_API int64_t nz_kernel_launch_count(void);
+NZ_API int32_t nz_last_timing(nz_timing* out);
+
+/* ---- host-side helpers that need no GPU (host logic of the stages) ------------------ */
+
+/* FractalJob.CalcFractalNormValue, Noise/Fractal/Fractal.cs:31-40 (startingAmplitude ignored). */
+NZ_API float nz_fractal_norm_value(float hurst, int32_t octaves);
+/* GaussianKernel.GetKernel, Filter/Kernel/Blur/BlurKernels.cs:42-58 (+ tables :59-316):
+ * normalised sampled Gaussian of odd `width` (after BlurHelper.limitWidth :30-36); writes
+ * `*width_out` floats to `out` (capacity >= NZ_MAX_KERNEL_WIDTH). */
+NZ_API int32_t nz_gauss_kernel(int32_t sigma, int32_t width, float* out, int32_t* width_out);
+/* BlurHelper.limitWidth, BlurKernels.cs:30-36 */
+NZ_API int32_t nz_limit_width(int32_t width);
+/* SeparableKernelFilter tables, Filter/Kernel/KernelJob.cs:97-136,217-292: fills kx,kz (capacity
+ * >= 9), *ksize, *factor for every filter except SOBEL3_2D (returns NZ_E_UNSUPPORTED there:
+ * that one is a two-branch reduce, KernelJob.cs:187-215). */
+NZ_API int32_t nz_kernel_filter_table(int32_t filter_type, float* kx, float* kz, int32_t* ksize, float* factor);
+/* MeshTileGenerator tile maths, Scripts/MeshTileGenerator.cs:166-177,197-206 */
+NZ_API int32_t nz_tile_geometry(int32_t tile_resolution, int32_t tile_size, int32_t margin,
+                                int32_t* mesh_resolution, int32_t* margin_pix, float* mesh_tile_size);
+
+/* ---- host layer: one call per reference delegate ------------------------------------- */
+
+/* FractalJobDelegate, Noise/Fractal/Fractal.cs:76-88, table Noise/NoiseStage.cs:26-35.
+ * dst.length must be resolution*resolution. */
+NZ_API int32_t nz_fractal(nz_slice_f32 dst, int32_t resolution, int32_t noise_type, float hurst,
+                          float starting_amplitude, float stepdown, float detune_rate, int32_t octaves,
+                          int32_t xpos, int32_t zpos, int32_t noise_size);
+
+/* SeperableKernelFilterDelegate, Filter/Kernel/KernelJob.cs:308-314, applied `iterations` times as
+ * KernelFilterStage.Schedule does (Filter/KernelFilterStage.cs:31-43).  `tmp` is accepted for
+ * signature parity and never touched (the GPU path ping-pongs in HBM); it may be {NULL,0,0}. */
+NZ_API int32_t nz_kernel_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t filter_type,
+                                int32_t resolution, int32_t iterations);
+
+/* SeparableKernelFilter.ScheduleSeries, KernelJob.cs:165-185: arbitrary odd ksize <= 25. */
+NZ_API int32_t nz_separable(nz_slice_f32 src, nz_slice_f32 tmp, int32_t ksize, const float* kx,
+                            const float* kz, float factor, int32_t resolution, int32_t iterations);
+
+/* GaussFilter.GaussFilterDelegate, Filter/Kernel/Blur/BlurJob.cs:23-30 (+StageGaussianBlur.cs:33-46) */
+NZ_API int32_t nz_gauss_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t width, int32_t sigma,
+                               int32_t resolution, int32_t iterations);
+/* SmoothFilter.SmoothFilterDelegate, BlurJob.cs:46-52 (+StageSmoothBlur.cs:33-46) */
+NZ_API int32_t nz_smooth_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t width,
+                                int32_t resolution, int32_t iterations);
+
+/* ErosionKernelJobDelegate, KernelJob.cs:350 (Schedule :333-347), applied `iterations` times
+ * ("Value Erosion"): per call X pass min(src(x-1,z),src(x,z)) then Z pass likewise. */
+NZ_API int32_t nz_min_erosion(nz_slice_f32 src, int32_t resolution, int32_t iterations);
+
+/* FlowMapStage.ScheduleAll, Geologic/Stage/FlowMapStage.cs:124-195: fill water 1e-4, `iterations` x
+ * (outflow step, water step), velocity magnitude written over `height`, then (v-normMin)/(normMax-normMin).
+ * Flow fields start at zero (the reference leaves them uninitialised, FlowMapStage.cs:55-62). */
+NZ_API int32_t nz_flowmap(nz_slice_f32 height, int32_t resolution, int32_t iterations,
+                          float norm_min, float norm_max);
+
+/* HeightMapMeshJobScheduleDelegate, Mesh/Job/HeightMapMeshJob.cs:55-65, table MeshTileStage.cs:30-33.
+ * vertices: (resolution+1)^2 * 48 B (Mesh.MeshData.GetVertexData<Stream0>, PositionStream.cs:121);
+ * indices : 6*resolution^2 uint32     (GetIndexData<uint>, :122).  Both HOST pointers. */
+NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* indices,
+                                 int32_t resolution, int32_t input_resolution, int32_t margin_pix,
+                                 float tile_height, float tile_size, nz_slice_f32 heights);
+
+/* ---- host layer: residency ---------------------------------------------------------- */
+
+/* Between begin/end (per calling thread) the device mirror of every host slice a stage touches
+ * stays in HBM and D2H is deferred: chained stages pay one H2D (none if the first stage is a
+ * generator) and one D2H.  nz_pipeline_end flushes every dirty mirror to its host slice. */
+NZ_API int32_t nz_pipeline_begin(void);
+NZ_API int32_t nz_pipeline_end(void);
+/* Flush one mirror early (e.g. before a Burst stage reads the slice). */
+NZ_API int32_t nz_flush_to_host(const float* host_ptr);
+/* cudaHostRegister / Unregister a long-lived host allocation (PipelineStateManager buffers). */
+NZ_API int32_t nz_pin(void* host_ptr, size_t bytes);
+NZ_API int32_t nz_unpin(void* host_ptr);
+
+/* ---- device layer ------------------------------------------------------------------- */
+/* All pointers are DEVICE pointers unless named h_*.  `stream` is a cudaStream_t (NULL = legacy
+ * default stream).  Grids are width x rows, contiguous.  Calls only enqueue work.           */
+
+/* Noise rows [z_first, z_first+rows) of the tile whose origin is (xpos,zpos): cell (x,r) gets
+ * NoiseValue(x, z_first+r) of Fractal.cs:114-131. */
+NZ_API int32_t nz_dev_fractal(float* d_dst, int32_t width, int32_t rows, int32_t z_first,
+                              int32_t noise_type, float hurst, float starting_amplitude, float stepdown,
+                              float detune_rate, int32_t octaves, int32_t xpos, int32_t zpos,
+                              int32_t noise_size, void* stream);
+
+/* `iterations` x (X pass, Z pass).  Input in d_data; d_tmp is scratch of the same size.  The
+ * result is left in whichever of the two the last pass wrote; *d_result receives that pointer.
+ * Pass d_result==NULL to force the result into d_data (may cost one extra copy). */
+NZ_API int32_t nz_dev_separable(float* d_data, float* d_tmp, int32_t width, int32_t rows,
+                                int32_t ksize, const float* h_kx, const float* h_kz, float factor,
+                                int32_t iterations, float** d_result, void* stream);
+NZ_API int32_t nz_dev_kernel_filter(float* d_data, float* d_tmp, int32_t width, int32_t rows,
+                                    int32_t filter_type, int32_t iterations, float** d_result, void* stream);
+NZ_API int32_t nz_dev_min_erosion(float* d_data, float* d_tmp, int32_t width, int32_t rows,
+                                  int32_t iterations, float** d_result, void* stream);
+
+/* Bytes of scratch nz_dev_flowmap needs for a width x rows grid. */
+NZ_API size_t  nz_dev_flowmap_scratch_bytes(int32_t width, int32_t rows, int32_t iterations);
+NZ_API int32_t nz_dev_flowmap(float* d_height, void* d_scratch, int32_t width, int32_t rows,
+                              int32_t iterations, float norm_min, float norm_max,
+                              float** d_result, void* stream);
+
+/* Vertex rows [vz_begin, vz_end) (0 <= vz < resolution+1) and the triangle rows they close
+ * (row z>0 writes the 2*resolution triangles between vertex rows z-1 and z).
+ * d_heights points at input row `h_row_first` of the input_resolution^2 height grid and holds
+ * `h_rows` rows; d_vertices points at vertex row vz_begin; d_indices at triangle row
+ * max(vz_begin,1).  Index VALUES are global. */
+NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32_t* d_indices,
+                                     int32_t resolution, int32_t input_resolution, int32_t margin_pix,
+                                     float tile_height, float tile_size, const float* d_heights,
+                                     int32_t h_row_first, int32_t h_rows,
+                                     int32_t vz_begin, int32_t vz_end, void* stream);
+
+/* FP32 FMA-pipe peak micro-benchmark: launches `grid` CTAs of 256 threads each running `iters`
+ * x 16 independent dependent-chain FFMAs per thread; returns FLOP count in *flops.  Used by
+ * bench.py to measure the FP32 roofline denominator on the box it runs on. */
+NZ_API int32_t nz_dev_fma_peak(float* d_sink, int32_t grid, int32_t iters, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOIZE_B200_H */
