@@ -1,0 +1,704 @@
+// abi.cu — the C ABI of libnoize_b200.so (include/noize_b200.h): status/error plumbing, host-side
+// stage logic (tables, normalisation value, tile geometry), the device layer (nz_dev_*) and the host
+// layer (nz_*) with its per-thread stream, device-buffer pool and residency map.
+//
+// There is deliberately no CPU path in this file: every compute entry point ends in a kernel
+// launch from noise/filter/flow/mesh_kernels.cu or fails with NZ_E_CUDA.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include "nz_common.cuh"
+
+namespace nz {
+
+// ---- errors -----------------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+int32_t cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return e == cudaErrorMemoryAllocation ? NZ_E_NOMEM : NZ_E_CUDA;
+}
+
+// ---- host-side stage logic --------------------------------------------------------------------
+// Normalised sampled Gaussian; equals every literal table of Filter/Kernel/Blur/BlurKernels.cs:59-316
+// and gauss*_s* of Filter/Kernel/KernelJob.cs:97-105 after rounding to float (tests/test_host_logic.py).
+void gauss_table(double sigma, int width, float* out) {
+    const int r = width / 2;
+    double g[NZ_MAX_KERNEL_WIDTH + 1], sum = 0.0;
+    for (int i = -r; i <= r; i++) {
+        g[i + r] = exp(-(double)(i * i) / (2.0 * sigma * sigma));
+        sum += g[i + r];
+    }
+    for (int i = 0; i < width; i++) out[i] = (float)(g[i] / sum);
+}
+
+// SeparableKernelFilter.Schedule switch, KernelJob.cs:217-292
+int32_t kernel_filter_table(int filter, float* kx, float* kz, int* ksize, float* factor) {
+    static const float k_m101[3] = {-1.f, 0.f, 1.f}, k_121[3] = {1.f, 2.f, 1.f}, k_10m1[3] = {1.f, 0.f, -1.f},
+                       k_111[3] = {1.f, 1.f, 1.f};
+    float g[9];
+    const float *x = k_111, *z = k_111;
+    int size = 3;
+    float f = 1.0f;
+    switch (filter) {
+        case NZ_FILTER_GAUSS9_S1: size = 9; gauss_table(1.0, 9, g); x = z = g; break;
+        case NZ_FILTER_GAUSS7_S1: size = 7; gauss_table(1.0, 7, g); x = z = g; break;
+        case NZ_FILTER_GAUSS5_S1: size = 5; gauss_table(1.0, 5, g); x = z = g; break;
+        case NZ_FILTER_GAUSS3_S1: size = 3; gauss_table(1.0, 3, g); x = z = g; break;
+        case NZ_FILTER_GAUSS9_S2: size = 9; gauss_table(2.0, 9, g); x = z = g; break;
+        case NZ_FILTER_GAUSS7_S2: size = 7; gauss_table(2.0, 7, g); x = z = g; break;
+        case NZ_FILTER_GAUSS5_S2: size = 5; gauss_table(2.0, 5, g); x = z = g; break;
+        case NZ_FILTER_GAUSS3_S2: size = 3; gauss_table(2.0, 3, g); x = z = g; break;
+        case NZ_FILTER_SMOOTH3: f = 1.0f / 3.0f; break;
+        case NZ_FILTER_SOBEL3_HORIZONTAL: x = k_m101; z = k_121; break;
+        case NZ_FILTER_SOBEL3_VERTICAL: x = k_121; z = k_10m1; break;
+        case NZ_FILTER_PREWITT3_HORIZONTAL: x = k_10m1; z = k_111; break;
+        case NZ_FILTER_PREWITT3_VERTICAL: x = k_111; z = k_m101; break;
+        case NZ_FILTER_SOBEL3_2D:
+            set_error("kernel_filter_table: Sobel3_2D is a two-branch reduce, not one separable kernel");
+            return NZ_E_UNSUPPORTED;
+        default:
+            set_error("kernel_filter_table: filter_type %d out of range", filter);
+            return NZ_E_INVALID;
+    }
+    memcpy(kx, x, size * sizeof(float));
+    memcpy(kz, z, size * sizeof(float));
+    *ksize = size;
+    *factor = f;
+    return NZ_OK;
+}
+
+// ---- process context ----------------------------------------------------------------------------
+struct Context {
+    std::mutex mu;
+    bool ready = false;
+    int device = 0;
+    // device-buffer pool: freed blocks are kept, keyed by size (stage buffers repeat the same sizes)
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+};
+static Context g_ctx;
+
+static int32_t ensure_init() {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.ready) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0) {
+            set_error("no CUDA device available (%s); libnoize_b200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+            return NZ_E_CUDA;
+        }
+        if (g_ctx.device >= n) {
+            set_error("device %d requested but only %d visible", g_ctx.device, n);
+            return NZ_E_CUDA;
+        }
+        g_ctx.ready = true;
+    }
+    NZ_CUDA(cudaSetDevice(g_ctx.device));
+    return NZ_OK;
+}
+
+static int32_t pool_alloc(void** p, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        auto it = g_ctx.free_blocks.find(bytes);
+        if (it != g_ctx.free_blocks.end()) {
+            *p = it->second;
+            g_ctx.free_blocks.erase(it);
+            g_ctx.live[*p] = bytes;
+            return NZ_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_ctx.mu);
+            for (auto& kv : g_ctx.free_blocks) drop.push_back(kv.second);
+            g_ctx.free_blocks.clear();
+        }
+        for (void* d : drop) cudaFree(d);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    g_ctx.live[*p] = bytes;
+    return NZ_OK;
+}
+
+static void pool_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    auto it = g_ctx.live.find(p);
+    if (it == g_ctx.live.end()) return;
+    g_ctx.free_blocks.emplace(it->second, p);
+    g_ctx.live.erase(it);
+}
+
+// ---- per-thread state: stream, timing events, residency map ------------------------------------
+struct Mirror {
+    float* d = nullptr;    // device copy of the slice (contiguous n floats)
+    float* d_tmp = nullptr;  // ping-pong partner, allocated on demand, same size
+    size_t n = 0;
+    nz_slice_f32 host{};
+    bool dirty = false;  // device newer than host
+};
+
+struct ThreadState {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after h2d, after kernels, after d2h
+    bool timed = false;
+    long long launches_at_start = 0;
+    int launches = 0;
+    bool in_pipeline = false;
+    std::unordered_map<const void*, Mirror> mirrors;
+    ~ThreadState() {}
+};
+static thread_local ThreadState t_state;
+
+static int32_t thread_ready() {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    if (!t_state.stream) {
+        NZ_CUDA(cudaStreamCreateWithFlags(&t_state.stream, cudaStreamNonBlocking));
+        for (auto& e : t_state.ev) NZ_CUDA(cudaEventCreate(&e));
+    }
+    return NZ_OK;
+}
+
+static int32_t check_slice(const nz_slice_f32& s, long long expect, const char* who) {
+    NZ_REQUIRE(s.ptr != nullptr, "%s: slice pointer is null", who);
+    NZ_REQUIRE(s.stride_bytes >= 4, "%s: slice stride %d < 4", who, s.stride_bytes);
+    NZ_REQUIRE((long long)s.length == expect, "%s: slice length %d != %lld (resolution^2)", who, s.length, expect);
+    return NZ_OK;
+}
+
+static int32_t upload(Mirror& m) {
+    cudaStream_t s = t_state.stream;
+    if (m.host.stride_bytes == 4) {
+        NZ_CUDA(cudaMemcpyAsync(m.d, m.host.ptr, m.n * sizeof(float), cudaMemcpyHostToDevice, s));
+        return NZ_OK;
+    }
+    // strided NativeSlice (e.g. one channel of an RGBAFloat texture): move the span, gather on device
+    const size_t span = (m.n - 1) * (size_t)m.host.stride_bytes + sizeof(float);
+    void* raw = nullptr;
+    int32_t rc = pool_alloc(&raw, span);
+    if (rc != NZ_OK) return rc;
+    cudaError_t e = cudaMemcpyAsync(raw, m.host.ptr, span, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        rc = launch_gather_strided(m.d, (const unsigned char*)raw, m.host.stride_bytes, m.n, s);
+        if (rc == NZ_OK) e = cudaStreamSynchronize(s);
+    }
+    pool_free(raw);
+    if (e != cudaSuccess) return cuda_fail(e, "strided upload");
+    return rc;
+}
+
+static int32_t download(Mirror& m) {
+    cudaStream_t s = t_state.stream;
+    if (m.host.stride_bytes == 4) {
+        NZ_CUDA(cudaMemcpyAsync(m.host.ptr, m.d, m.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        // scatter back without touching the other channels of the host span
+        NZ_CUDA(cudaMemcpy2DAsync(m.host.ptr, (size_t)m.host.stride_bytes, m.d, sizeof(float), sizeof(float), m.n,
+                                  cudaMemcpyDeviceToHost, s));
+    }
+    m.dirty = false;
+    return NZ_OK;
+}
+
+// Obtain the device mirror of a host slice.  `need_contents`: the stage reads the slice (H2D unless a
+// resident mirror is already newer than the host).
+static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out) {
+    auto it = t_state.mirrors.find(s.ptr);
+    if (it != t_state.mirrors.end() && (it->second.n != (size_t)s.length || it->second.host.stride_bytes != s.stride_bytes)) {
+        // same base pointer, different shape: drop the stale mirror
+        if (it->second.dirty) {
+            int32_t rc = download(it->second);
+            if (rc != NZ_OK) return rc;
+            NZ_CUDA(cudaStreamSynchronize(t_state.stream));
+        }
+        pool_free(it->second.d);
+        pool_free(it->second.d_tmp);
+        t_state.mirrors.erase(it);
+        it = t_state.mirrors.end();
+    }
+    if (it == t_state.mirrors.end()) {
+        Mirror m;
+        m.n = (size_t)s.length;
+        m.host = s;
+        int32_t rc = pool_alloc((void**)&m.d, m.n * sizeof(float));
+        if (rc != NZ_OK) return rc;
+        it = t_state.mirrors.emplace(s.ptr, m).first;
+        if (need_contents) {
+            rc = upload(it->second);
+            if (rc != NZ_OK) return rc;
+        }
+    }
+    *out = &it->second;
+    return NZ_OK;
+}
+
+static int32_t ensure_tmp(Mirror& m) {
+    if (!m.d_tmp) return pool_alloc((void**)&m.d_tmp, m.n * sizeof(float));
+    return NZ_OK;
+}
+
+// A stage left its result in `result` (either m.d or m.d_tmp): make it the mirror's primary buffer.
+static void adopt_result(Mirror& m, float* result) {
+    if (result == m.d_tmp) {
+        m.d_tmp = m.d;
+        m.d = result;
+    }
+    m.dirty = true;
+}
+
+// End of a host-layer stage: outside a pipeline, bring the result home and drop the mirror.
+static int32_t finish(Mirror* m) {
+    cudaStream_t s = t_state.stream;
+    NZ_CUDA(cudaEventRecord(t_state.ev[2], s));
+    if (!t_state.in_pipeline) {
+        int32_t rc = NZ_OK;
+        if (m->dirty) rc = download(*m);
+        cudaError_t e = cudaEventRecord(t_state.ev[3], s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        pool_free(m->d);
+        pool_free(m->d_tmp);
+        t_state.mirrors.erase(m->host.ptr);
+        if (rc != NZ_OK) return rc;
+        if (e != cudaSuccess) return cuda_fail(e, "stage completion");
+    } else {
+        NZ_CUDA(cudaEventRecord(t_state.ev[3], s));
+    }
+    t_state.timed = true;
+    t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
+    return NZ_OK;
+}
+
+static int32_t begin_stage() {
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    t_state.timed = false;
+    t_state.launches_at_start = g_launches.load();
+    NZ_CUDA(cudaEventRecord(t_state.ev[0], t_state.stream));
+    return NZ_OK;
+}
+static int32_t mark_uploaded() {
+    NZ_CUDA(cudaEventRecord(t_state.ev[1], t_state.stream));
+    return NZ_OK;
+}
+
+static int32_t fractal_params(FractalParams* p, int width, int rows, int z_first, int noise_type, float hurst,
+                              float start_amp, float stepdown, float detune, int octaves, int xpos, int zpos,
+                              int noise_size) {
+    NZ_REQUIRE(noise_type >= 0 && noise_type < NZ_NOISE__COUNT, "fractal: noise_type %d out of range", noise_type);
+    NZ_REQUIRE(width > 0 && rows > 0, "fractal: bad grid %d x %d", width, rows);
+    NZ_REQUIRE(octaves >= 1 && octaves <= 64, "fractal: octaves %d out of range [1,64]", octaves);
+    NZ_REQUIRE(noise_size != 0, "fractal: noise_size must be non-zero");
+    p->width = width;
+    p->rows = rows;
+    p->z_first = z_first;
+    p->octaves = octaves;
+    p->posx = (float)xpos;  // FractalGenerator.SetPosition, Fractal.cs:109-112
+    p->posz = (float)zpos;
+    p->noise_size = (float)noise_size;
+    p->start_amp = start_amp;
+    p->stepdown = stepdown;
+    p->detune_rate = detune;
+    p->G = exp2f(-hurst);                                // Fractal.cs:118
+    p->norm = nz_fractal_norm_value(hurst, octaves);     // Fractal.cs:31-40
+    return NZ_OK;
+}
+
+}  // namespace nz
+
+using namespace nz;
+
+// =================================================================================================
+// lifecycle / introspection
+// =================================================================================================
+extern "C" {
+
+NZ_API int32_t nz_init(const int32_t* devices, int32_t n) {
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        g_ctx.device = (devices && n > 0) ? devices[0] : 0;
+        g_ctx.ready = false;
+    }
+    return ensure_init();
+}
+
+NZ_API int32_t nz_shutdown(void) {
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        for (auto& kv : g_ctx.free_blocks) drop.push_back(kv.second);
+        g_ctx.free_blocks.clear();
+    }
+    for (void* d : drop) cudaFree(d);
+    return NZ_OK;
+}
+
+NZ_API const char* nz_last_error(void) { return t_err; }
+NZ_API const char* nz_version(void) { return "noize_b200 0.1.0 (sm_100a)"; }
+NZ_API int64_t nz_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
+
+NZ_API int32_t nz_last_timing(nz_timing* out) {
+    NZ_REQUIRE(out, "nz_last_timing: null output");
+    if (!t_state.timed) {
+        set_error("nz_last_timing: no completed host-layer call on this thread");
+        return NZ_E_STATE;
+    }
+    NZ_CUDA(cudaEventSynchronize(t_state.ev[3]));
+    NZ_CUDA(cudaEventElapsedTime(&out->ms_h2d, t_state.ev[0], t_state.ev[1]));
+    NZ_CUDA(cudaEventElapsedTime(&out->ms_kernel, t_state.ev[1], t_state.ev[2]));
+    NZ_CUDA(cudaEventElapsedTime(&out->ms_d2h, t_state.ev[2], t_state.ev[3]));
+    out->kernel_launches = t_state.launches;
+    return NZ_OK;
+}
+
+// =================================================================================================
+// host-side helpers (no GPU)
+// =================================================================================================
+NZ_API float nz_fractal_norm_value(float hurst, int32_t octaves) {
+    float G = exp2f(-hurst);
+    float a = 1.0f, t = 0.0f;
+    for (int i = 0; i < octaves; i++) {
+        t += a * 1.0f;
+        a *= G;
+    }
+    return t;
+}
+
+NZ_API int32_t nz_limit_width(int32_t width) {
+    if (width % 2 == 0) width += 1;
+    if (width > NZ_MAX_KERNEL_WIDTH) width = NZ_MAX_KERNEL_WIDTH;
+    return width < 3 ? 3 : width;
+}
+
+NZ_API int32_t nz_gauss_kernel(int32_t sigma, int32_t width, float* out, int32_t* width_out) {
+    NZ_REQUIRE(sigma >= 0 && sigma < NZ_SIGMA__COUNT, "nz_gauss_kernel: sigma index %d out of range", sigma);
+    NZ_REQUIRE(out, "nz_gauss_kernel: null output");
+    width = nz_limit_width(width);
+    gauss_table(0.5 * (sigma + 1), width, out);
+    if (width_out) *width_out = width;
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_kernel_filter_table(int32_t filter_type, float* kx, float* kz, int32_t* ksize, float* factor) {
+    NZ_REQUIRE(kx && kz && ksize && factor, "nz_kernel_filter_table: null output");
+    return kernel_filter_table(filter_type, kx, kz, ksize, factor);
+}
+
+NZ_API int32_t nz_tile_geometry(int32_t tile_resolution, int32_t tile_size, int32_t margin, int32_t* mesh_resolution,
+                                int32_t* margin_pix, float* mesh_tile_size) {
+    NZ_REQUIRE(tile_resolution > 0 && tile_size > 0, "nz_tile_geometry: bad tile");
+    // calcTotalResolution / calcMarginVerts / calculateMarginWS, Scripts/MeshTileGenerator.cs:166-177
+    double patchRes = (tile_resolution * 1.0) / tile_size;
+    int total = tile_resolution + (2 * (int)(float)(margin * patchRes));
+    int mv = (int)((total - tile_resolution) / 2);
+    float marginWS = mv * (float)((tile_size * 1.0) / tile_resolution);
+    if (mesh_resolution) *mesh_resolution = total;
+    if (margin_pix) *margin_pix = mv;
+    if (mesh_tile_size) *mesh_tile_size = tile_size + (2 * marginWS);  // RequestMesh, :197-206
+    return NZ_OK;
+}
+
+// =================================================================================================
+// device layer
+// =================================================================================================
+NZ_API int32_t nz_dev_fractal(float* d_dst, int32_t width, int32_t rows, int32_t z_first, int32_t noise_type,
+                              float hurst, float starting_amplitude, float stepdown, float detune_rate,
+                              int32_t octaves, int32_t xpos, int32_t zpos, int32_t noise_size, void* stream) {
+    NZ_REQUIRE(d_dst, "nz_dev_fractal: null destination");
+    FractalParams p;
+    int32_t rc = fractal_params(&p, width, rows, z_first, noise_type, hurst, starting_amplitude, stepdown, detune_rate,
+                                octaves, xpos, zpos, noise_size);
+    if (rc != NZ_OK) return rc;
+    rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_fractal(d_dst, noise_type, p, (cudaStream_t)stream);
+}
+
+NZ_API int32_t nz_dev_separable(float* d_data, float* d_tmp, int32_t width, int32_t rows, int32_t ksize,
+                                const float* h_kx, const float* h_kz, float factor, int32_t iterations,
+                                float** d_result, void* stream) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_separable(d_data, d_tmp, width, rows, ksize, h_kx, h_kz, factor, iterations, d_result,
+                            (cudaStream_t)stream);
+}
+
+NZ_API int32_t nz_dev_kernel_filter(float* d_data, float* d_tmp, int32_t width, int32_t rows, int32_t filter_type,
+                                    int32_t iterations, float** d_result, void* stream) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    NZ_REQUIRE(filter_type >= 0 && filter_type < NZ_FILTER__COUNT, "kernel_filter: filter_type %d out of range", filter_type);
+    if (filter_type == NZ_FILTER_SOBEL3_2D)
+        return launch_sobel2d(d_data, d_tmp, width, rows, iterations, d_result, (cudaStream_t)stream);
+    float kx[9], kz[9], factor;
+    int ksize;
+    rc = kernel_filter_table(filter_type, kx, kz, &ksize, &factor);
+    if (rc != NZ_OK) return rc;
+    return launch_separable(d_data, d_tmp, width, rows, ksize, kx, kz, factor, iterations, d_result, (cudaStream_t)stream);
+}
+
+NZ_API int32_t nz_dev_min_erosion(float* d_data, float* d_tmp, int32_t width, int32_t rows, int32_t iterations,
+                                  float** d_result, void* stream) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_min_erosion(d_data, d_tmp, width, rows, iterations, d_result, (cudaStream_t)stream);
+}
+
+NZ_API size_t nz_dev_flowmap_scratch_bytes(int32_t width, int32_t rows, int32_t iterations) {
+    if (width <= 0 || rows <= 0) return 0;
+    return flowmap_scratch_bytes(width, rows, iterations);
+}
+
+NZ_API int32_t nz_dev_flowmap(float* d_height, void* d_scratch, int32_t width, int32_t rows, int32_t iterations,
+                              float norm_min, float norm_max, float** d_result, void* stream) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_flowmap(d_height, d_scratch, width, rows, iterations, norm_min, norm_max, d_result, (cudaStream_t)stream);
+}
+
+NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32_t* d_indices, int32_t resolution,
+                                     int32_t input_resolution, int32_t margin_pix, float tile_height, float tile_size,
+                                     const float* d_heights, int32_t h_row_first, int32_t h_rows, int32_t vz_begin,
+                                     int32_t vz_end, void* stream) {
+    (void)margin_pix;  // consumed only by MarginScale(), which nothing calls (SquareGridHeightMap.cs:41-56)
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_mesh(mesh_type, d_vertices, d_indices, resolution, input_resolution, tile_height, tile_size, d_heights,
+                       h_row_first, h_rows, vz_begin, vz_end, (cudaStream_t)stream);
+}
+
+NZ_API int32_t nz_dev_fma_peak(float* d_sink, int32_t grid, int32_t iters, double* flops, void* stream) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_fma_peak(d_sink, grid, iters, flops, (cudaStream_t)stream);
+}
+
+// =================================================================================================
+// host layer
+// =================================================================================================
+NZ_API int32_t nz_pipeline_begin(void) {
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    if (t_state.in_pipeline) {
+        set_error("nz_pipeline_begin: already inside a pipeline on this thread");
+        return NZ_E_STATE;
+    }
+    t_state.in_pipeline = true;
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_flush_to_host(const float* host_ptr) {
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    auto it = t_state.mirrors.find(host_ptr);
+    if (it == t_state.mirrors.end()) return NZ_OK;  // nothing resident: host is current
+    if (it->second.dirty) {
+        rc = download(it->second);
+        if (rc != NZ_OK) return rc;
+    }
+    NZ_CUDA(cudaStreamSynchronize(t_state.stream));
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_pipeline_end(void) {
+    if (!t_state.in_pipeline) {
+        set_error("nz_pipeline_end: no pipeline open on this thread");
+        return NZ_E_STATE;
+    }
+    int32_t rc = NZ_OK;
+    for (auto& kv : t_state.mirrors)
+        if (kv.second.dirty && rc == NZ_OK) rc = download(kv.second);
+    cudaError_t e = cudaStreamSynchronize(t_state.stream);
+    for (auto& kv : t_state.mirrors) {
+        pool_free(kv.second.d);
+        pool_free(kv.second.d_tmp);
+    }
+    t_state.mirrors.clear();
+    t_state.in_pipeline = false;
+    if (rc != NZ_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "nz_pipeline_end");
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_pin(void* host_ptr, size_t bytes) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    NZ_REQUIRE(host_ptr && bytes, "nz_pin: null/empty range");
+    NZ_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+    return NZ_OK;
+}
+NZ_API int32_t nz_unpin(void* host_ptr) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    NZ_CUDA(cudaHostUnregister(host_ptr));
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_fractal(nz_slice_f32 dst, int32_t resolution, int32_t noise_type, float hurst,
+                          float starting_amplitude, float stepdown, float detune_rate, int32_t octaves, int32_t xpos,
+                          int32_t zpos, int32_t noise_size) {
+    NZ_REQUIRE(resolution > 0 && resolution <= 46340, "nz_fractal: resolution %d out of range", resolution);
+    int32_t rc = check_slice(dst, (long long)resolution * resolution, "nz_fractal");
+    if (rc != NZ_OK) return rc;
+    FractalParams p;
+    rc = fractal_params(&p, resolution, resolution, 0, noise_type, hurst, starting_amplitude, stepdown, detune_rate,
+                        octaves, xpos, zpos, noise_size);
+    if (rc != NZ_OK) return rc;
+    if ((rc = begin_stage()) != NZ_OK) return rc;
+    Mirror* m;
+    if ((rc = acquire(dst, /*need_contents=*/false, &m)) != NZ_OK) return rc;
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    rc = launch_fractal(m->d, noise_type, p, t_state.stream);
+    if (rc == NZ_OK) m->dirty = true;
+    int32_t rc2 = finish(m);
+    return rc != NZ_OK ? rc : rc2;
+}
+
+}  // extern "C"
+
+// shared body of the in-place two-buffer stages
+template <typename F>
+static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const char* who, bool need_tmp, F&& body) {
+    NZ_REQUIRE(resolution > 0 && resolution <= 46340, "%s: resolution %d out of range", who, resolution);
+    int32_t rc = check_slice(src, (long long)resolution * resolution, who);
+    if (rc != NZ_OK) return rc;
+    if ((rc = begin_stage()) != NZ_OK) return rc;
+    Mirror* m;
+    if ((rc = acquire(src, /*need_contents=*/true, &m)) != NZ_OK) return rc;
+    if (need_tmp && (rc = ensure_tmp(*m)) != NZ_OK) return rc;
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    float* result = m->d;
+    rc = body(*m, &result);
+    if (rc == NZ_OK) adopt_result(*m, result);
+    int32_t rc2 = finish(m);
+    return rc != NZ_OK ? rc : rc2;
+}
+
+extern "C" {
+
+NZ_API int32_t nz_separable(nz_slice_f32 src, nz_slice_f32 tmp, int32_t ksize, const float* kx, const float* kz,
+                            float factor, int32_t resolution, int32_t iterations) {
+    (void)tmp;
+    return run_inplace_stage(src, resolution, "nz_separable", true, [&](Mirror& m, float** res) {
+        return launch_separable(m.d, m.d_tmp, resolution, resolution, ksize, kx, kz, factor, iterations, res, t_state.stream);
+    });
+}
+
+NZ_API int32_t nz_kernel_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t filter_type, int32_t resolution,
+                                int32_t iterations) {
+    (void)tmp;
+    NZ_REQUIRE(filter_type >= 0 && filter_type < NZ_FILTER__COUNT, "nz_kernel_filter: filter_type %d out of range", filter_type);
+    NZ_REQUIRE(iterations >= 1, "nz_kernel_filter: iterations %d < 1", iterations);
+    return run_inplace_stage(src, resolution, "nz_kernel_filter", true, [&](Mirror& m, float** res) {
+        return nz_dev_kernel_filter(m.d, m.d_tmp, resolution, resolution, filter_type, iterations, res, t_state.stream);
+    });
+}
+
+NZ_API int32_t nz_gauss_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t width, int32_t sigma, int32_t resolution,
+                               int32_t iterations) {
+    (void)tmp;
+    float k[NZ_MAX_KERNEL_WIDTH];
+    int32_t w = 0;
+    int32_t rc = nz_gauss_kernel(sigma, width, k, &w);
+    if (rc != NZ_OK) return rc;
+    return nz_separable(src, tmp, w, k, k, 1.0f, resolution, iterations);
+}
+
+NZ_API int32_t nz_smooth_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t width, int32_t resolution, int32_t iterations) {
+    // SmoothBlur.GetKernel, BlurKernels.cs:38-44 (after StageSmoothBlur's limitWidth)
+    int32_t w = nz_limit_width(width);
+    float k[NZ_MAX_KERNEL_WIDTH];
+    for (int i = 0; i < w; i++) k[i] = 1.0f / w;
+    return nz_separable(src, tmp, w, k, k, 1.0f, resolution, iterations);
+}
+
+NZ_API int32_t nz_min_erosion(nz_slice_f32 src, int32_t resolution, int32_t iterations) {
+    NZ_REQUIRE(iterations >= 0, "nz_min_erosion: iterations %d < 0", iterations);
+    return run_inplace_stage(src, resolution, "nz_min_erosion", true, [&](Mirror& m, float** res) {
+        return launch_min_erosion(m.d, m.d_tmp, resolution, resolution, iterations, res, t_state.stream);
+    });
+}
+
+NZ_API int32_t nz_flowmap(nz_slice_f32 height, int32_t resolution, int32_t iterations, float norm_min, float norm_max) {
+    NZ_REQUIRE(iterations >= 0, "nz_flowmap: iterations %d < 0", iterations);
+    void* scratch = nullptr;
+    int32_t rc = run_inplace_stage(height, resolution, "nz_flowmap", false, [&](Mirror& m, float** res) {
+        int32_t r = pool_alloc(&scratch, flowmap_scratch_bytes(resolution, resolution, iterations));
+        if (r != NZ_OK) return r;
+        return launch_flowmap(m.d, scratch, resolution, resolution, iterations, norm_min, norm_max, res, t_state.stream);
+    });
+    if (scratch) {
+        // the stream may still be using it inside a pipeline: order the release after the work
+        if (t_state.in_pipeline) cudaStreamSynchronize(t_state.stream);
+        pool_free(scratch);
+    }
+    return rc;
+}
+
+NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* indices, int32_t resolution,
+                                 int32_t input_resolution, int32_t margin_pix, float tile_height, float tile_size,
+                                 nz_slice_f32 heights) {
+    (void)margin_pix;
+    NZ_REQUIRE(vertices && indices, "nz_heightmap_mesh: null output buffer");
+    NZ_REQUIRE(resolution > 0 && input_resolution > 0 && input_resolution <= 46340, "nz_heightmap_mesh: bad resolution");
+    int32_t rc = check_slice(heights, (long long)input_resolution * input_resolution, "nz_heightmap_mesh");
+    if (rc != NZ_OK) return rc;
+    if ((rc = begin_stage()) != NZ_OK) return rc;
+    Mirror* m;
+    if ((rc = acquire(heights, /*need_contents=*/true, &m)) != NZ_OK) return rc;
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    const size_t vbytes = (size_t)(resolution + 1) * (resolution + 1) * NZ_MESH_VERTEX_BYTES;
+    const size_t ibytes = (size_t)6 * resolution * resolution * sizeof(uint32_t);
+    void *d_v = nullptr, *d_i = nullptr;
+    cudaStream_t s = t_state.stream;
+    rc = pool_alloc(&d_v, vbytes);
+    if (rc == NZ_OK) rc = pool_alloc(&d_i, ibytes);
+    if (rc == NZ_OK)
+        rc = launch_mesh(mesh_type, d_v, (uint32_t*)d_i, resolution, input_resolution, tile_height, tile_size, m->d, 0,
+                         input_resolution, 0, resolution + 1, s);
+    cudaError_t e = cudaSuccess;
+    if (rc == NZ_OK) {
+        e = cudaEventRecord(t_state.ev[2], s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(vertices, d_v, vbytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(indices, d_i, ibytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventRecord(t_state.ev[3], s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    pool_free(d_v);
+    pool_free(d_i);
+    if (!t_state.in_pipeline) {
+        // heights were only read: nothing to bring home
+        pool_free(m->d);
+        pool_free(m->d_tmp);
+        t_state.mirrors.erase(heights.ptr);
+    }
+    if (rc != NZ_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "nz_heightmap_mesh");
+    t_state.timed = true;
+    t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
+    return NZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// filter_kernels.cu — separable kernel filter, Sobel3_2D reduce and value (min) erosion (hot loop 2).
+//
+// Replaces GenericKernelJob<KernelTileMutation<KernelSample{X,Z}Operator>, RWTileData> and the
+// KernelMin{X,Z}Operator variants (Filter/Kernel/KernelJob.cs:18-54,165-185,317-347,
+// Filter/Kernel/KernelOperators.cs:18-117), with clamp-to-edge reads (Pipeline/Tiles/TileData.cs:72-77).
+// The reference's per-pass copy-back (FlushWriteSlice, TileData.cs:16-40) is result-neutral and is
+// replaced by ping-ponging between the two HBM buffers.
+//
+// Arithmetic order (must match oracle/noize_oracle.cpp generic_kernel_job):
+//   X pass: total = 0; for k = -r..r : total = fma(src(x+k,z), K[r+k], total);  out = total*factor
+//   Z pass: total = 0; for k = r..-r : total = fma(src(x,z+k), K[r-k], total);  out = total*factor
+#include "nz_common.cuh"
+
+namespace nz {
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------
+// Generic one-pass kernels (any odd ksize <= 25): one thread per cell, 4 cells per thread along x
+// for the Z pass so loads/stores are float4 when the row pitch allows.  HBM/L2 bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int TX = 128;
+
+__global__ void __launch_bounds__(TX) sep_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
+                                                   int rows, int ksize, float factor, Taps taps) {
+    __shared__ float line[TX + NZ_MAX_KERNEL_WIDTH - 1];
+    const int z = blockIdx.y;
+    const int x0 = blockIdx.x * TX;
+    const int r = (ksize - 1) >> 1;
+    const float* row = src + (size_t)z * width;
+    for (int i = threadIdx.x; i < TX + 2 * r; i += TX) line[i] = __ldg(row + clampi(x0 + i - r, 0, width - 1));
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= width) return;
+    float total = 0.0f;
+    for (int k = 0; k < ksize; k++) total = fmaf(line[threadIdx.x + k], taps.k[k], total);
+    dst[(size_t)z * width + x] = total * factor;
+}
+
+__global__ void __launch_bounds__(TX) sep_z_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
+                                                   int rows, int ksize, float factor, Taps taps) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const int r = (ksize - 1) >> 1;
+    float total = 0.0f;
+    for (int k = r; k >= -r; k--) {
+        const int zi = clampi(z + k, 0, rows - 1);
+        total = fmaf(__ldg(src + (size_t)zi * width + x), taps.k[r - k], total);
+    }
+    dst[(size_t)z * width + x] = total * factor;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sobel3_2D (SeparableKernelFilter.ScheduleReduce<RootSumSquaresTiles>, KernelJob.cs:187-215;
+// RootSumSquaresTiles, Filter/Operators/SimpleMutation.cs:148-171), intended semantics:
+//   A = Z{1,2,1}( X{-1,0,1}(src) ),  B = Z{1,0,-1}( X{1,2,1}(src) ),  out = sqrt(A*A + B*B)
+// fused into one 3x3 pass in the exact order of the two separable branches.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TX) sobel2d_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
+                                                     int rows) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const int xl = max(x - 1, 0), xr = min(x + 1, width - 1);
+    float ax[3], bx[3];  // X-pass results of rows z-1, z, z+1
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float* row = src + (size_t)clampi(z + j - 1, 0, rows - 1) * width;
+        const float l = __ldg(row + xl), c = __ldg(row + x), rr = __ldg(row + xr);
+        // total = 0; total = fma(v, K, total) for K = HX {-1,0,1}
+        float ta = fmaf(l, -1.0f, 0.0f);
+        ta = fmaf(c, 0.0f, ta);
+        ta = fmaf(rr, 1.0f, ta);
+        ax[j] = ta * 1.0f;
+        // VX {1,2,1}
+        float tb = fmaf(l, 1.0f, 0.0f);
+        tb = fmaf(c, 2.0f, tb);
+        tb = fmaf(rr, 1.0f, tb);
+        bx[j] = tb * 1.0f;
+    }
+    // Z pass, descending k: taps pair K[0] with z+1, K[1] with z, K[2] with z-1
+    float A = fmaf(ax[2], 1.0f, 0.0f);
+    A = fmaf(ax[1], 2.0f, A);
+    A = fmaf(ax[0], 1.0f, A);
+    float B = fmaf(bx[2], 1.0f, 0.0f);
+    B = fmaf(bx[1], 0.0f, B);
+    B = fmaf(bx[0], -1.0f, B);
+    dst[(size_t)z * width + x] = sqrtf(fmaf(B, B, A * A));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Value erosion: N calls of (X pass, Z pass) with taps {-1,0} == min over the trailing window
+// [x-N..x] x [z-N..z] with clamp at 0 (exact: min is associative/commutative).  Two passes:
+// X window then Z window.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TX) min_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
+                                                   int rows, int n) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const float* row = src + (size_t)z * width;
+    float m = 3.402823466e+38f;
+    for (int k = min(n, x); k >= 0; k--) m = fminf(m, __ldg(row + x - k));
+    dst[(size_t)z * width + x] = m;
+}
+
+__global__ void __launch_bounds__(TX) min_z_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
+                                                   int rows, int n) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    float m = 3.402823466e+38f;
+    for (int k = min(n, z); k >= 0; k--) m = fminf(m, __ldg(src + (size_t)(z - k) * width + x));
+    dst[(size_t)z * width + x] = m;
+}
+
+__global__ void gather_strided_kernel(float* __restrict__ dst, const unsigned char* __restrict__ src, int stride, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = *reinterpret_cast<const float*>(src + i * (size_t)stride);
+}
+
+}  // namespace
+
+int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
+                         const float* kz, float factor, int iterations, float** d_result, cudaStream_t s) {
+    NZ_REQUIRE(d_data && d_tmp, "separable: null device buffer");
+    NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535, "separable: bad grid %d x %d", width, rows);
+    NZ_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= NZ_MAX_KERNEL_WIDTH, "separable: ksize %d must be odd and <= %d",
+               ksize, NZ_MAX_KERNEL_WIDTH);
+    NZ_REQUIRE(iterations >= 0 && kx && kz, "separable: bad iterations/taps");
+    Taps tx, tz;
+    for (int i = 0; i < NZ_MAX_KERNEL_WIDTH; i++) {
+        tx.k[i] = i < ksize ? kx[i] : 0.0f;
+        tz.k[i] = i < ksize ? kz[i] : 0.0f;
+    }
+    dim3 grid(cdiv(width, TX), rows);
+    for (int it = 0; it < iterations; it++) {
+        sep_x_kernel<<<grid, TX, 0, s>>>(d_data, d_tmp, width, rows, ksize, factor, tx);
+        NZ_LAUNCHED();
+        sep_z_kernel<<<grid, TX, 0, s>>>(d_tmp, d_data, width, rows, ksize, factor, tz);
+        NZ_LAUNCHED();
+    }
+    if (d_result) *d_result = d_data;
+    return NZ_OK;
+}
+
+int32_t launch_sobel2d(float* d_data, float* d_tmp, int width, int rows, int iterations, float** d_result,
+                       cudaStream_t s) {
+    NZ_REQUIRE(d_data && d_tmp, "sobel2d: null device buffer");
+    NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "sobel2d: bad arguments");
+    dim3 grid(cdiv(width, TX), rows);
+    float *a = d_data, *b = d_tmp;
+    for (int it = 0; it < iterations; it++) {
+        sobel2d_kernel<<<grid, TX, 0, s>>>(a, b, width, rows);
+        NZ_LAUNCHED();
+        float* t = a; a = b; b = t;
+    }
+    if (d_result) {
+        *d_result = a;
+    } else if (a != d_data) {
+        NZ_CUDA(cudaMemcpyAsync(d_data, a, (size_t)width * rows * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return NZ_OK;
+}
+
+int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int iterations, float** d_result,
+                           cudaStream_t s) {
+    NZ_REQUIRE(d_data && d_tmp, "min_erosion: null device buffer");
+    NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "min_erosion: bad arguments");
+    if (iterations > 0) {
+        dim3 grid(cdiv(width, TX), rows);
+        min_x_kernel<<<grid, TX, 0, s>>>(d_data, d_tmp, width, rows, iterations);
+        NZ_LAUNCHED();
+        min_z_kernel<<<grid, TX, 0, s>>>(d_tmp, d_data, width, rows, iterations);
+        NZ_LAUNCHED();
+    }
+    if (d_result) *d_result = d_data;
+    return NZ_OK;
+}
+
+int32_t launch_gather_strided(float* d_dst, const unsigned char* d_src, int stride_bytes, size_t n, cudaStream_t s) {
+    gather_strided_kernel<<<cdiv((long long)n, 256), 256, 0, s>>>(d_dst, d_src, stride_bytes, n);
+    NZ_LAUNCHED();
+    return NZ_OK;
+}
+
+}  // namespace nz

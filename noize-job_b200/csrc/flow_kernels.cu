@@ -1,0 +1,150 @@
+// flow_kernels.cu — pipe-model flow map (hot loop 3).
+//
+// Replaces FlowMapStage.ScheduleAll (Geologic/Stage/FlowMapStage.cs:124-195) and its jobs:
+//   FillArrayJob                      Geologic/FlowMap/FlowMapComponents.cs:176-202   water := 1e-4
+//   ComputeFlowStep.CalculateCell     FlowMapComponents.cs:20-65   (job FlowMapJob.cs:17-80)
+//   UpdateWaterStep.CalculateCell     FlowMapComponents.cs:81-104  (job FlowMapJob.cs:101-153)
+//   CreateVelocityField.CalculateCell FlowMapComponents.cs:120-139 (job FlowMapJob.cs:168-218)
+//   NormalizeMap.CalculateCell        FlowMapComponents.cs:157-165 (job Filter/NormalizeJob.cs:58-92)
+// Flow fields start at zero (the reference leaves them uninitialised, FlowMapStage.cs:55-62).
+//
+// State per cell: water + 4 outflows (W,E,S,N).  The outflow step reads only the cell's own flows
+// and the 5-point (height+water) stencil, the water step only the cell's own water and the 5-point
+// flow stencil, so both update IN PLACE (the reference's READ/WRITE pairs + copy-backs vanish).
+#include "nz_common.cuh"
+
+namespace nz {
+namespace {
+
+constexpr int TX = 128;
+constexpr float TIMESTEP = 0.2f;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+struct FlowFields {
+    float* water;
+    float* fW;
+    float* fE;
+    float* fS;
+    float* fN;
+};
+
+template <bool FIRST>
+__global__ void __launch_bounds__(TX) flow_step_kernel(const float* __restrict__ height, FlowFields f, int width, int rows) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const size_t i = (size_t)z * width + x;
+    const int xW = max(x - 1, 0), xE = min(x + 1, width - 1);
+    const size_t rS = (size_t)max(z - 1, 0) * width, rN = (size_t)min(z + 1, rows - 1) * width, r0 = (size_t)z * width;
+    // FIRST iteration: water is the fill value everywhere and flows are zero -> nothing to read but height
+    const float w0 = FIRST ? 0.0001f : f.water[i];
+    const float h0 = __ldg(height + i);
+    const float totalHt = w0 + h0;
+    const float dW = totalHt - ((FIRST ? 0.0001f : f.water[r0 + xW]) + __ldg(height + r0 + xW));
+    const float dE = totalHt - ((FIRST ? 0.0001f : f.water[r0 + xE]) + __ldg(height + r0 + xE));
+    const float dS = totalHt - ((FIRST ? 0.0001f : f.water[rS + x]) + __ldg(height + rS + x));
+    const float dN = totalHt - ((FIRST ? 0.0001f : f.water[rN + x]) + __ldg(height + rN + x));
+    const float flW = fmaxf(0.0f, (FIRST ? 0.0f : f.fW[i]) + dW);
+    const float flE = fmaxf(0.0f, (FIRST ? 0.0f : f.fE[i]) + dE);
+    const float flS = fmaxf(0.0f, (FIRST ? 0.0f : f.fS[i]) + dS);
+    const float flN = fmaxf(0.0f, (FIRST ? 0.0f : f.fN[i]) + dN);
+    const float sum_ = (flW + flE) + (flS + flN);  // math.csum(float4)
+    float K = 0.0f;
+    if (sum_ > 0.0f) {
+        K = w0 / (sum_ * TIMESTEP);
+        K = fminf(fmaxf(K, 0.0f), 1.0f);
+    }
+    // sum_ <= 0 means every flow is 0 already (they are clamped at 0), so flow*0 == the reference's explicit 0
+    f.fW[i] = sum_ > 0.0f ? flW * K : 0.0f;
+    f.fE[i] = sum_ > 0.0f ? flE * K : 0.0f;
+    f.fS[i] = sum_ > 0.0f ? flS * K : 0.0f;
+    f.fN[i] = sum_ > 0.0f ? flN * K : 0.0f;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(TX) water_step_kernel(FlowFields f, int width, int rows) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const size_t i = (size_t)z * width + x;
+    const int xW = max(x - 1, 0), xE = min(x + 1, width - 1);
+    const size_t rS = (size_t)max(z - 1, 0) * width, rN = (size_t)min(z + 1, rows - 1) * width, r0 = (size_t)z * width;
+    const float flowOUT = ((f.fW[i] + f.fE[i]) + f.fS[i]) + f.fN[i];
+    float flowIN = 0.0f;
+    flowIN += f.fE[r0 + xW];
+    flowIN += f.fW[r0 + xE];
+    flowIN += f.fN[rS + x];
+    flowIN += f.fS[rN + x];
+    const float ht = fmaf(flowIN - flowOUT, TIMESTEP, FIRST ? 0.0001f : f.water[i]);
+    f.water[i] = fmaxf(0.0f, ht);
+}
+
+__global__ void __launch_bounds__(TX) velocity_norm_kernel(float* __restrict__ out, FlowFields f, int width, int rows,
+                                                           float norm_min, float norm_range) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const size_t i = (size_t)z * width + x;
+    const int xW = max(x - 1, 0), xE = min(x + 1, width - 1);
+    const size_t rS = (size_t)max(z - 1, 0) * width, rN = (size_t)min(z + 1, rows - 1) * width, r0 = (size_t)z * width;
+    const float dl = f.fE[r0 + xW] - f.fW[i];
+    const float dr = f.fE[i] - f.fW[r0 + xE];
+    const float dt = f.fS[rN + x] - f.fN[i];
+    const float db = f.fS[i] - f.fN[rS + x];
+    const float vx = (dl + dr) * 0.5f, vy = (dt + db) * 0.5f;
+    float v = sqrtf(fmaf(vy, vy, vx * vx));
+    if (norm_range < 1e-12f) v = 0.0f;
+    out[i] = (v - norm_min) / norm_range;
+}
+
+// iterations == 0: velocity of an all-zero flow field is 0
+__global__ void __launch_bounds__(TX) fill_norm_zero_kernel(float* __restrict__ out, size_t n, float norm_min,
+                                                            float norm_range) {
+    size_t i = (size_t)blockIdx.x * TX + threadIdx.x;
+    if (i < n) out[i] = (0.0f - norm_min) / norm_range;
+}
+
+}  // namespace
+
+size_t flowmap_scratch_bytes(int width, int rows, int iterations) {
+    (void)iterations;
+    return (size_t)width * rows * sizeof(float) * 5;
+}
+
+int32_t launch_flowmap(float* d_height, void* d_scratch, int width, int rows, int iterations, float norm_min,
+                       float norm_max, float** d_result, cudaStream_t s) {
+    NZ_REQUIRE(d_height, "flowmap: null height buffer");
+    NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "flowmap: bad arguments");
+    const size_t n = (size_t)width * rows;
+    const float norm_range = norm_max - norm_min;  // FlowMapStage.cs:48-51
+    dim3 grid(cdiv(width, TX), rows);
+    if (iterations == 0) {
+        fill_norm_zero_kernel<<<cdiv((long long)n, TX), TX, 0, s>>>(d_height, n, norm_min, norm_range);
+        NZ_LAUNCHED();
+        if (d_result) *d_result = d_height;
+        return NZ_OK;
+    }
+    NZ_REQUIRE(d_scratch, "flowmap: null scratch buffer (need nz_dev_flowmap_scratch_bytes)");
+    float* sc = (float*)d_scratch;
+    FlowFields f = {sc, sc + n, sc + 2 * n, sc + 3 * n, sc + 4 * n};
+    for (int it = 0; it < iterations; it++) {
+        if (it == 0) {
+            flow_step_kernel<true><<<grid, TX, 0, s>>>(d_height, f, width, rows);
+            NZ_LAUNCHED();
+            water_step_kernel<true><<<grid, TX, 0, s>>>(f, width, rows);
+            NZ_LAUNCHED();
+        } else {
+            flow_step_kernel<false><<<grid, TX, 0, s>>>(d_height, f, width, rows);
+            NZ_LAUNCHED();
+            water_step_kernel<false><<<grid, TX, 0, s>>>(f, width, rows);
+            NZ_LAUNCHED();
+        }
+    }
+    velocity_norm_kernel<<<grid, TX, 0, s>>>(d_height, f, width, rows, norm_min, norm_range);
+    NZ_LAUNCHED();
+    if (d_result) *d_result = d_height;
+    return NZ_OK;
+}
+
+}  // namespace nz

@@ -1,0 +1,351 @@
+// noise_kernels.cu — fBm fractal noise evaluator (hot loop 1).
+//
+// Replaces FractalJob<FractalGenerator<*Getter>, WriteTileData> (Noise/Fractal/Fractal.cs:20-138,
+// getters :141-278, delegate table Noise/NoiseStage.cs:26-35).  The basis functions restate
+// Unity.Mathematics.noise (com.unity.mathematics@1.2.1: snoise/cnoise/psrnoise/cellular), i.e. the
+// webgl-noise algorithms, in the canonical evaluation order of oracle/noize_oracle.cpp.
+//
+// Shape of the kernel: FP32-pipe bound (about 2.3k ops per 4-byte store), no memory traffic but
+// the store.  One thread owns NZ_CELLS consecutive-in-block cells (stride blockDim.x along x) so
+// the independent octave chains of several cells interleave (ILP) and every store is a coalesced
+// 128 B line per warp.  All hashing state lives in registers; there is no shared memory.
+#include <math.h>
+#include "nz_common.cuh"
+
+namespace nz {
+namespace {
+
+// ---- Unity.Mathematics.noise common.cs ------------------------------------------------------
+__device__ __forceinline__ float mod289(float x) { return fmaf(-floorf(x * (1.0f / 289.0f)), 289.0f, x); }
+__device__ __forceinline__ float mod7(float x) { return fmaf(-floorf(x * (1.0f / 7.0f)), 7.0f, x); }
+__device__ __forceinline__ float permute(float x) { return mod289(fmaf(34.0f, x, 1.0f) * x); }
+__device__ __forceinline__ float taylorInvSqrt(float r) { return fmaf(-0.85373472095314f, r, 1.79284291400159f); }
+__device__ __forceinline__ float fade(float t) { return t * t * t * fmaf(t, fmaf(t, 6.0f, -15.0f), 10.0f); }
+__device__ __forceinline__ float fracf_(float x) { return x - floorf(x); }
+__device__ __forceinline__ float lerpf_(float a, float b, float t) { return fmaf(t, b - a, a); }
+__device__ __forceinline__ float stepf_(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
+__device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return fmaf(ay, by, ax * bx); }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return fmaf(az, bz, fmaf(ay, by, ax * bx));
+}
+__device__ __forceinline__ float dot4(float ax, float ay, float az, float aw, float bx, float by, float bz, float bw) {
+    return fmaf(aw, bw, fmaf(az, bz, fmaf(ay, by, ax * bx)));
+}
+__device__ __forceinline__ float rectify(float v) { return (1.0f + v) * 0.5f; }
+
+// ---- snoise(float2) ---------------------------------------------------------------------------
+// Same operations as the oracle's snoise2; the only restructuring is exact: the middle corner's
+// inner hash permute(iy + i1y) is one of the two hashes already computed for the outer corners
+// (i1y is 0 or 1), so it is selected instead of recomputed.
+__device__ __forceinline__ float snoise2(float vx, float vy) {
+    const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
+    const float Cz = -0.577350269189626f, Cw = 0.024390243902439f;
+    float s = dot2(vx, vy, Cy, Cy);
+    float ix = floorf(vx + s), iy = floorf(vy + s);
+    float t = dot2(ix, iy, Cx, Cx);
+    float x0x = vx - ix + t, x0y = vy - iy + t;
+    const bool xgty = x0x > x0y;
+    float i1x = xgty ? 1.0f : 0.0f, i1y = xgty ? 0.0f : 1.0f;
+    float x1x = x0x + Cx - i1x, x1y = x0y + Cx - i1y;
+    float x2x = x0x + Cz, x2y = x0y + Cz;
+    ix = mod289(ix);
+    iy = mod289(iy);
+    float py0 = permute(iy), py1 = permute(iy + 1.0f);
+    float p0 = permute(py0 + ix);
+    float p1 = permute((xgty ? py0 : py1) + ix + i1x);
+    float p2 = permute(py1 + ix + 1.0f);
+    float m0 = fmaxf(0.5f - dot2(x0x, x0y, x0x, x0y), 0.0f);
+    float m1 = fmaxf(0.5f - dot2(x1x, x1y, x1x, x1y), 0.0f);
+    float m2 = fmaxf(0.5f - dot2(x2x, x2y, x2x, x2y), 0.0f);
+    m0 = m0 * m0; m0 = m0 * m0;
+    m1 = m1 * m1; m1 = m1 * m1;
+    m2 = m2 * m2; m2 = m2 * m2;
+    float gx0 = fmaf(2.0f, fracf_(p0 * Cw), -1.0f), gx1 = fmaf(2.0f, fracf_(p1 * Cw), -1.0f),
+          gx2 = fmaf(2.0f, fracf_(p2 * Cw), -1.0f);
+    float h0 = fabsf(gx0) - 0.5f, h1 = fabsf(gx1) - 0.5f, h2 = fabsf(gx2) - 0.5f;
+    float a0 = gx0 - floorf(gx0 + 0.5f), a1 = gx1 - floorf(gx1 + 0.5f), a2 = gx2 - floorf(gx2 + 0.5f);
+    m0 = m0 * taylorInvSqrt(fmaf(h0, h0, a0 * a0));
+    m1 = m1 * taylorInvSqrt(fmaf(h1, h1, a1 * a1));
+    m2 = m2 * taylorInvSqrt(fmaf(h2, h2, a2 * a2));
+    float g0 = fmaf(h0, x0y, a0 * x0x);
+    float g1 = fmaf(h1, x1y, a1 * x1x);
+    float g2 = fmaf(h2, x2y, a2 * x2x);
+    return 130.0f * dot3(m0, m1, m2, g0, g1, g2);
+}
+
+// ---- cnoise(float2) ---------------------------------------------------------------------------
+__device__ __forceinline__ float cnoise2(float Px, float Py) {
+    float flx = floorf(Px), fly = floorf(Py);
+    float pfx0 = Px - flx, pfy0 = Py - fly;
+    float pfx1 = pfx0 - 1.0f, pfy1 = pfy0 - 1.0f;
+    float pix0 = mod289(flx), pix1 = mod289(flx + 1.0f);
+    float piy0 = mod289(fly), piy1 = mod289(fly + 1.0f);
+    float hx0 = permute(pix0), hx1 = permute(pix1);
+    float n[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float fx = (k & 1) ? pfx1 : pfx0, fy = (k >> 1) ? pfy1 : pfy0;
+        float i = permute(((k & 1) ? hx1 : hx0) + ((k >> 1) ? piy1 : piy0));
+        float g = fmaf(fracf_(i * (1.0f / 41.0f)), 2.0f, -1.0f);
+        float gy = fabsf(g) - 0.5f;
+        float gx = g - floorf(g + 0.5f);
+        float norm = taylorInvSqrt(dot2(gx, gy, gx, gy));
+        n[k] = dot2(gx * norm, gy * norm, fx, fy);
+    }
+    float fdx = fade(pfx0), fdy = fade(pfy0);
+    return 2.3f * lerpf_(lerpf_(n[0], n[1], fdx), lerpf_(n[2], n[3], fdx), fdy);
+}
+
+// ---- psrnoise(float2, float2 per, float rot) --------------------------------------------------
+__device__ __forceinline__ void rgrad2(float px, float py, float rot, float& gx, float& gy) {
+    float u = fmaf(permute(permute(px) + py), 0.0243902439f, rot);
+    u = fracf_(u) * 6.28318530718f;
+    gx = cosf(u);
+    gy = sinf(u);
+}
+__device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, float pery, float rot) {
+    posy += 0.001f;
+    float ux = fmaf(posy, 0.5f, posx), uy = posy;
+    float i0x = floorf(ux), i0y = floorf(uy);
+    float f0x = ux - i0x, f0y = uy - i0y;
+    const bool c = f0x > f0y;
+    float i1x = c ? 1.0f : 0.0f, i1y = c ? 0.0f : 1.0f;
+    float p0x = fmaf(-i0y, 0.5f, i0x), p0y = i0y;
+    float p1x = p0x + i1x - i1y * 0.5f, p1y = p0y + i1y;
+    float p2x = p0x + 0.5f, p2y = p0y + 1.0f;
+    float d0x = posx - p0x, d0y = posy - p0y;
+    float d1x = posx - p1x, d1y = posy - p1y;
+    float d2x = posx - p2x, d2y = posy - p2y;
+    float xw0 = fmodf(p0x, perx), xw1 = fmodf(p1x, perx), xw2 = fmodf(p2x, perx);
+    float yw0 = fmodf(p0y, pery), yw1 = fmodf(p1y, pery), yw2 = fmodf(p2y, pery);
+    float g0x, g0y, g1x, g1y, g2x, g2y;
+    rgrad2(fmaf(0.5f, yw0, xw0), yw0, rot, g0x, g0y);
+    rgrad2(fmaf(0.5f, yw1, xw1), yw1, rot, g1x, g1y);
+    rgrad2(fmaf(0.5f, yw2, xw2), yw2, rot, g2x, g2y);
+    float w0 = dot2(g0x, g0y, d0x, d0y), w1 = dot2(g1x, g1y, d1x, d1y), w2 = dot2(g2x, g2y, d2x, d2y);
+    float t0 = fmaxf(0.8f - dot2(d0x, d0y, d0x, d0y), 0.0f);
+    float t1 = fmaxf(0.8f - dot2(d1x, d1y, d1x, d1y), 0.0f);
+    float t2 = fmaxf(0.8f - dot2(d2x, d2y, d2x, d2y), 0.0f);
+    t0 = t0 * t0; t0 = t0 * t0;
+    t1 = t1 * t1; t1 = t1 * t1;
+    t2 = t2 * t2; t2 = t2 * t2;
+    return 11.0f * dot3(t0, t1, t2, w0, w1, w2);
+}
+
+// ---- cellular(float2) -> F1*F2 rectified ------------------------------------------------------
+__device__ __forceinline__ float cellular2_rectified(float Px, float Py) {
+    const float K = 0.142857142857f, Ko = 0.428571428571f;
+    float flx = floorf(Px), fly = floorf(Py);
+    float Pix = mod289(flx), Piy = mod289(fly);
+    float Pfx = Px - flx, Pfy = Py - fly;
+    float d[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float oic = (float)(c - 1);
+        const float xo = 0.5f - (float)c;
+        float pxc = permute(Pix + oic);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const float oij = (float)(j - 1), ofj = (float)j - 0.5f;
+            float p = permute(pxc + Piy + oij);
+            float ox = fracf_(p * K) - Ko;
+            float oy = fmaf(mod7(floorf(p * K)), K, -Ko);
+            float dx = Pfx + xo + ox;
+            float dy = Pfy - ofj + oy;
+            d[c][j] = fmaf(dy, dy, dx * dx);
+        }
+    }
+    float d1[3], d2[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float d1a = fminf(d[0][j], d[1][j]);
+        float t = fmaxf(d[0][j], d[1][j]);
+        t = fminf(t, d[2][j]);
+        d1[j] = fminf(d1a, t);
+        d2[j] = fmaxf(d1a, t);
+    }
+    if (!(d1[0] < d1[1])) { float t = d1[0]; d1[0] = d1[1]; d1[1] = t; }
+    if (!(d1[0] < d1[2])) { float t = d1[0]; d1[0] = d1[2]; d1[2] = t; }
+    d1[1] = fminf(d1[1], d2[1]);
+    d1[2] = fminf(d1[2], d2[2]);
+    d1[1] = fminf(d1[1], d1[2]);
+    d1[1] = fminf(d1[1], d2[0]);
+    return rectify(sqrtf(d1[0])) * rectify(sqrtf(d1[1]));
+}
+
+// ---- snoise(float3) ---------------------------------------------------------------------------
+__device__ float snoise3(float vx, float vy, float vz) {
+    const float Cx = 1.0f / 6.0f, Cy = 1.0f / 3.0f;
+    float s = dot3(vx, vy, vz, Cy, Cy, Cy);
+    float i0 = floorf(vx + s), i1_ = floorf(vy + s), i2_ = floorf(vz + s);
+    float t = dot3(i0, i1_, i2_, Cx, Cx, Cx);
+    float x0[3] = {vx - i0 + t, vy - i1_ + t, vz - i2_ + t};
+    float g[3] = {stepf_(x0[1], x0[0]), stepf_(x0[2], x0[1]), stepf_(x0[0], x0[2])};
+    float l[3] = {1.0f - g[0], 1.0f - g[1], 1.0f - g[2]};
+    float i1[3] = {fminf(g[0], l[2]), fminf(g[1], l[0]), fminf(g[2], l[1])};
+    float i2[3] = {fmaxf(g[0], l[2]), fmaxf(g[1], l[0]), fmaxf(g[2], l[1])};
+    float xs[4][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        xs[0][k] = x0[k];
+        xs[1][k] = x0[k] - i1[k] + Cx;
+        xs[2][k] = x0[k] - i2[k] + Cy;
+        xs[3][k] = x0[k] - 0.5f;
+    }
+    float ii[3] = {mod289(i0), mod289(i1_), mod289(i2_)};
+    const float oz[4] = {0.0f, i1[2], i2[2], 1.0f}, oy[4] = {0.0f, i1[1], i2[1], 1.0f}, ox[4] = {0.0f, i1[0], i2[0], 1.0f};
+    const float n_ = 0.142857142857f;
+    const float nsx = n_ * 2.0f - 0.0f, nsy = n_ * 0.5f - 1.0f, nsz = n_ * 1.0f - 0.0f;
+    float m[4], pd[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float p = permute(permute(permute(ii[2] + oz[k]) + ii[1] + oy[k]) + ii[0] + ox[k]);
+        float j = fmaf(-49.0f, floorf(p * nsz * nsz), p);
+        float x_ = floorf(j * nsz);
+        float y_ = floorf(fmaf(-7.0f, x_, j));
+        float X = fmaf(x_, nsx, nsy), Y = fmaf(y_, nsx, nsy);
+        float H = 1.0f - fabsf(X) - fabsf(Y);
+        float sh = -stepf_(H, 0.0f);
+        float sx = fmaf(floorf(X), 2.0f, 1.0f), sy = fmaf(floorf(Y), 2.0f, 1.0f);
+        float Px = fmaf(sx, sh, X), Py = fmaf(sy, sh, Y), Pz = H;
+        float norm = taylorInvSqrt(dot3(Px, Py, Pz, Px, Py, Pz));
+        Px *= norm; Py *= norm; Pz *= norm;
+        float mm = fmaxf(0.6f - dot3(xs[k][0], xs[k][1], xs[k][2], xs[k][0], xs[k][1], xs[k][2]), 0.0f);
+        mm = mm * mm;
+        m[k] = mm * mm;
+        pd[k] = dot3(Px, Py, Pz, xs[k][0], xs[k][1], xs[k][2]);
+    }
+    return 42.0f * dot4(m[0], m[1], m[2], m[3], pd[0], pd[1], pd[2], pd[3]);
+}
+
+// ---- cnoise(float3) ---------------------------------------------------------------------------
+__device__ float cnoise3(float Px, float Py, float Pz) {
+    float P[3] = {Px, Py, Pz};
+    float Pi0[3], Pi1[3], Pf0[3], Pf1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float fl = floorf(P[k]);
+        Pi0[k] = mod289(fl);
+        Pi1[k] = mod289(fl + 1.0f);
+        Pf0[k] = P[k] - fl;
+        Pf1[k] = Pf0[k] - 1.0f;
+    }
+    float n[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float ix = (k & 1) ? Pi1[0] : Pi0[0], iy = (k >> 1) ? Pi1[1] : Pi0[1];
+        float ixy = permute(permute(ix) + iy);
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            float ixyz = permute(ixy + (sl ? Pi1[2] : Pi0[2]));
+            float gx = ixyz * (1.0f / 7.0f);
+            float gy = fracf_(floorf(gx) * (1.0f / 7.0f)) - 0.5f;
+            gx = fracf_(gx);
+            float gz = 0.5f - fabsf(gx) - fabsf(gy);
+            float sz = stepf_(gz, 0.0f);
+            gx = gx - sz * (stepf_(0.0f, gx) - 0.5f);
+            gy = gy - sz * (stepf_(0.0f, gy) - 0.5f);
+            float norm = taylorInvSqrt(dot3(gx, gy, gz, gx, gy, gz));
+            float fx = (k & 1) ? Pf1[0] : Pf0[0], fy = (k >> 1) ? Pf1[1] : Pf0[1], fz = sl ? Pf1[2] : Pf0[2];
+            n[sl][k] = dot3(gx * norm, gy * norm, gz * norm, fx, fy, fz);
+        }
+    }
+    float fdx = fade(Pf0[0]), fdy = fade(Pf0[1]), fdz = fade(Pf0[2]);
+    float nz0 = lerpf_(n[0][0], n[1][0], fdz), nz1 = lerpf_(n[0][1], n[1][1], fdz);
+    float nz2 = lerpf_(n[0][2], n[1][2], fdz), nz3 = lerpf_(n[0][3], n[1][3], fdz);
+    return 2.2f * lerpf_(lerpf_(nz0, nz2, fdy), lerpf_(nz1, nz3, fdy), fdx);
+}
+
+// ---- basis getters, Fractal.cs:141-278 ----------------------------------------------------------
+template <int TYPE>
+__device__ __forceinline__ float basis_value(float x, float z) {
+    if (TYPE == NZ_NOISE_SIN) {
+        float vx = fmaf(0.5f, sinf(x), 0.5f), vz = fmaf(0.5f, sinf(z), 0.5f);
+        return vx * vz;
+    } else if (TYPE == NZ_NOISE_PERLIN) {
+        return rectify(cnoise2(x, z));
+    } else if (TYPE == NZ_NOISE_PERIODIC_PERLIN) {
+        return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.0f));
+    } else if (TYPE == NZ_NOISE_SIMPLEX) {
+        return rectify(snoise2(x, z));
+    } else if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) {
+        return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.62f));
+    } else if (TYPE == NZ_NOISE_CELLULAR) {
+        return cellular2_rectified(x, z);
+    } else {
+        float xz = x + z;
+        float s2 = xz * -0.211324865405187f;
+        float xr = x + s2, zr = z + s2;
+        float yr = xz * -0.577350269189626f;
+        return rectify(TYPE == NZ_NOISE_DOMAIN_ROTATED_PERLIN ? cnoise3(xr, zr, yr) : snoise3(xr, zr, yr));
+    }
+}
+
+// ---- the fBm kernel: FractalGenerator.NoiseValue / Execute, Fractal.cs:114-138 -------------------
+constexpr int NZ_FBM_THREADS = 128;
+
+template <int TYPE, int CELLS>
+__global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__ dst, FractalParams p) {
+    const int r = blockIdx.y;
+    const int xbase = blockIdx.x * (NZ_FBM_THREADS * CELLS) + threadIdx.x;
+    const float zi = ((float)(p.z_first + r) + p.posz) / p.noise_size;
+    float xi[CELLS], t[CELLS];
+#pragma unroll
+    for (int c = 0; c < CELLS; c++) {
+        xi[c] = ((float)(xbase + c * NZ_FBM_THREADS) + p.posx) / p.noise_size;
+        t[c] = 0.0f;
+    }
+    float detune = 0.0f, f = 1.0f, a = p.start_amp;
+    for (int i = 0; i < p.octaves; i++) {
+        const float zV = f * zi;
+#pragma unroll
+        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE>(f * xi[c], zV), t[c]);
+        detune += p.detune_rate;
+        f *= (p.stepdown - detune);
+        a *= p.G;
+    }
+    float* row = dst + (size_t)r * p.width;
+#pragma unroll
+    for (int c = 0; c < CELLS; c++) {
+        const int x = xbase + c * NZ_FBM_THREADS;
+        if (x < p.width) row[x] = t[c] / p.norm;
+    }
+}
+
+template <int TYPE, int CELLS>
+int32_t launch_typed(float* d_dst, const FractalParams& p, cudaStream_t s) {
+    dim3 grid(cdiv(p.width, NZ_FBM_THREADS * CELLS), p.rows);
+    fbm_kernel<TYPE, CELLS><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
+    NZ_LAUNCHED();
+    return NZ_OK;
+}
+
+}  // namespace
+
+int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s) {
+    if (p.rows > 65535) {
+        // gridDim.y limit: split into row chunks
+        FractalParams q = p;
+        for (int r0 = 0; r0 < p.rows; r0 += 32768) {
+            q.rows = p.rows - r0 < 32768 ? p.rows - r0 : 32768;
+            q.z_first = p.z_first + r0;
+            int32_t rc = launch_fractal(d_dst + (size_t)r0 * p.width, noise_type, q, s);
+            if (rc != NZ_OK) return rc;
+        }
+        return NZ_OK;
+    }
+    switch (noise_type) {
+        case NZ_NOISE_SIN: return launch_typed<NZ_NOISE_SIN, 2>(d_dst, p, s);
+        case NZ_NOISE_PERLIN: return launch_typed<NZ_NOISE_PERLIN, 2>(d_dst, p, s);
+        case NZ_NOISE_PERIODIC_PERLIN: return launch_typed<NZ_NOISE_PERIODIC_PERLIN, 1>(d_dst, p, s);
+        case NZ_NOISE_SIMPLEX: return launch_typed<NZ_NOISE_SIMPLEX, 2>(d_dst, p, s);
+        case NZ_NOISE_ROTATED_SIMPLEX: return launch_typed<NZ_NOISE_ROTATED_SIMPLEX, 1>(d_dst, p, s);
+        case NZ_NOISE_CELLULAR: return launch_typed<NZ_NOISE_CELLULAR, 1>(d_dst, p, s);
+        case NZ_NOISE_DOMAIN_ROTATED_PERLIN: return launch_typed<NZ_NOISE_DOMAIN_ROTATED_PERLIN, 1>(d_dst, p, s);
+        case NZ_NOISE_DOMAIN_ROTATED_SIMPLEX: return launch_typed<NZ_NOISE_DOMAIN_ROTATED_SIMPLEX, 1>(d_dst, p, s);
+    }
+    set_error("nz_fractal: noise_type %d out of range", noise_type);
+    return NZ_E_INVALID;
+}
+
+}  // namespace nz

@@ -1,0 +1,78 @@
+// nz_common.cuh — shared declarations of libnoize_b200.so (sm_100a only).
+//
+// Numerics contract: every kernel is compiled with --fmad=false, so a fused multiply-add exists
+// exactly where the source says fmaf()/__fmaf_rn — the same places oracle/noize_oracle.cpp writes
+// fmaf().  Division and sqrt are the IEEE-rounded forms (nvcc defaults -prec-div/-prec-sqrt=true),
+// denormals are kept (-ftz=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/noize_b200.h"
+
+namespace nz {
+
+// ---- error plumbing (thread-local message, integer status) ---------------------------------
+void set_error(const char* fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char* what);
+extern std::atomic<long long> g_launches;
+
+#define NZ_CUDA(call)                                                   \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return ::nz::cuda_fail(_e, #call);       \
+    } while (0)
+
+#define NZ_REQUIRE(cond, ...)                                           \
+    do {                                                                \
+        if (!(cond)) {                                                  \
+            ::nz::set_error(__VA_ARGS__);                               \
+            return NZ_E_INVALID;                                        \
+        }                                                               \
+    } while (0)
+
+// count + check a kernel launch
+#define NZ_LAUNCHED()                                                   \
+    do {                                                                \
+        ::nz::g_launches.fetch_add(1, std::memory_order_relaxed);       \
+        cudaError_t _e = cudaGetLastError();                            \
+        if (_e != cudaSuccess) return ::nz::cuda_fail(_e, "kernel launch"); \
+    } while (0)
+
+struct Taps {
+    float k[NZ_MAX_KERNEL_WIDTH];
+};
+
+// ---- device-layer launchers (one per .cu file) ----------------------------------------------
+struct FractalParams {
+    int width, rows, z_first;
+    int octaves;
+    float posx, posz, noise_size;
+    float start_amp, stepdown, detune_rate;
+    float G;     // exp2f(-hurst), computed on the host with the same libm call the oracle uses
+    float norm;  // CalcFractalNormValue
+};
+int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
+
+int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
+                         const float* kz, float factor, int iterations, float** d_result, cudaStream_t s);
+int32_t launch_sobel2d(float* d_data, float* d_tmp, int width, int rows, int iterations, float** d_result,
+                       cudaStream_t s);
+int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int iterations, float** d_result,
+                           cudaStream_t s);
+size_t flowmap_scratch_bytes(int width, int rows, int iterations);
+int32_t launch_flowmap(float* d_height, void* d_scratch, int width, int rows, int iterations, float norm_min,
+                       float norm_max, float** d_result, cudaStream_t s);
+int32_t launch_mesh(int mesh_type, void* d_vtx, uint32_t* d_idx, int R, int inRes, float tile_height,
+                    float tile_size, const float* d_heights, int h_row_first, int h_rows, int vz_begin, int vz_end,
+                    cudaStream_t s);
+int32_t launch_fma_peak(float* d_sink, int grid, int iters, double* flops, cudaStream_t s);
+int32_t launch_gather_strided(float* d_dst, const unsigned char* d_src, int stride_bytes, size_t n, cudaStream_t s);
+
+// host-side table helpers (tables.cpp part of abi.cu)
+void gauss_table(double sigma, int width, float* out);
+int32_t kernel_filter_table(int filter, float* kx, float* kz, int* ksize, float* factor);
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace nz

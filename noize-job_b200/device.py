@@ -1,0 +1,99 @@
+"""Device layer of the C ABI (nz_dev_*): caller-owned DEVICE buffers on a caller stream.
+
+torch is used only as the device allocator / stream provider: every function takes torch CUDA tensors,
+passes their raw pointers to libnoize_b200.so and returns.  Grids are (rows, width) float32, contiguous.
+Functions that ping-pong return the tensor (one of the two passed in) that holds the result.
+"""
+import ctypes as C
+
+from . import lib as _l
+
+
+def _grid(t, name="grid"):
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous 2-D float32 CUDA tensor")
+    return t
+
+
+def _pick(result_ptr, a, b):
+    return a if result_ptr.value == a.data_ptr() else b
+
+
+def fractal(dst, noise_type, hurst, starting_amplitude=1.0, stepdown=2.0, detune_rate=0.0, octaves=1, xpos=0, zpos=0,
+            noise_size=1000, z_first=0, stream=None):
+    """Rows [z_first, z_first+rows) of the tile at (xpos,zpos); see nz_dev_fractal."""
+    _grid(dst, "dst")
+    rows, width = dst.shape
+    _l.check(_l.load().nz_dev_fractal(dst.data_ptr(), width, rows, z_first, int(noise_type), hurst, starting_amplitude,
+                                      stepdown, detune_rate, octaves, xpos, zpos, noise_size, _l.stream_ptr(stream)))
+    return dst
+
+
+def separable(data, tmp, kx, kz, factor=1.0, iterations=1, stream=None):
+    _grid(data, "data"); _grid(tmp, "tmp")
+    assert data.shape == tmp.shape
+    kx, pkx = _l.fptr(kx)
+    kz, pkz = _l.fptr(kz)
+    res = C.c_void_p()
+    _l.check(_l.load().nz_dev_separable(data.data_ptr(), tmp.data_ptr(), data.shape[1], data.shape[0], kx.size, pkx, pkz,
+                                        factor, iterations, C.byref(res), _l.stream_ptr(stream)))
+    return _pick(res, data, tmp)
+
+
+def kernel_filter(data, tmp, filter_type, iterations=1, stream=None):
+    _grid(data, "data"); _grid(tmp, "tmp")
+    assert data.shape == tmp.shape
+    res = C.c_void_p()
+    _l.check(_l.load().nz_dev_kernel_filter(data.data_ptr(), tmp.data_ptr(), data.shape[1], data.shape[0], int(filter_type),
+                                            iterations, C.byref(res), _l.stream_ptr(stream)))
+    return _pick(res, data, tmp)
+
+
+def min_erosion(data, tmp, iterations=1, stream=None):
+    _grid(data, "data"); _grid(tmp, "tmp")
+    assert data.shape == tmp.shape
+    res = C.c_void_p()
+    _l.check(_l.load().nz_dev_min_erosion(data.data_ptr(), tmp.data_ptr(), data.shape[1], data.shape[0], iterations,
+                                          C.byref(res), _l.stream_ptr(stream)))
+    return _pick(res, data, tmp)
+
+
+def flowmap_scratch_bytes(width, rows, iterations):
+    return int(_l.load().nz_dev_flowmap_scratch_bytes(width, rows, iterations))
+
+
+def flowmap(height, scratch, iterations=5, norm_min=-0.1, norm_max=0.1, stream=None):
+    """`scratch`: a CUDA tensor of at least flowmap_scratch_bytes(...) bytes.  Returns the tensor holding the
+    result: `height`, or a (rows,width) view into `scratch`."""
+    _grid(height, "height")
+    rows, width = height.shape
+    need = flowmap_scratch_bytes(width, rows, iterations)
+    if scratch.numel() * scratch.element_size() < need:
+        raise ValueError(f"flowmap scratch too small: {scratch.numel() * scratch.element_size()} < {need}")
+    res = C.c_void_p()
+    _l.check(_l.load().nz_dev_flowmap(height.data_ptr(), scratch.data_ptr(), width, rows, iterations, norm_min, norm_max,
+                                      C.byref(res), _l.stream_ptr(stream)))
+    if res.value == height.data_ptr():
+        return height
+    import torch
+    off = (res.value - scratch.data_ptr()) // 4
+    return scratch.view(torch.float32).view(-1)[off:off + rows * width].view(rows, width)
+
+
+def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, margin_pix, tile_height, tile_size,
+                   heights, h_row_first=0, vz_begin=0, vz_end=None, stream=None):
+    """`heights` holds rows [h_row_first, h_row_first+heights.shape[0]) of the input grid.  `vertices` /
+    `indices` are CUDA tensors whose first element is vertex row vz_begin / triangle row max(vz_begin,1)."""
+    _grid(heights, "heights")
+    if vz_end is None:
+        vz_end = resolution + 1
+    _l.check(_l.load().nz_dev_heightmap_mesh(int(mesh_type), vertices.data_ptr(), indices.data_ptr(), resolution,
+                                             input_resolution, margin_pix, tile_height, tile_size, heights.data_ptr(),
+                                             h_row_first, heights.shape[0], vz_begin, vz_end, _l.stream_ptr(stream)))
+
+
+def fma_peak(sink, grid, iters, stream=None):
+    flops = C.c_double()
+    _l.check(_l.load().nz_dev_fma_peak(sink.data_ptr(), grid, iters, C.byref(flops), _l.stream_ptr(stream)))
+    return flops.value

@@ -1,0 +1,151 @@
+"""Host layer of the C ABI (nz_*): HOST buffers in, HOST buffers out — the call a reference stage makes.
+
+Each function mirrors one static job delegate of the reference (argument order kept) and mutates the
+numpy array it is given in place, exactly like the Burst jobs mutate their NativeSlice<float>.
+"""
+import ctypes as C
+from contextlib import contextmanager
+
+import numpy as np
+
+from . import lib as _l
+
+
+def version():
+    return _l.load().nz_version().decode()
+
+
+def init(device=0):
+    arr = (C.c_int32 * 1)(device)
+    _l.check(_l.load().nz_init(arr, 1))
+
+
+def kernel_launch_count():
+    return int(_l.load().nz_kernel_launch_count())
+
+
+def last_timing():
+    t = _l.Timing()
+    _l.check(_l.load().nz_last_timing(C.byref(t)))
+    return {"ms_h2d": t.ms_h2d, "ms_kernel": t.ms_kernel, "ms_d2h": t.ms_d2h, "kernel_launches": t.kernel_launches}
+
+
+# ---- host-side stage logic (no GPU needed) ------------------------------------------------------
+def fractal_norm_value(hurst, octaves):
+    """FractalJob.CalcFractalNormValue, Noise/Fractal/Fractal.cs:31-40."""
+    return float(_l.load().nz_fractal_norm_value(hurst, octaves))
+
+
+def limit_width(width):
+    """BlurHelper.limitWidth, Filter/Kernel/Blur/BlurKernels.cs:30-36."""
+    return int(_l.load().nz_limit_width(width))
+
+
+def gauss_kernel(sigma, width):
+    """GaussianKernel.GetKernel, BlurKernels.cs:42-58."""
+    out = np.zeros(32, np.float32)
+    w = C.c_int32()
+    _l.check(_l.load().nz_gauss_kernel(int(sigma), width, out.ctypes.data_as(_l._pf32), C.byref(w)))
+    return out[:w.value].copy()
+
+
+def kernel_filter_table(filter_type):
+    """SeparableKernelFilter.Schedule's table switch, Filter/Kernel/KernelJob.cs:217-292."""
+    kx, kz = np.zeros(9, np.float32), np.zeros(9, np.float32)
+    ks, f = C.c_int32(), C.c_float()
+    _l.check(_l.load().nz_kernel_filter_table(int(filter_type), kx.ctypes.data_as(_l._pf32), kz.ctypes.data_as(_l._pf32),
+                                              C.byref(ks), C.byref(f)))
+    return kx[:ks.value].copy(), kz[:ks.value].copy(), float(f.value)
+
+
+def tile_geometry(tile_resolution, tile_size, margin):
+    """MeshTileGenerator.calcTotalResolution/calcMarginVerts/RequestMesh, Scripts/MeshTileGenerator.cs:166-206."""
+    a, b, c = C.c_int32(), C.c_int32(), C.c_float()
+    _l.check(_l.load().nz_tile_geometry(tile_resolution, tile_size, margin, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, float(c.value)
+
+
+# ---- stage delegates ---------------------------------------------------------------------------
+def fractal(dst, resolution, noise_type, hurst, starting_amplitude, stepdown, detune_rate, octaves, xpos, zpos,
+            noise_size):
+    """FractalJobDelegate, Fractal.cs:76-88."""
+    _l.check(_l.load().nz_fractal(_l.as_slice(dst), resolution, int(noise_type), hurst, starting_amplitude, stepdown,
+                                  detune_rate, octaves, xpos, zpos, noise_size))
+
+
+def kernel_filter(src, tmp, filter_type, resolution, iterations=1):
+    """SeperableKernelFilterDelegate (KernelJob.cs:308-314) x KernelFilterStage.iterations."""
+    _l.check(_l.load().nz_kernel_filter(_l.as_slice(src), _l.as_slice(tmp), int(filter_type), resolution, iterations))
+
+
+def separable(src, tmp, kx, kz, factor, resolution, iterations=1):
+    """SeparableKernelFilter.ScheduleSeries, KernelJob.cs:165-185."""
+    kx, pkx = _l.fptr(kx)
+    kz, pkz = _l.fptr(kz)
+    if kx.size != kz.size:
+        raise ValueError("kx and kz must have the same size")
+    _l.check(_l.load().nz_separable(_l.as_slice(src), _l.as_slice(tmp), kx.size, pkx, pkz, factor, resolution, iterations))
+
+
+def gauss_filter(src, tmp, width, sigma, resolution, iterations=1):
+    """GaussFilter.GaussFilterDelegate, Filter/Kernel/Blur/BlurJob.cs:23-30."""
+    _l.check(_l.load().nz_gauss_filter(_l.as_slice(src), _l.as_slice(tmp), width, int(sigma), resolution, iterations))
+
+
+def smooth_filter(src, tmp, width, resolution, iterations=1):
+    """SmoothFilter.SmoothFilterDelegate, BlurJob.cs:46-52."""
+    _l.check(_l.load().nz_smooth_filter(_l.as_slice(src), _l.as_slice(tmp), width, resolution, iterations))
+
+
+def min_erosion(src, resolution, iterations=1):
+    """ErosionKernelJobDelegate, KernelJob.cs:350."""
+    _l.check(_l.load().nz_min_erosion(_l.as_slice(src), resolution, iterations))
+
+
+def flowmap(height, resolution, iterations=5, norm_min=-0.1, norm_max=0.1):
+    """FlowMapStage.ScheduleAll, Geologic/Stage/FlowMapStage.cs:124-195."""
+    _l.check(_l.load().nz_flowmap(_l.as_slice(height), resolution, iterations, norm_min, norm_max))
+
+
+def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, margin_pix, tile_height, tile_size,
+                   heights):
+    """HeightMapMeshJobScheduleDelegate, Mesh/Job/HeightMapMeshJob.cs:55-65.  `vertices` is a writable
+    ((R+1)^2, 12) float32 array (48-byte Stream0 records), `indices` a writable 6*R^2 uint32 array."""
+    R = resolution
+    if vertices.dtype != np.float32 or vertices.size != (R + 1) * (R + 1) * 12 or not vertices.flags["C_CONTIGUOUS"]:
+        raise ValueError("vertices must be a contiguous float32 array of (R+1)^2 x 12")
+    if indices.dtype != np.uint32 or indices.size != 6 * R * R or not indices.flags["C_CONTIGUOUS"]:
+        raise ValueError("indices must be a contiguous uint32 array of 6*R^2")
+    _l.check(_l.load().nz_heightmap_mesh(int(mesh_type), vertices.ctypes.data, indices.ctypes.data, R, input_resolution,
+                                         margin_pix, tile_height, tile_size, _l.as_slice(heights)))
+
+
+# ---- residency -----------------------------------------------------------------------------------
+def pipeline_begin():
+    _l.check(_l.load().nz_pipeline_begin())
+
+
+def pipeline_end():
+    _l.check(_l.load().nz_pipeline_end())
+
+
+@contextmanager
+def pipeline():
+    """Keep device mirrors resident across chained stage calls; one D2H per dirty slice at exit."""
+    pipeline_begin()
+    try:
+        yield
+    finally:
+        pipeline_end()
+
+
+def flush_to_host(arr):
+    _l.check(_l.load().nz_flush_to_host(arr.ctypes.data))
+
+
+def pin(arr):
+    _l.check(_l.load().nz_pin(arr.ctypes.data, arr.nbytes))
+
+
+def unpin(arr):
+    _l.check(_l.load().nz_unpin(arr.ctypes.data))

@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's Pipeline stage API, bound to the C ABI.
+
+Same names, fields, defaults and error behaviour as the C# classes, so a reference user can read this
+file side by side with the originals (paths relative to xshazwar/noize-job):
+
+  PipelineStage / IStage            Pipeline/Stage/PipelineStage.cs:10-62, Pipeline/Interface.cs:7-45
+  StageIO, GeneratorData, ...       Pipeline/Stage/StageIO.cs:8-11, Pipeline/Stage/StageIOTypes/*.cs
+  PipelineWorkItem                  Pipeline/Stage/PipelineDefinition.cs:18-25
+  NoiseStage                        Noise/NoiseStage.cs:13-61
+  KernelFilterStage                 Filter/KernelFilterStage.cs:13-51
+  StageGaussianBlur/StageSmoothBlur Filter/Kernel/Blur/StageGaussianBlur.cs, StageSmoothBlur.cs
+  FlowMapStage                      Geologic/Stage/FlowMapStage.cs:16-221
+  MeshTileStage                     Mesh/Stage/MeshTileStage.cs:28-62
+  BasePipeline (scheduling chain)   Pipeline/Executable/Pipeline.cs:104-181
+  ErosionFilterStage                NEW: wraps ErosionKernelJob (Filter/Kernel/KernelJob.cs:317-350), which no
+                                    stage binds in the current reference tree ("Value Erosion", README.md:18)
+
+The C# production shim (unity/Interop/NoizeB200.cs) has the same structure with [DllImport] stubs.
+A `NativeSlice<float>` is a 1-D numpy float32 view here (it may be strided).  `JobHandle.Complete()`
+returns when the host buffers hold the results, as the reference's handle does.
+"""
+from collections import deque
+from enum import IntEnum
+
+import numpy as np
+
+from . import host as _h
+
+
+# ---- enums (numeric order == the C# enums == include/noize_b200.h) --------------------------------
+class FractalNoise(IntEnum):           # Noise/NoiseStage.cs:15-24
+    Sin = 0
+    Perlin = 1
+    PeriodicPerlin = 2
+    Simplex = 3
+    RotatedSimplex = 4
+    Cellular = 5
+    DomainRotatedPerlin = 6
+    DomainRotatedSimplex = 7
+
+
+class KernelFilterType(IntEnum):       # Filter/Kernel/KernelJob.cs:79-94
+    Gauss9_S1 = 0
+    Gauss7_S1 = 1
+    Gauss5_S1 = 2
+    Gauss3_S1 = 3
+    Gauss9_S2 = 4
+    Gauss7_S2 = 5
+    Gauss5_S2 = 6
+    Gauss3_S2 = 7
+    Smooth3 = 8
+    Sobel3Horizontal = 9
+    Sobel3Vertical = 10
+    Sobel3_2D = 11
+    Prewitt3Horizontal = 12
+    Prewitt3Vertical = 13
+
+
+class GaussSigma(IntEnum):             # Filter/Kernel/Blur/BlurKernels.cs:8-25
+    s0d50 = 0; s1d00 = 1; s1d50 = 2; s2d00 = 3; s2d50 = 4; s3d00 = 5; s3d50 = 6; s4d00 = 7
+    s4d50 = 8; s5d00 = 9; s5d50 = 10; s6d00 = 11; s6d50 = 12; s7d00 = 13; s7d50 = 14; s8d00 = 15
+
+
+class MeshType(IntEnum):               # Mesh/Stage/MeshTileStage.cs:22-25
+    SquareGridHeightMap = 0
+    OvershootSquareGridHeightMap = 1
+
+
+# ---- job handle -------------------------------------------------------------------------------------
+class JobHandle:
+    """Completion token of scheduled GPU work.  Complete() brings every deferred result back to host."""
+
+    def __init__(self, pipeline_scope=None):
+        self._scope = pipeline_scope
+        self.IsCompleted = pipeline_scope is None
+
+    def Complete(self):
+        if not self.IsCompleted:
+            self._scope.close()
+            self.IsCompleted = True
+
+
+class _ResidencyScope:
+    """One nz_pipeline_begin/nz_pipeline_end bracket shared by the stages of a scheduled chain."""
+
+    def __init__(self):
+        _h.pipeline_begin()
+        self.open = True
+
+    def close(self):
+        if self.open:
+            self.open = False
+            _h.pipeline_end()
+
+
+# ---- stage IO ---------------------------------------------------------------------------------------
+class StageIO:
+    def __init__(self, uuid="", data=None):
+        self.uuid = uuid
+        self.data = data          # NativeSlice<float>: 1-D float32 numpy view
+
+
+class GeneratorData(StageIO):
+    def __init__(self, uuid="", data=None, resolution=512, xpos=0, zpos=0):
+        super().__init__(uuid, data)
+        self.resolution, self.xpos, self.zpos = resolution, xpos, zpos
+
+
+class Mesh:
+    """Stand-in for UnityEngine.Mesh + Mesh.MeshData: the two buffers PositionStream32.Setup declares
+    (Mesh/Streams/PositionStream.cs:90-123) and the bounds HeightMapMeshJob assigns."""
+
+    def __init__(self):
+        self.vertices = None      # ((R+1)^2, 12) float32: pos3, normal3, tangent4, uv2
+        self.indices = None       # 6*R^2 uint32
+        self.bounds = None        # (center xyz, size xyz)
+
+
+class MeshStageData(StageIO):
+    def __init__(self, uuid="", data=None, resolution=512, inputResolution=512, marginPix=5, tileSize=512.0,
+                 tileHeight=512.0, xpos=0, zpos=0, mesh=None):
+        super().__init__(uuid, data)
+        self.resolution, self.inputResolution, self.marginPix = resolution, inputResolution, marginPix
+        self.tileSize, self.tileHeight, self.xpos, self.zpos, self.mesh = tileSize, tileHeight, xpos, zpos, mesh
+
+
+class PipelineWorkItem:
+    def __init__(self, data, completeAction=None, scheduledAction=None, dependency=None, stageManager=None):
+        self.data, self.completeAction, self.scheduledAction = data, completeAction, scheduledAction
+        self.dependency, self.stageManager = dependency, stageManager
+
+
+# ---- stage base -------------------------------------------------------------------------------------
+class PipelineStage:
+    def __init__(self):
+        self.jobHandle = None
+        self.OnStageScheduledAction = None
+        self.arraysInitialized = False
+        self.dataLength = 0
+
+    def ResizeNativeContainers(self, size):
+        pass
+
+    def IsSchedulable(self, job):
+        return True
+
+    def CheckRequirements(self, T, requirements):
+        if isinstance(requirements.data, T):
+            n = requirements.data.data.size
+            if n != self.dataLength:
+                self.dataLength = n
+                self.ResizeNativeContainers(n)
+        else:
+            raise Exception(f"Unhandled stageio {type(requirements.data).__name__}")
+
+    def Schedule(self, requirements, dependency):
+        pass
+
+    def ReceiveHandledInput(self, requirements, dependency):
+        self.Schedule(requirements, dependency)
+        self.TransformData(requirements)
+        self.OnStageScheduled(requirements, self.jobHandle)
+
+    def Destroy(self):
+        self.OnDestroy()
+
+    def TransformData(self, data):
+        pass
+
+    def OnStageScheduled(self, requirements, dependency):
+        if self.OnStageScheduledAction is not None:
+            self.OnStageScheduledAction(requirements, self.jobHandle)
+
+    def OnStageComplete(self):
+        pass
+
+    def OnDestroy(self):
+        pass
+
+
+def _chain(dependency):
+    """GPU stages of one chain share the upstream handle's residency scope (or open a new one)."""
+    if isinstance(dependency, JobHandle) and not dependency.IsCompleted:
+        return dependency
+    return JobHandle(_ResidencyScope())
+
+
+class NoiseStage(PipelineStage):
+    def __init__(self, noiseType=FractalNoise.Sin, hurst=0.0, startingAmplitude=1.0, octaves=1, stepdown=2.0,
+                 detuneRate=0.0, noiseSize=1000):
+        super().__init__()
+        self.noiseType, self.hurst, self.startingAmplitude = noiseType, hurst, startingAmplitude
+        self.octaves, self.stepdown, self.detuneRate, self.noiseSize = octaves, stepdown, detuneRate, noiseSize
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.fractal(d.data, d.resolution, self.noiseType, self.hurst, self.startingAmplitude, self.stepdown,
+                   self.detuneRate, self.octaves, d.xpos, d.zpos, self.noiseSize)
+
+
+class KernelFilterStage(PipelineStage):
+    def __init__(self, filter=KernelFilterType.Gauss9_S1, iterations=1):
+        super().__init__()
+        self.filter, self.iterations = filter, iterations
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        # the reference schedules `iterations` dependent jobs; the GPU stage issues ONE fused call
+        _h.kernel_filter(d.data, None, self.filter, d.resolution, self.iterations)
+
+
+class StageGaussianBlur(PipelineStage):
+    def __init__(self, iterations=1, sigma=GaussSigma.s0d50, width=3):
+        super().__init__()
+        self.iterations, self.sigma, self.width = iterations, sigma, width
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.gauss_filter(d.data, None, self.width, self.sigma, d.resolution, self.iterations)
+
+
+class StageSmoothBlur(PipelineStage):
+    def __init__(self, iterations=1, width=1):
+        super().__init__()
+        self.iterations, self.width = iterations, width
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.smooth_filter(d.data, None, self.width, d.resolution, self.iterations)
+
+
+class ErosionFilterStage(PipelineStage):
+    def __init__(self, iterations=5):
+        super().__init__()
+        self.iterations = iterations
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.min_erosion(d.data, d.resolution, self.iterations)
+
+
+class FlowMapStage(PipelineStage):
+    def __init__(self, iterations=5, normMin=-0.1, normMax=0.1):
+        super().__init__()
+        self.iterations, self.normMin, self.normMax = iterations, normMin, normMax
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.flowmap(d.data, d.resolution, self.iterations, self.normMin, self.normMax)
+
+
+class MeshTileStage(PipelineStage):
+    def __init__(self, meshType=MeshType.SquareGridHeightMap):
+        super().__init__()
+        self.meshType = meshType
+        self.currentMesh = None
+
+    def Schedule(self, requirements, dependency):
+        d = requirements.data
+        if not isinstance(d, MeshStageData):
+            raise Exception(f"Unhandled stageio {type(d).__name__}")
+        self.currentMesh = d.mesh if d.mesh is not None else Mesh()
+        d.mesh = self.currentMesh
+        R = d.resolution
+        # Mesh.AllocateWritableMeshData(1) + PositionStream32.Setup
+        self.currentMesh.vertices = np.empty(((R + 1) * (R + 1), 12), np.float32)
+        self.currentMesh.indices = np.empty(6 * R * R, np.uint32)
+        self.currentMesh.bounds = ((0.5 * d.tileSize, 0.5 * d.tileHeight, 0.5 * d.tileSize),
+                                   (d.tileSize, d.tileHeight, d.tileSize))
+        self.jobHandle = _chain(dependency)
+        _h.heightmap_mesh(self.meshType, self.currentMesh.vertices, self.currentMesh.indices, R, d.inputResolution,
+                          d.marginPix, d.tileHeight, d.tileSize, d.data)
+
+
+# ---- pipeline executor (the scheduling chain of BasePipeline) ------------------------------------------
+class BasePipeline:
+    """Queue + stage chaining of Pipeline/Executable/Pipeline.cs: stage i's OnStageScheduledAction feeds
+    stage i+1's ReceiveHandledInput with the JobHandle as dependency (:130-151); Update() schedules the
+    next queued item (:154-158,216-230), LateUpdate() completes it and fires completeAction (:160-181)."""
+
+    def __init__(self, stages, alias="pipeline"):
+        if not stages:
+            raise Exception("No stages in pipeline")
+        self.alias = alias
+        self.stage_instances = list(stages)
+        self.queue = deque()
+        self.pipelineRunning = False
+        self.pipelineQueued = False
+        self.pipelineHandle = None
+        self.activeItem = None
+        for i, st in enumerate(self.stage_instances):
+            if i + 1 < len(self.stage_instances):
+                st.OnStageScheduledAction = self.stage_instances[i + 1].ReceiveHandledInput
+            else:
+                st.OnStageScheduledAction = self.OnPipelineFullyScheduled
+
+    def Enqueue(self, input, scheduleAction=None, completeAction=None, dependency=None):
+        self.queue.append(PipelineWorkItem(input, completeAction, scheduleAction, dependency))
+
+    def Schedule(self, workItem):
+        if self.pipelineRunning:
+            raise Exception("Pipeline already running")
+        self.activeItem = workItem
+        self.pipelineQueued = True
+        self.stage_instances[0].ReceiveHandledInput(workItem, workItem.dependency)
+
+    def OnPipelineFullyScheduled(self, requirements, dependency):
+        self.pipelineHandle = dependency
+        self.pipelineQueued = False
+        self.pipelineRunning = True
+        if requirements.scheduledAction is not None:
+            requirements.scheduledAction(requirements.data, dependency)
+
+    def Update(self):
+        if not self.pipelineRunning and not self.pipelineQueued and self.queue:
+            self.Schedule(self.queue.popleft())
+
+    def LateUpdate(self):
+        if self.pipelineRunning:
+            self.pipelineHandle.Complete()
+            self.pipelineRunning = False
+            for st in self.stage_instances:
+                st.OnStageComplete()
+            item, self.activeItem = self.activeItem, None
+            if item.completeAction is not None:
+                item.completeAction(item.data)
+
+    def Run(self, input, **kw):
+        """Convenience: Enqueue + pump Update/LateUpdate once (what the editor window does per frame)."""
+        self.Enqueue(input, **kw)
+        self.Update()
+        self.LateUpdate()
+        return input
+
+    def Destroy(self):
+        for st in self.stage_instances:
+            st.Destroy()

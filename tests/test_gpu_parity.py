@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances: noise <= 1e-6 abs, separable filter / flow map <= 1e-6 abs on the
+normalised output, value erosion bit-exact, mesh indices bit-exact, vertices/normals <= 1e-5 abs.
+Band / tiling invariance is bit-exact (same kernels, different window).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_NOISE = 1e-6
+TOL_FILTER = 1e-6
+TOL_FLOW = 1e-6
+TOL_MESH = 1e-5
+
+C1 = dict(hurst=0.4, starting_amplitude=1.0, stepdown=2.0, detune_rate=0.0, octaves=13, noise_size=1700)
+
+
+def rand_grid(n, m=None, seed=20221018):
+    return np.random.default_rng(seed).random((n, m or n), dtype=np.float32)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def gpu_fractal(nz, res, noise_type, xpos=0, zpos=0, **kw):
+    p = dict(C1)
+    p.update(kw)
+    out = np.full(res * res, np.nan, np.float32)
+    nz.host.fractal(out, res, noise_type, p["hurst"], p["starting_amplitude"], p["stepdown"], p["detune_rate"],
+                    p["octaves"], xpos, zpos, p["noise_size"])
+    return out.reshape(res, res)
+
+
+def ref_fractal(oracle, res, noise_type, xpos=0, zpos=0, **kw):
+    p = dict(C1)
+    p.update(kw)
+    return oracle.fractal(res, res, noise_type, p["hurst"], p["starting_amplitude"], p["stepdown"], p["detune_rate"],
+                          p["octaves"], xpos, zpos, p["noise_size"])
+
+
+# ---------------------------------------------------------------------------------------------
+# noise
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pos", [(0, 0), (0, 424)])
+def test_c1_simplex_fbm(nz, oracle, pos):
+    got = gpu_fractal(nz, 256, 3, *pos)
+    ref = ref_fractal(oracle, 256, 3, *pos)
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= TOL_NOISE
+
+
+@pytest.mark.parametrize("noise_type", range(8))
+def test_every_basis_matches_oracle(nz, oracle, noise_type):
+    got = gpu_fractal(nz, 192, noise_type, 1000, 3000)
+    ref = ref_fractal(oracle, 192, noise_type, 1000, 3000)
+    assert np.abs(got - ref).max() <= TOL_NOISE
+
+
+@pytest.mark.parametrize("noise_type", [3, 5, 4])
+def test_noise_far_from_origin_c5_coordinates(nz, oracle, noise_type):
+    # the last 160 rows/cols of the 16384^2 grid: lattice coordinates up to 4096*16384/1700
+    got = gpu_fractal(nz, 160, noise_type, 16384 - 160, 16384 - 160)
+    ref = ref_fractal(oracle, 160, noise_type, 16384 - 160, 16384 - 160)
+    assert np.abs(got - ref).max() <= TOL_NOISE
+
+
+def test_noise_parameters_detune_amplitude_odd_sizes(nz, oracle):
+    for res, kw in ((37, dict(detune_rate=0.03, stepdown=2.2, starting_amplitude=3.0, octaves=24, hurst=1.3)),
+                    (8, dict(octaves=1, noise_size=5)), (301, dict(detune_rate=-0.05, stepdown=1.8, octaves=7))):
+        got = gpu_fractal(nz, res, 3, 17, 90, **kw)
+        ref = ref_fractal(oracle, res, 3, 17, 90, **kw)
+        assert np.abs(got - ref).max() <= TOL_NOISE * max(1.0, kw.get("starting_amplitude", 1.0))
+
+
+def test_noise_band_rows_equal_full_tile_bitwise(nz, torch_cuda):
+    torch = torch_cuda
+    full = torch.empty(300, 300, device="cuda")
+    nz.device.fractal(full, 3, 0.4, octaves=13, noise_size=1700, xpos=5, zpos=9)
+    band = torch.empty(77, 300, device="cuda")
+    nz.device.fractal(band, 3, 0.4, octaves=13, noise_size=1700, xpos=5, zpos=9, z_first=111)
+    torch.cuda.synchronize()
+    assert torch.equal(full[111:188], band)
+
+
+def test_strided_native_slice(nz, oracle):
+    # one float channel of an RGBAFloat texture (Scripts/Editor/VisualizePipeline.cs:141): stride 16 B
+    res = 64
+    tex = np.full((res * res, 4), 7.0, np.float32)
+    nz.host.fractal(tex[:, 2], res, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 0, 1700)
+    ref = ref_fractal(oracle, res, 3)
+    assert np.abs(tex[:, 2].reshape(res, res) - ref).max() <= TOL_NOISE
+    assert (tex[:, [0, 1, 3]] == 7.0).all()
+    nz.host.kernel_filter(tex[:, 2], None, 2, res, 2)
+    assert np.abs(tex[:, 2].reshape(res, res) - oracle.kernel_filter(ref, 2, 2)).max() <= 2 * TOL_FILTER
+    assert (tex[:, [0, 1, 3]] == 7.0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# separable filters
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ftype", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13])
+def test_kernel_filter_types(nz, oracle, ftype):
+    a = rand_grid(200)
+    got = a.copy().ravel()
+    nz.host.kernel_filter(got, None, ftype, 200, 2)
+    ref = oracle.kernel_filter(a, ftype, 2)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(got.reshape(200, 200) - ref).max() <= TOL_FILTER * scale
+
+
+@pytest.mark.parametrize("res", [1024, 257, 5, 2])
+def test_gauss5_x17(nz, oracle, res):
+    a = rand_grid(res)
+    got = a.copy().ravel()
+    nz.host.kernel_filter(got, None, 2, res, 17)
+    ref = oracle.kernel_filter(a, 2, 17)
+    assert np.abs(got.reshape(res, res) - ref).max() <= TOL_FILTER
+
+
+def test_gauss_and_smooth_blur_stages(nz, oracle):
+    a = rand_grid(150)
+    for width, sigma in ((3, 0), (7, 3), (25, 15), (12, 5)):
+        got = a.copy().ravel()
+        nz.host.gauss_filter(got, None, width, sigma, 150, 2)
+        assert np.abs(got.reshape(150, 150) - oracle.gauss_filter(a, width, sigma, 2)).max() <= TOL_FILTER
+    for width in (3, 9, 25):
+        got = a.copy().ravel()
+        nz.host.smooth_filter(got, None, width, 150, 3)
+        assert np.abs(got.reshape(150, 150) - oracle.smooth_filter(a, width, 3)).max() <= TOL_FILTER
+
+
+def test_sobel3_2d(nz, oracle):
+    a = rand_grid(180)
+    for iters in (1, 2):
+        got = a.copy().ravel()
+        nz.host.kernel_filter(got, None, 11, 180, iters)
+        ref = oracle.kernel_filter(a, 11, iters)
+        assert np.abs(got.reshape(180, 180) - ref).max() <= 1e-6 * max(1.0, ref.max())
+
+
+def test_rectangular_window_equals_full_interior_bitwise(nz, torch_cuda):
+    """A row band with T*r ghost rows reproduces the full-grid result on its owned rows (what the
+    multi-GPU band path relies on)."""
+    torch = torch_cuda
+    n, iters, r = 384, 6, 2
+    a = torch.from_numpy(rand_grid(n)).cuda()
+    full = nz.device.kernel_filter(a.clone(), torch.empty_like(a), 2, iters).clone()
+    z0, z1, h = 100, 260, iters * r
+    win = a[z0 - h:z1 + h].clone()
+    out = nz.device.kernel_filter(win, torch.empty_like(win), 2, iters)
+    torch.cuda.synchronize()
+    assert torch.equal(out[h:h + (z1 - z0)], full[z0:z1])
+    # top band: global clamp at z=0 must be honoured
+    win = a[0:z1 + h].clone()
+    out = nz.device.kernel_filter(win, torch.empty_like(win), 2, iters)
+    assert torch.equal(out[0:z1], full[0:z1])
+
+
+# ---------------------------------------------------------------------------------------------
+# value erosion
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("res,iters", [(512, 5), (100, 1), (33, 12), (3, 5), (1, 1)])
+def test_min_erosion_bit_exact(nz, oracle, res, iters):
+    a = rand_grid(res)
+    got = a.copy().ravel()
+    nz.host.min_erosion(got, res, iters)
+    assert np.array_equal(got.reshape(res, res), oracle.min_erosion(a, iters))
+
+
+# ---------------------------------------------------------------------------------------------
+# flow map
+# ---------------------------------------------------------------------------------------------
+def _terrain(oracle, res):
+    return oracle.kernel_filter(oracle.fractal(res, res, 3, 0.4, octaves=13, noise_size=1700), 2, 17)
+
+
+@pytest.mark.parametrize("res,iters", [(512, 5), (130, 1), (64, 16), (2, 3)])
+def test_flowmap_on_terrain(nz, oracle, res, iters):
+    h = _terrain(oracle, res)
+    got = h.copy().ravel()
+    nz.host.flowmap(got, res, iters, 0.0, 0.005)
+    ref = oracle.flowmap(h, iters, 0.0, 0.005)
+    assert np.abs(got.reshape(res, res) - ref).max() <= TOL_FLOW * max(1.0, np.abs(ref).max())
+
+
+def test_flowmap_default_norm_and_random_field(nz, oracle):
+    a = rand_grid(256)
+    got = a.copy().ravel()
+    nz.host.flowmap(got, 256, 5, -0.1, 0.1)
+    ref = oracle.flowmap(a, 5, -0.1, 0.1)
+    assert np.abs(got.reshape(256, 256) - ref).max() <= TOL_FLOW * max(1.0, np.abs(ref).max())
+    got = a.copy().ravel()
+    nz.host.flowmap(got, 256, 0, -0.1, 0.1)
+    assert np.array_equal(got.reshape(256, 256), oracle.flowmap(a, 0, -0.1, 0.1))
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mesh_type", [0, 1])
+@pytest.mark.parametrize("R,in_res", [(1016, 1024), (200, 208), (129, 131), (7, 16)])
+def test_mesh(nz, oracle, mesh_type, R, in_res):
+    h = rand_grid(in_res)
+    vtx = np.zeros(((R + 1) ** 2, 12), np.float32)
+    idx = np.zeros(6 * R * R, np.uint32)
+    T = R * (500.0 / 256.0)
+    nz.host.heightmap_mesh(mesh_type, vtx, idx, R, in_res, 4, 2000.0, T, h.ravel())
+    rv, ri = oracle.heightmap_mesh(mesh_type, h, R, 4, 2000.0, T)
+    assert np.array_equal(idx, ri)
+    assert np.abs(vtx[:, 0:3] - rv[:, 0:3]).max() <= TOL_MESH * 2000.0
+    assert np.abs(vtx[:, 3:10] - rv[:, 3:10]).max() <= TOL_MESH
+    assert np.abs(vtx[:, 10:12] - rv[:, 10:12]).max() <= TOL_MESH
+
+
+def test_mesh_row_bands_equal_full_mesh_bitwise(nz, oracle, torch_cuda):
+    torch = torch_cuda
+    R, in_res, off = 300, 308, 4
+    h = torch.from_numpy(rand_grid(in_res)).cuda()
+    vfull = torch.zeros((R + 1) ** 2, 12, device="cuda")
+    ifull = torch.zeros(6 * R * R, dtype=torch.int32, device="cuda")
+    nz.device.heightmap_mesh(1, vfull, ifull, R, in_res, 4, 2000.0, 600.0, h)
+    for vz0, vz1 in ((0, 90), (90, 222), (222, R + 1)):
+        hr0, hr1 = max(vz0 - 1 + off, 0), min(vz1 + 1 + off, in_res)
+        v = torch.zeros((vz1 - vz0) * (R + 1), 12, device="cuda")
+        t0 = max(vz0, 1)
+        i = torch.zeros(6 * R * (vz1 - t0), dtype=torch.int32, device="cuda")
+        nz.device.heightmap_mesh(1, v, i, R, in_res, 4, 2000.0, 600.0, h[hr0:hr1].contiguous(), h_row_first=hr0,
+                                 vz_begin=vz0, vz_end=vz1)
+        torch.cuda.synchronize()
+        assert torch.equal(v, vfull[vz0 * (R + 1):vz1 * (R + 1)])
+        assert torch.equal(i, ifull[6 * R * (t0 - 1):6 * R * (vz1 - 1)])
+
+
+# ---------------------------------------------------------------------------------------------
+# the stage API and full chains (BASELINE configs C2, C3 at test size, C4 tile)
+# ---------------------------------------------------------------------------------------------
+def test_c2_chain_through_stage_api(nz, oracle):
+    res, R = 1024, 1016
+    data = np.zeros(res * res, np.float32)
+    chain = nz.BasePipeline([
+        nz.NoiseStage(nz.FractalNoise.Simplex, hurst=0.4, octaves=13, noiseSize=1700),
+        nz.KernelFilterStage(nz.KernelFilterType.Gauss5_S1, iterations=17),
+        nz.FlowMapStage(iterations=5, normMin=0.0, normMax=0.005),
+        nz.ErosionFilterStage(iterations=5),
+    ])
+    done = []
+    chain.Run(nz.GeneratorData("c2", data, res, 0, 0), completeAction=done.append)
+    assert len(done) == 1
+    mesh_data = nz.MeshStageData("c2", data, R, res, 4, 1984.375, 2000.0)
+    nz.BasePipeline([nz.MeshTileStage(nz.MeshType.OvershootSquareGridHeightMap)]).Run(mesh_data)
+
+    ref = oracle.fractal(res, res, 3, 0.4, octaves=13, noise_size=1700)
+    ref = oracle.kernel_filter(ref, 2, 17)
+    ref = oracle.flowmap(ref, 5, 0.0, 0.005)
+    ref = oracle.min_erosion(ref, 5)
+    got = data.reshape(res, res)
+    # the flow map divides by 0.005: noise-level differences of 1e-7 are amplified; compare at flow tolerance
+    assert np.abs(got - ref).max() <= 5e-5 * max(1.0, np.abs(ref).max())
+    rv, ri = oracle.heightmap_mesh(1, got, R, 4, 2000.0, 1984.375)
+    assert np.array_equal(mesh_data.mesh.indices, ri)
+    assert np.abs(mesh_data.mesh.vertices - rv).max() <= TOL_MESH * 2000.0
+    assert np.abs(mesh_data.mesh.vertices[:, 3:] - rv[:, 3:]).max() <= TOL_MESH
+
+
+def test_c3_cellular_chain_reduced_size(nz, oracle):
+    res = 512
+    data = np.zeros(res * res, np.float32)
+    with nz.host.pipeline():
+        nz.host.fractal(data, res, 5, 0.4, 1.0, 2.0, 0.0, 13, 2048, 1024, 1700)
+        nz.host.kernel_filter(data, None, 2, res, 17)
+    ref = oracle.kernel_filter(oracle.fractal(res, res, 5, 0.4, octaves=13, xpos=2048, zpos=1024, noise_size=1700), 2, 17)
+    assert np.abs(data.reshape(res, res) - ref).max() <= TOL_NOISE
+
+
+def test_c4_tile_rotated_simplex_gauss3_sobel(nz, oracle):
+    res, tx, tz = 256, 3, 7
+    data = np.zeros(res * res, np.float32)
+    with nz.host.pipeline():
+        nz.host.fractal(data, res, 4, 0.4, 1.0, 2.0, 0.0, 13, 1000 * tx, 1000 * tz, 1700)
+        nz.host.kernel_filter(data, None, 3, res, 3)
+        nz.host.flush_to_host(data)
+        blurred = data.copy()
+        nz.host.kernel_filter(data, None, 11, res, 1)
+    ref_b = oracle.kernel_filter(oracle.fractal(res, res, 4, 0.4, octaves=13, xpos=1000 * tx, zpos=1000 * tz, noise_size=1700), 3, 3)
+    assert np.abs(blurred.reshape(res, res) - ref_b).max() <= 2e-6
+    assert np.abs(data.reshape(res, res) - oracle.kernel_filter(blurred.reshape(res, res), 11, 1)).max() <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour of the boundary
+# ---------------------------------------------------------------------------------------------
+def test_errors_are_status_codes_not_crashes(nz):
+    with pytest.raises(nz.NzError) as e:
+        nz.host.fractal(np.zeros(10, np.float32), 4, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 0, 1700)
+    assert e.value.code == nz.lib.NZ_E_INVALID and "length" in str(e.value)
+    with pytest.raises(nz.NzError):
+        nz.host.fractal(np.zeros(16, np.float32), 4, 99, 0.4, 1.0, 2.0, 0.0, 13, 0, 0, 1700)
+    with pytest.raises(nz.NzError):
+        nz.host.kernel_filter(np.zeros(16, np.float32), None, 77, 4, 1)
+    with pytest.raises(nz.NzError):
+        nz.host.separable(np.zeros(16, np.float32), None, np.ones(4, np.float32), np.ones(4, np.float32), 1.0, 4, 1)
+    with pytest.raises(nz.NzError):
+        nz.host.heightmap_mesh(0, np.zeros((17 * 17, 12), np.float32), np.zeros(6 * 256, np.uint32), 16, 16, 0, 1.0, 1.0,
+                               np.zeros(256, np.float32))
+    with pytest.raises(nz.NzError) as e:
+        nz.host.pipeline_end()
+    assert e.value.code == nz.lib.NZ_E_STATE
+    with pytest.raises(Exception, match="Unhandled stageio"):
+        nz.NoiseStage().Schedule(nz.PipelineWorkItem(nz.MeshStageData(data=np.zeros(4, np.float32))), None)
+
+
+def test_kernels_actually_launch(nz):
+    before = nz.host.kernel_launch_count()
+    a = np.zeros(64 * 64, np.float32)
+    nz.host.fractal(a, 64, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 0, 1700)
+    assert nz.host.kernel_launch_count() == before + 1
+    t = nz.host.last_timing()
+    assert t["kernel_launches"] == 1 and t["ms_kernel"] > 0
