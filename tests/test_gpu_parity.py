@@ -204,7 +204,7 @@ def test_flowmap_default_norm_and_random_field(nz, oracle):
 # mesh
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mesh_type", [0, 1])
-@pytest.mark.parametrize("R,in_res", [(1016, 1024), (200, 208), (129, 131), (7, 16)])
+@pytest.mark.parametrize("R,in_res", [(1016, 1024), (200, 208), (129, 133), (7, 16)])
 def test_mesh(nz, oracle, mesh_type, R, in_res):
     h = rand_grid(in_res)
     vtx = np.zeros(((R + 1) ** 2, 12), np.float32)
