@@ -130,6 +130,8 @@ int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int k
     NZ_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= NZ_MAX_KERNEL_WIDTH, "separable: ksize %d must be odd and <= %d",
                ksize, NZ_MAX_KERNEL_WIDTH);
     NZ_REQUIRE(iterations >= 0 && kx && kz, "separable: bad iterations/taps");
+    if (separable_fused_supported(ksize) && iterations > 0)
+        return launch_separable_fused(d_data, d_tmp, width, rows, ksize, kx, kz, factor, iterations, d_result, s);
     Taps tx, tz;
     for (int i = 0; i < NZ_MAX_KERNEL_WIDTH; i++) {
         tx.k[i] = i < ksize ? kx[i] : 0.0f;
