@@ -4,6 +4,7 @@ Each function mirrors one static job delegate of the reference (argument order k
 numpy array it is given in place, exactly like the Burst jobs mutate their NativeSlice<float>.
 """
 import ctypes as C
+import threading
 from contextlib import contextmanager
 
 import numpy as np
@@ -121,12 +122,25 @@ def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, m
 
 
 # ---- residency -----------------------------------------------------------------------------------
+_scope = threading.local()
+
+
 def pipeline_begin():
-    _l.check(_l.load().nz_pipeline_begin())
+    """Open a residency scope on this thread.  Scopes nest: only the outermost one talks to the library, so a
+    caller can keep tiles resident across several pipelines (e.g. the generator pipeline and the mesh pipeline)."""
+    depth = getattr(_scope, "depth", 0)
+    if depth == 0:
+        _l.check(_l.load().nz_pipeline_begin())
+    _scope.depth = depth + 1
 
 
 def pipeline_end():
-    _l.check(_l.load().nz_pipeline_end())
+    depth = getattr(_scope, "depth", 0)
+    if depth <= 1:
+        _scope.depth = 0
+        _l.check(_l.load().nz_pipeline_end())   # NZ_E_STATE when nothing is open
+    else:
+        _scope.depth = depth - 1
 
 
 @contextmanager

@@ -274,9 +274,13 @@ class MeshTileStage(PipelineStage):
         self.currentMesh = d.mesh if d.mesh is not None else Mesh()
         d.mesh = self.currentMesh
         R = d.resolution
-        # Mesh.AllocateWritableMeshData(1) + PositionStream32.Setup
-        self.currentMesh.vertices = np.empty(((R + 1) * (R + 1), 12), np.float32)
-        self.currentMesh.indices = np.empty(6 * R * R, np.uint32)
+        # Mesh.AllocateWritableMeshData(1) + PositionStream32.Setup; buffers the caller already attached to
+        # the Mesh (e.g. pinned memory) are reused when they have the right shape
+        v, i = self.currentMesh.vertices, self.currentMesh.indices
+        if not (isinstance(v, np.ndarray) and v.dtype == np.float32 and v.size == (R + 1) * (R + 1) * 12):
+            self.currentMesh.vertices = np.empty(((R + 1) * (R + 1), 12), np.float32)
+        if not (isinstance(i, np.ndarray) and i.dtype == np.uint32 and i.size == 6 * R * R):
+            self.currentMesh.indices = np.empty(6 * R * R, np.uint32)
         self.currentMesh.bounds = ((0.5 * d.tileSize, 0.5 * d.tileHeight, 0.5 * d.tileSize),
                                    (d.tileSize, d.tileHeight, d.tileSize))
         self.jobHandle = _chain(dependency)
