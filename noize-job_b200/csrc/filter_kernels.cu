@@ -95,6 +95,43 @@ __global__ void __launch_bounds__(TX) sobel2d_kernel(const float* __restrict__ s
 // [x-N..x] x [z-N..z] with clamp at 0 (exact: min is associative/commutative).  Two passes:
 // X window then Z window.
 // ---------------------------------------------------------------------------------------------
+// One fused pass: dst(x,z) = min over the trailing (n+1) x (n+1) window, staged through shared memory
+// (X window first, then Z window): 4 B read + 4 B written per cell instead of two HBM round trips.
+constexpr int MW = 128, MH = 32, MIN_FUSED_MAX_N = 32, MTHREADS = 256;
+
+__global__ void __launch_bounds__(MTHREADS) min_window_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int width, int rows, int n) {
+    extern __shared__ float msm[];
+    const int aw = MW + n, ah = MH + n;   // staged input: n extra columns to the left, n extra rows above
+    float* A = msm;                       // ah x aw
+    float* B = msm + ah * aw;             // ah x MW : X-window minima
+    const int x0 = blockIdx.x * MW, z0 = blockIdx.y * MH;
+    for (int idx = threadIdx.x; idx < ah * aw; idx += MTHREADS) {
+        const int j = idx / aw, i = idx - j * aw;
+        A[idx] = __ldg(src + (size_t)clampi(z0 - n + j, 0, rows - 1) * width + clampi(x0 - n + i, 0, width - 1));
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ah * MW; idx += MTHREADS) {
+        const int j = idx / MW, i = idx - j * MW;
+        const float* a = A + j * aw + i;
+        float m = a[0];
+        for (int k = 1; k <= n; k++) m = fminf(m, a[k]);
+        B[idx] = m;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < MH * MW; idx += MTHREADS) {
+        const int j = idx / MW, i = idx - j * MW;
+        const int x = x0 + i, z = z0 + j;
+        if (x < width && z < rows) {
+            const float* b = B + j * MW + i;
+            float m = b[0];
+            for (int k = 1; k <= n; k++) m = fminf(m, b[k * MW]);
+            dst[(size_t)z * width + x] = m;
+        }
+    }
+}
+
+// fallback for n > MIN_FUSED_MAX_N: separable X window then Z window through HBM
 __global__ void __launch_bounds__(TX) min_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
                                                    int rows, int n) {
     const int z = blockIdx.y;
@@ -171,6 +208,26 @@ int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int
                            cudaStream_t s) {
     NZ_REQUIRE(d_data && d_tmp, "min_erosion: null device buffer");
     NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "min_erosion: bad arguments");
+    if (iterations > MIN_FUSED_MAX_N) NZ_REQUIRE(rows <= 65535, "min_erosion: too many rows");
+    if (iterations > 0 && iterations <= MIN_FUSED_MAX_N) {
+        const int n = iterations;
+        const size_t smem = ((size_t)(MH + n) * (MW + n) + (size_t)(MH + n) * MW) * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            NZ_CUDA(cudaFuncSetAttribute(min_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((MH + MIN_FUSED_MAX_N) * (MW + MIN_FUSED_MAX_N) + (MH + MIN_FUSED_MAX_N) * MW) * sizeof(float))));
+            attr_set = true;
+        }
+        dim3 grid(cdiv(width, MW), cdiv(rows, MH));
+        min_window_kernel<<<grid, MTHREADS, smem, s>>>(d_data, d_tmp, width, rows, n);
+        NZ_LAUNCHED();
+        if (d_result) {
+            *d_result = d_tmp;
+        } else {
+            NZ_CUDA(cudaMemcpyAsync(d_data, d_tmp, (size_t)width * rows * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+        return NZ_OK;
+    }
     if (iterations > 0) {
         dim3 grid(cdiv(width, TX), rows);
         min_x_kernel<<<grid, TX, 0, s>>>(d_data, d_tmp, width, rows, iterations);

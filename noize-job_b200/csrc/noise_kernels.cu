@@ -37,7 +37,25 @@ __device__ __forceinline__ float rectify(float v) { return (1.0f + v) * 0.5f; }
 // Same operations as the oracle's snoise2; the only restructuring is exact: the middle corner's
 // inner hash permute(iy + i1y) is one of the two hashes already computed for the outer corners
 // (i1y is 0 or 1), so it is selected instead of recomputed.
-__device__ __forceinline__ float snoise2(float vx, float vy) {
+//
+// FRND (floorf) issues at 0.5 warp-inst/clk/SM on B200, 1/8 of the FP32 rate (profiles/r1_ubench_*), and
+// the straightforward form needs 15 of them per octave, which saturates the XU pipe before the FMA pipe.
+// Two more exact rewrites move 5 of them onto the FP32 pipe at no extra instruction count:
+//   * the two INNER hashes use a round-to-nearest quotient (magic-number add) instead of floor: the
+//     result r = u - 289*rn(u/289) is congruent to u mod 289 (|r| <= 144) and only ever feeds the outer
+//     hash, whose polynomial (34x+1)x maps congruent inputs to congruent outputs, so the canonical
+//     residue the outer hash produces is unchanged.  u <= 2.9e6 < 2^22 keeps the magic add exact.
+//   * floor(gx + 0.5) == rn(gx) for every gx the 289 hash values can produce (no ties), checked
+//     exhaustively in tests/test_oracle.py.
+constexpr float NZ_MAGIC = 12582912.0f;  // 1.5 * 2^23: (x + MAGIC) - MAGIC == rint(x) for |x| < 2^22
+__device__ __forceinline__ float permute_centered(float x) {
+    const float u = fmaf(34.0f, x, 1.0f) * x;
+    const float q = fmaf(u, 1.0f / 289.0f, NZ_MAGIC) - NZ_MAGIC;
+    return fmaf(-289.0f, q, u);
+}
+
+// returns dot(m, g), i.e. snoise(float2) / 130 (the getter folds the factor, see basis_value)
+__device__ __forceinline__ float snoise2_raw(float vx, float vy) {
     const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
     const float Cz = -0.577350269189626f, Cw = 0.024390243902439f;
     float s = dot2(vx, vy, Cy, Cy);
@@ -50,27 +68,28 @@ __device__ __forceinline__ float snoise2(float vx, float vy) {
     float x2x = x0x + Cz, x2y = x0y + Cz;
     ix = mod289(ix);
     iy = mod289(iy);
-    float py0 = permute(iy), py1 = permute(iy + 1.0f);
+    float py0 = permute_centered(iy), py1 = permute_centered(iy + 1.0f);
     float p0 = permute(py0 + ix);
     float p1 = permute((xgty ? py0 : py1) + ix + i1x);
     float p2 = permute(py1 + ix + 1.0f);
-    float m0 = fmaxf(0.5f - dot2(x0x, x0y, x0x, x0y), 0.0f);
-    float m1 = fmaxf(0.5f - dot2(x1x, x1y, x1x, x1y), 0.0f);
-    float m2 = fmaxf(0.5f - dot2(x2x, x2y, x2x, x2y), 0.0f);
+    float m0 = fmaxf(fmaf(-x0y, x0y, fmaf(-x0x, x0x, 0.5f)), 0.0f);
+    float m1 = fmaxf(fmaf(-x1y, x1y, fmaf(-x1x, x1x, 0.5f)), 0.0f);
+    float m2 = fmaxf(fmaf(-x2y, x2y, fmaf(-x2x, x2x, 0.5f)), 0.0f);
     m0 = m0 * m0; m0 = m0 * m0;
     m1 = m1 * m1; m1 = m1 * m1;
     m2 = m2 * m2; m2 = m2 * m2;
     float gx0 = fmaf(2.0f, fracf_(p0 * Cw), -1.0f), gx1 = fmaf(2.0f, fracf_(p1 * Cw), -1.0f),
           gx2 = fmaf(2.0f, fracf_(p2 * Cw), -1.0f);
     float h0 = fabsf(gx0) - 0.5f, h1 = fabsf(gx1) - 0.5f, h2 = fabsf(gx2) - 0.5f;
-    float a0 = gx0 - floorf(gx0 + 0.5f), a1 = gx1 - floorf(gx1 + 0.5f), a2 = gx2 - floorf(gx2 + 0.5f);
+    float a0 = gx0 - ((gx0 + NZ_MAGIC) - NZ_MAGIC), a1 = gx1 - ((gx1 + NZ_MAGIC) - NZ_MAGIC),
+          a2 = gx2 - ((gx2 + NZ_MAGIC) - NZ_MAGIC);
     m0 = m0 * taylorInvSqrt(fmaf(h0, h0, a0 * a0));
     m1 = m1 * taylorInvSqrt(fmaf(h1, h1, a1 * a1));
     m2 = m2 * taylorInvSqrt(fmaf(h2, h2, a2 * a2));
     float g0 = fmaf(h0, x0y, a0 * x0x);
     float g1 = fmaf(h1, x1y, a1 * x1x);
     float g2 = fmaf(h2, x2y, a2 * x2x);
-    return 130.0f * dot3(m0, m1, m2, g0, g1, g2);
+    return dot3(m0, m1, m2, g0, g1, g2);
 }
 
 // ---- cnoise(float2) ---------------------------------------------------------------------------
@@ -267,7 +286,7 @@ __device__ __forceinline__ float basis_value(float x, float z) {
     } else if (TYPE == NZ_NOISE_PERIODIC_PERLIN) {
         return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.0f));
     } else if (TYPE == NZ_NOISE_SIMPLEX) {
-        return rectify(snoise2(x, z));
+        return fmaf(65.0f, snoise2_raw(x, z), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
     } else if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) {
         return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.62f));
     } else if (TYPE == NZ_NOISE_CELLULAR) {
@@ -338,7 +357,16 @@ int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cud
         case NZ_NOISE_SIN: return launch_typed<NZ_NOISE_SIN, 2>(d_dst, p, s);
         case NZ_NOISE_PERLIN: return launch_typed<NZ_NOISE_PERLIN, 2>(d_dst, p, s);
         case NZ_NOISE_PERIODIC_PERLIN: return launch_typed<NZ_NOISE_PERIODIC_PERLIN, 1>(d_dst, p, s);
-        case NZ_NOISE_SIMPLEX: return launch_typed<NZ_NOISE_SIMPLEX, 2>(d_dst, p, s);
+        case NZ_NOISE_SIMPLEX: {
+            // cells per thread is a tuning knob (NZ_FBM_CELLS=1|2|4 overrides the default while profiling)
+            static const int cells = [] {
+                const char* e = getenv("NZ_FBM_CELLS");
+                return e ? atoi(e) : 2;
+            }();
+            if (cells == 1) return launch_typed<NZ_NOISE_SIMPLEX, 1>(d_dst, p, s);
+            if (cells == 4) return launch_typed<NZ_NOISE_SIMPLEX, 4>(d_dst, p, s);
+            return launch_typed<NZ_NOISE_SIMPLEX, 2>(d_dst, p, s);
+        }
         case NZ_NOISE_ROTATED_SIMPLEX: return launch_typed<NZ_NOISE_ROTATED_SIMPLEX, 1>(d_dst, p, s);
         case NZ_NOISE_CELLULAR: return launch_typed<NZ_NOISE_CELLULAR, 1>(d_dst, p, s);
         case NZ_NOISE_DOMAIN_ROTATED_PERLIN: return launch_typed<NZ_NOISE_DOMAIN_ROTATED_PERLIN, 1>(d_dst, p, s);

@@ -45,7 +45,7 @@ struct TapsR {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // X pass of the two columns (c, c+1) of one tile row
-template <int R>
+template <int R, bool SCALE>
 __device__ __forceinline__ float2 xrow(const float* __restrict__ in, int row, int c, const TapsR<R>& kx, float factor) {
     const float* p = in + row * FW + c;
     const float2 l = *reinterpret_cast<const float2*>(p - 2);
@@ -71,10 +71,10 @@ __device__ __forceinline__ float2 xrow(const float* __restrict__ in, int row, in
             o1 = fmaf(w[5 + k], kx.k[R + k], o1);
         }
     }
-    return make_float2(o0 * factor, o1 * factor);
+    return SCALE ? make_float2(o0 * factor, o1 * factor) : make_float2(o0, o1);  // x * 1.0f == x: skipping is exact
 }
 
-template <int R>
+template <int R, bool SCALE>
 __global__ void __launch_bounds__(FTHREADS, 2)
 sep_fused_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, int T, float factor,
                  TapsR<R> kx, TapsR<R> kz, int force_scalar) {
@@ -119,12 +119,12 @@ sep_fused_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, 
         // register window: slot s holds the X pass of tile row (a - R + s') with s' == s (mod KS)
         float2 xp[KS];
 #pragma unroll
-        for (int j = 0; j < 2 * R; j++) xp[j] = xrow<R>(in, a - R + j, c, kx, factor);
+        for (int j = 0; j < 2 * R; j++) xp[j] = xrow<R, SCALE>(in, a - R + j, c, kx, factor);
         for (int z = a; z < b; z += KS) {
 #pragma unroll
             for (int u = 0; u < KS; u++) {
                 const int row = z + u;
-                xp[(u + 2 * R) % KS] = xrow<R>(in, min(row + R, FH - 1), c, kx, factor);
+                xp[(u + 2 * R) % KS] = xrow<R, SCALE>(in, min(row + R, FH - 1), c, kx, factor);
                 float o0 = 0.0f, o1 = 0.0f;
 #pragma unroll
                 for (int k = R; k >= -R; k--) {
@@ -132,7 +132,7 @@ sep_fused_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, 
                     o0 = fmaf(v.x, kz.k[R - k], o0);
                     o1 = fmaf(v.y, kz.k[R - k], o1);
                 }
-                if (active && row < b) *reinterpret_cast<float2*>(out + row * FW + c) = make_float2(o0 * factor, o1 * factor);
+                if (active && row < b) *reinterpret_cast<float2*>(out + row * FW + c) = (SCALE ? make_float2(o0 * factor, o1 * factor) : make_float2(o0, o1));
             }
         }
         __syncthreads();
@@ -173,7 +173,8 @@ int32_t launch_fused_r(float* d_data, float* d_tmp, int width, int rows, const f
                        int iterations, float** d_result, cudaStream_t s) {
     static bool attr_set = false;  // benign race: the attribute is idempotent
     if (!attr_set) {
-        NZ_CUDA(cudaFuncSetAttribute(sep_fused_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        NZ_CUDA(cudaFuncSetAttribute(sep_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        NZ_CUDA(cudaFuncSetAttribute(sep_fused_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     TapsR<R> tx, tz;
@@ -192,7 +193,10 @@ int32_t launch_fused_r(float* d_data, float* d_tmp, int width, int rows, const f
     int left = iterations;
     for (int l = 0; l < launches; l++) {
         const int T = (left + (launches - l) - 1) / (launches - l);  // spread evenly
-        sep_fused_kernel<R><<<grid, FTHREADS, SMEM_BYTES, s>>>(cur, other, width, rows, T, factor, tx, tz, force_scalar);
+        if (factor == 1.0f)  // every Gauss table: the two `* factor` per cell-iteration are exact no-ops
+            sep_fused_kernel<R, false><<<grid, FTHREADS, SMEM_BYTES, s>>>(cur, other, width, rows, T, factor, tx, tz, force_scalar);
+        else
+            sep_fused_kernel<R, true><<<grid, FTHREADS, SMEM_BYTES, s>>>(cur, other, width, rows, T, factor, tx, tz, force_scalar);
         NZ_LAUNCHED();
         left -= T;
         float* tmp = cur; cur = other; other = tmp;

@@ -54,8 +54,9 @@ static inline float dot4(float ax, float ay, float az, float aw, float bx, float
     return fmaf(aw, bw, fmaf(az, bz, fmaf(ay, by, ax * bx)));
 }
 
-/* noise.snoise(float2) — noise2D.cs (webgl-noise noise2D.glsl).  Call site Fractal.cs:234. */
-static float snoise2(float vx, float vy) {
+/* noise.snoise(float2) — noise2D.cs (webgl-noise noise2D.glsl).  Call site Fractal.cs:234.
+ * Returns dot(m, g) WITHOUT the final factor 130 so the getter can fold it (see basis_value case 3). */
+static float snoise2_raw(float vx, float vy) {
     const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
     const float Cz = -0.577350269189626f, Cw = 0.024390243902439f;
     float s = dot2(vx, vy, Cy, Cy);
@@ -69,8 +70,9 @@ static float snoise2(float vx, float vy) {
     iy = mod289(iy);
     float p[3] = {permute(permute(iy + 0.0f) + ix + 0.0f), permute(permute(iy + i1y) + ix + i1x),
                   permute(permute(iy + 1.0f) + ix + 1.0f)};
-    float m[3] = {fmaxf(0.5f - dot2(x0x, x0y, x0x, x0y), 0.0f), fmaxf(0.5f - dot2(x1x, x1y, x1x, x1y), 0.0f),
-                  fmaxf(0.5f - dot2(x2x, x2y, x2x, x2y), 0.0f)};
+    /* max(0.5 - dot(x,x), 0): canonical contraction 0.5 - x*x - y*y -> fma(-y,y, fma(-x,x, 0.5)) */
+    float m[3] = {fmaxf(fmaf(-x0y, x0y, fmaf(-x0x, x0x, 0.5f)), 0.0f), fmaxf(fmaf(-x1y, x1y, fmaf(-x1x, x1x, 0.5f)), 0.0f),
+                  fmaxf(fmaf(-x2y, x2y, fmaf(-x2x, x2x, 0.5f)), 0.0f)};
     float a0[3], h[3];
     for (int k = 0; k < 3; k++) {
         m[k] = m[k] * m[k];
@@ -84,8 +86,10 @@ static float snoise2(float vx, float vy) {
     float g0 = fmaf(h[0], x0y, a0[0] * x0x);
     float g1 = fmaf(h[1], x1y, a0[1] * x1x);
     float g2 = fmaf(h[2], x2y, a0[2] * x2x);
-    return 130.0f * dot3(m[0], m[1], m[2], g0, g1, g2);
+    return dot3(m[0], m[1], m[2], g0, g1, g2);
 }
+/* noise.snoise(float2) = 130 * dot(m, g) */
+static float snoise2(float vx, float vy) { return 130.0f * snoise2_raw(vx, vy); }
 
 /* noise.cnoise(float2) — classicnoise2D.cs.  Call site Fractal.cs:147. */
 static float cnoise2(float Px, float Py) {
@@ -307,7 +311,8 @@ static inline float basis_value(int type, float x, float z) {
         }
         case 1: return rectify(cnoise2(x, z));                              /* PerlinGetter :141-154 */
         case 2: return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.0f));    /* PeriodicPerlinGetter :176-191 */
-        case 3: return rectify(snoise2(x, z));                              /* SimplexGetter :227-241 */
+        case 3: /* SimplexGetter :227-241: Rectify(130*d) = (1 + 130*d)/2, canonical contraction 0.5 + 65*d */
+            return fmaf(65.0f, snoise2_raw(x, z), 0.5f);
         case 4: return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.62f));   /* RotatedSimplexGetter :193-208 */
         case 5: { /* CellularGetter :262-278 */
             float f1, f2;

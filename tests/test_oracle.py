@@ -291,3 +291,27 @@ def test_tile_geometry(oracle):
     total, mpix, tsize = oracle.tile_geometry(256, 500, 3)
     assert (total, mpix) == (258, 1) and abs(tsize - (500 + 2 * 500 / 256)) < 1e-4
     assert oracle.tile_geometry(1000, 1000, 5) == (1010, 5, 1010.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# exact rewrites the CUDA noise kernel relies on (noize-job_b200/csrc/noise_kernels.cu)
+# ---------------------------------------------------------------------------------------------
+def test_round_to_nearest_equals_floor_plus_half_on_all_hash_values():
+    f = np.float32
+    p = np.arange(0, 290, dtype=np.float32)
+    fr = p * f(0.024390243902439)
+    gx = (f(2.0) * (fr - np.floor(fr)) - f(1.0)).astype(np.float32)
+    magic = f(12582912.0)
+    assert np.array_equal(np.floor((gx + f(0.5)).astype(np.float32)), ((gx + magic).astype(np.float32) - magic))
+
+
+def test_centered_permute_is_congruent_to_the_canonical_one(oracle):
+    f = np.float32
+    magic, c = f(12582912.0), f(1.0) / f(289.0)
+    for x in range(-300, 601):
+        u = f(34 * x + 1) * f(x)                       # exact integer < 2^24
+        q = f(np.float64(u) * np.float64(c) + np.float64(magic)) - magic   # fma: single rounding
+        r = np.float64(u) - 289.0 * np.float64(q)     # fma(-289, q, u) is exact
+        assert abs(r) <= 145 and (int(r) - int(u)) % 289 == 0
+        if x >= 0:
+            assert int(oracle.lib.nzref_permute(float(x))) == int(r) % 289
