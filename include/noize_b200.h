@@ -230,9 +230,12 @@ NZ_API int32_t nz_dev_kernel_filter(float* d_data, float* d_tmp, int32_t width, 
 NZ_API int32_t nz_dev_min_erosion(float* d_data, float* d_tmp, int32_t width, int32_t rows,
                                   int32_t iterations, float** d_result, void* stream);
 
-/* Bytes of scratch nz_dev_flowmap needs for a width x rows grid. */
+/* Flow map.  d_tmp is the ping-pong partner of d_height (same size).  For 1 <= iterations <= 5 on an
+ * even width the whole stage is ONE fused launch that reads d_height and writes d_tmp (state lives in
+ * shared memory) and needs no scratch; otherwise water + 4 flow fields are kept in d_scratch
+ * (nz_dev_flowmap_scratch_bytes, 0 when the fused path applies) and the result lands in d_height. */
 NZ_API size_t  nz_dev_flowmap_scratch_bytes(int32_t width, int32_t rows, int32_t iterations);
-NZ_API int32_t nz_dev_flowmap(float* d_height, void* d_scratch, int32_t width, int32_t rows,
+NZ_API int32_t nz_dev_flowmap(float* d_height, float* d_tmp, void* d_scratch, int32_t width, int32_t rows,
                               int32_t iterations, float norm_min, float norm_max,
                               float** d_result, void* stream);
 

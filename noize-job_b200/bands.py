@@ -101,8 +101,8 @@ class CudaEngine:
     def flowmap_scratch_bytes(self, width, rows, cfg):
         return _dev.flowmap_scratch_bytes(width, rows, cfg.flow_iterations)
 
-    def flowmap(self, height, scratch, cfg):
-        return _dev.flowmap(height, scratch, cfg.flow_iterations, cfg.norm_min, cfg.norm_max)
+    def flowmap(self, height, tmp, scratch, cfg):
+        return _dev.flowmap(height, tmp, scratch, cfg.flow_iterations, cfg.norm_min, cfg.norm_max)
 
     def min_erosion(self, data, tmp, cfg):
         return _dev.min_erosion(data, tmp, cfg.erosion_iterations)
@@ -223,13 +223,9 @@ class BandChain:
 
         def flow(win, tmp):
             need = eng.flowmap_scratch_bytes(win.shape[1], win.shape[0], cfg)
-            if self.flow_scratch is None or self.flow_scratch.numel() < need:
+            if need and (self.flow_scratch is None or self.flow_scratch.numel() < need):
                 self.flow_scratch = eng.empty_bytes(need)
-            res = eng.flowmap(win, self.flow_scratch, cfg)
-            if res.data_ptr() != win.data_ptr():      # result left in scratch: bring it into the band buffer
-                tmp.copy_(res)
-                return tmp
-            return win
+            return eng.flowmap(win, tmp, self.flow_scratch if need else None, cfg)
 
         stencil("flow", flow)
         stencil("erosion", lambda win, tmp: eng.min_erosion(win, tmp, cfg))

@@ -471,11 +471,12 @@ NZ_API size_t nz_dev_flowmap_scratch_bytes(int32_t width, int32_t rows, int32_t 
     return flowmap_scratch_bytes(width, rows, iterations);
 }
 
-NZ_API int32_t nz_dev_flowmap(float* d_height, void* d_scratch, int32_t width, int32_t rows, int32_t iterations,
-                              float norm_min, float norm_max, float** d_result, void* stream) {
+NZ_API int32_t nz_dev_flowmap(float* d_height, float* d_tmp, void* d_scratch, int32_t width, int32_t rows,
+                              int32_t iterations, float norm_min, float norm_max, float** d_result, void* stream) {
     int32_t rc = ensure_init();
     if (rc != NZ_OK) return rc;
-    return launch_flowmap(d_height, d_scratch, width, rows, iterations, norm_min, norm_max, d_result, (cudaStream_t)stream);
+    return launch_flowmap(d_height, d_tmp, d_scratch, width, rows, iterations, norm_min, norm_max, d_result,
+                          (cudaStream_t)stream);
 }
 
 NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32_t* d_indices, int32_t resolution,
@@ -644,10 +645,13 @@ NZ_API int32_t nz_min_erosion(nz_slice_f32 src, int32_t resolution, int32_t iter
 NZ_API int32_t nz_flowmap(nz_slice_f32 height, int32_t resolution, int32_t iterations, float norm_min, float norm_max) {
     NZ_REQUIRE(iterations >= 0, "nz_flowmap: iterations %d < 0", iterations);
     void* scratch = nullptr;
-    int32_t rc = run_inplace_stage(height, resolution, "nz_flowmap", false, [&](Mirror& m, float** res) {
-        int32_t r = pool_alloc(&scratch, flowmap_scratch_bytes(resolution, resolution, iterations));
-        if (r != NZ_OK) return r;
-        return launch_flowmap(m.d, scratch, resolution, resolution, iterations, norm_min, norm_max, res, t_state.stream);
+    int32_t rc = run_inplace_stage(height, resolution, "nz_flowmap", true, [&](Mirror& m, float** res) {
+        const size_t need = flowmap_scratch_bytes(resolution, resolution, iterations);
+        if (need) {
+            int32_t r = pool_alloc(&scratch, need);
+            if (r != NZ_OK) return r;
+        }
+        return launch_flowmap(m.d, m.d_tmp, scratch, resolution, resolution, iterations, norm_min, norm_max, res, t_state.stream);
     });
     if (scratch) {
         // the stream may still be using it inside a pipeline: order the release after the work

@@ -107,15 +107,28 @@ __global__ void __launch_bounds__(TX) fill_norm_zero_kernel(float* __restrict__ 
 
 }  // namespace
 
+// scratch is only needed by the per-iteration path (water + 4 flow fields in HBM); the fused wavefront
+// kernel (flowwave_kernels.cu) keeps all state in shared memory and needs just an output buffer
 size_t flowmap_scratch_bytes(int width, int rows, int iterations) {
-    (void)iterations;
+    if (flow_wave_supported(width, rows, iterations, nullptr, nullptr)) return 0;
     return (size_t)width * rows * sizeof(float) * 5;
 }
 
-int32_t launch_flowmap(float* d_height, void* d_scratch, int width, int rows, int iterations, float norm_min,
-                       float norm_max, float** d_result, cudaStream_t s) {
+int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width, int rows, int iterations,
+                       float norm_min, float norm_max, float** d_result, cudaStream_t s) {
     NZ_REQUIRE(d_height, "flowmap: null height buffer");
     NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "flowmap: bad arguments");
+    // NZ_FLOW_UNFUSED=1 forces the per-iteration kernels (used by the tests to cross-check the two paths bit for bit)
+    if (d_tmp && !getenv("NZ_FLOW_UNFUSED") && flow_wave_supported(width, rows, iterations, d_height, d_tmp)) {
+        int32_t rc = launch_flow_wave(d_height, d_tmp, width, rows, iterations, norm_min, norm_max, s);
+        if (rc != NZ_OK) return rc;
+        if (d_result) {
+            *d_result = d_tmp;
+        } else {
+            NZ_CUDA(cudaMemcpyAsync(d_height, d_tmp, (size_t)width * rows * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+        return NZ_OK;
+    }
     const size_t n = (size_t)width * rows;
     const float norm_range = norm_max - norm_min;  // FlowMapStage.cs:48-51
     dim3 grid(cdiv(width, TX), rows);

@@ -64,8 +64,11 @@ int32_t launch_sobel2d(float* d_data, float* d_tmp, int width, int rows, int ite
 int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int iterations, float** d_result,
                            cudaStream_t s);
 size_t flowmap_scratch_bytes(int width, int rows, int iterations);
-int32_t launch_flowmap(float* d_height, void* d_scratch, int width, int rows, int iterations, float norm_min,
-                       float norm_max, float** d_result, cudaStream_t s);
+int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width, int rows, int iterations,
+                       float norm_min, float norm_max, float** d_result, cudaStream_t s);
+bool flow_wave_supported(int width, int rows, int iterations, const void* a, const void* b);
+int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
+                         float norm_max, cudaStream_t s);
 int32_t launch_mesh(int mesh_type, void* d_vtx, uint32_t* d_idx, int R, int inRes, float tile_height,
                     float tile_size, const float* d_heights, int h_row_first, int h_rows, int vz_begin, int vz_end,
                     cudaStream_t s);

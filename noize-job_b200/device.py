@@ -63,22 +63,20 @@ def flowmap_scratch_bytes(width, rows, iterations):
     return int(_l.load().nz_dev_flowmap_scratch_bytes(width, rows, iterations))
 
 
-def flowmap(height, scratch, iterations=5, norm_min=-0.1, norm_max=0.1, stream=None):
-    """`scratch`: a CUDA tensor of at least flowmap_scratch_bytes(...) bytes.  Returns the tensor holding the
-    result: `height`, or a (rows,width) view into `scratch`."""
-    _grid(height, "height")
+def flowmap(height, tmp, scratch=None, iterations=5, norm_min=-0.1, norm_max=0.1, stream=None):
+    """`tmp`: ping-pong partner of `height`; `scratch`: a CUDA tensor of at least flowmap_scratch_bytes(...)
+    bytes (may be None when that is 0).  Returns the tensor (height or tmp) that holds the result."""
+    _grid(height, "height"); _grid(tmp, "tmp")
+    assert height.shape == tmp.shape
     rows, width = height.shape
     need = flowmap_scratch_bytes(width, rows, iterations)
-    if scratch.numel() * scratch.element_size() < need:
-        raise ValueError(f"flowmap scratch too small: {scratch.numel() * scratch.element_size()} < {need}")
+    have = 0 if scratch is None else scratch.numel() * scratch.element_size()
+    if have < need:
+        raise ValueError(f"flowmap scratch too small: {have} < {need}")
     res = C.c_void_p()
-    _l.check(_l.load().nz_dev_flowmap(height.data_ptr(), scratch.data_ptr(), width, rows, iterations, norm_min, norm_max,
-                                      C.byref(res), _l.stream_ptr(stream)))
-    if res.value == height.data_ptr():
-        return height
-    import torch
-    off = (res.value - scratch.data_ptr()) // 4
-    return scratch.view(torch.float32).view(-1)[off:off + rows * width].view(rows, width)
+    _l.check(_l.load().nz_dev_flowmap(height.data_ptr(), tmp.data_ptr(), None if scratch is None else scratch.data_ptr(),
+                                      width, rows, iterations, norm_min, norm_max, C.byref(res), _l.stream_ptr(stream)))
+    return _pick(res, height, tmp)
 
 
 def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, margin_pix, tile_height, tile_size,

@@ -68,7 +68,7 @@ SIGNATURES = {
     "nz_dev_kernel_filter": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "nz_dev_min_erosion": (_i32, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "nz_dev_flowmap_scratch_bytes": (_sz, [_i32, _i32, _i32]),
-    "nz_dev_flowmap": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, C.POINTER(_vp), _vp]),
+    "nz_dev_flowmap": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, C.POINTER(_vp), _vp]),
     "nz_dev_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "nz_dev_fma_peak": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_double), _vp]),
 }

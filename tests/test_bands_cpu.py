@@ -44,9 +44,9 @@ class OracleEngine:
     def flowmap_scratch_bytes(self, width, rows, cfg):
         return 16
 
-    def flowmap(self, height, scratch, cfg):
-        height.copy_(torch.from_numpy(self.o.flowmap(height.numpy(), cfg.flow_iterations, cfg.norm_min, cfg.norm_max)))
-        return height
+    def flowmap(self, height, tmp, scratch, cfg):
+        tmp.copy_(torch.from_numpy(self.o.flowmap(height.numpy(), cfg.flow_iterations, cfg.norm_min, cfg.norm_max)))
+        return tmp
 
     def min_erosion(self, data, tmp, cfg):
         data.copy_(torch.from_numpy(self.o.min_erosion(data.numpy(), cfg.erosion_iterations)))

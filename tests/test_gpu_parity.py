@@ -189,6 +189,37 @@ def test_flowmap_on_terrain(nz, oracle, res, iters):
     assert np.abs(got.reshape(res, res) - ref).max() <= TOL_FLOW * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("rows,width,iters", [(700, 600, 5), (300, 1000, 4), (97, 238, 3), (40, 18, 2), (513, 472, 1)])
+def test_flow_wavefront_kernel_equals_per_iteration_kernels_bitwise(nz, oracle, torch_cuda, monkeypatch, rows, width, iters):
+    """The fused single-launch flow map (state in shared-memory rings) against the per-iteration kernels
+    (state in HBM), on strip/chunk boundaries, grid borders and partial strips."""
+    torch = torch_cuda
+    h = torch.from_numpy(oracle.kernel_filter(rand_grid(rows, width), 3, 2) * np.float32(0.05)).cuda()
+    fused = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    monkeypatch.setenv("NZ_FLOW_UNFUSED", "1")
+    scratch = torch.empty(5 * rows * width * 4, dtype=torch.uint8, device="cuda")
+    plain = nz.device.flowmap(h.clone(), torch.empty_like(h), scratch, iters, 0.0, 0.005).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(fused, plain)
+    ref = oracle.flowmap(h.cpu().numpy(), iters, 0.0, 0.005)
+    assert np.abs(fused.cpu().numpy() - ref).max() <= TOL_FLOW * max(1.0, np.abs(ref).max())
+
+
+def test_flow_row_band_with_ghost_rows_equals_full_grid_bitwise(nz, oracle, torch_cuda):
+    torch = torch_cuda
+    n, iters = 640, 5
+    h = torch.from_numpy(oracle.kernel_filter(rand_grid(n), 3, 2) * np.float32(0.05)).cuda()
+    full = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    z0, z1, g = 200, 420, 2 * iters + 1
+    for lo, hi in ((z0 - g, z1 + g), (0, z1 + g), (z0 - g, n)):
+        win = h[lo:hi].clone()
+        out = nz.device.flowmap(win, torch.empty_like(win), None, iters, 0.0, 0.005)
+        torch.cuda.synchronize()
+        a = max(z0, lo) if lo > 0 else 0
+        b = min(z1, hi) if hi < n else n
+        assert torch.equal(out[a - lo:b - lo], full[a:b])
+
+
 def test_flowmap_default_norm_and_random_field(nz, oracle):
     a = rand_grid(256)
     got = a.copy().ravel()

@@ -30,7 +30,7 @@ def main():
     d = nz.device
     a = torch.empty(N, N, device="cuda")
     b = torch.empty_like(a)
-    scratch = torch.empty(d.flowmap_scratch_bytes(N, N, 5), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(max(16, d.flowmap_scratch_bytes(N, N, 5)), dtype=torch.uint8, device="cuda")
     cells = N * N
     rows = []
     for nt in (3, 5, 4, 1, 0):
@@ -43,7 +43,7 @@ def main():
     rows.append(("gauss3 x3", ms, 8 * cells))
     ms = timeit(lambda: d.kernel_filter(a, b, 11, 1), reps)
     rows.append(("sobel3_2d", ms, 8 * cells))
-    ms = timeit(lambda: d.flowmap(a, scratch, 5, 0.0, 0.005), reps)
+    ms = timeit(lambda: d.flowmap(a, b, scratch, 5, 0.0, 0.005), reps)
     rows.append(("flowmap x5", ms, 8 * cells))
     ms = timeit(lambda: d.min_erosion(a, b, 5), reps)
     rows.append(("min erosion x5", ms, 8 * cells))
