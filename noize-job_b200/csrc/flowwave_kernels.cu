@@ -72,144 +72,202 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
     oN = pos ? flN * K : 0.0f;
 }
 
+// ---- shared-memory rings -------------------------------------------------------------------------------
+// Every ring holds RING = 5 rows of FLW floats; ring q starts at float offset q*RING*FLW.
+//   F(t,k)  t=1..I, k=W,E,S,N   outflows of level t
+//   Wt(t)   t=1..I-1            water of level t
+//   Ht(t)   t=1..I-1            water + height of level t (what the outflow step of level t+1 reads)
+//   HC(t)   t=0..max(I-2,0)     height rows travelling with the pipeline: HC(0) is written by the loader,
+//                               HC(t) by the water stage of level t (which needs h to form Ht(t))
+template <int I> struct Rings {
+    static constexpr int NHC = I - 1 > 1 ? I - 1 : 1;
+    __host__ __device__ static constexpr int F(int t, int k) { return (((t - 1) * 4 + k) * RING) * FLW; }
+    __host__ __device__ static constexpr int Wt(int t) { return ((4 * I + (t - 1)) * RING) * FLW; }
+    __host__ __device__ static constexpr int Ht(int t) { return ((4 * I + (I - 1) + (t - 1)) * RING) * FLW; }
+    __host__ __device__ static constexpr int HC(int t) { return ((4 * I + 2 * (I - 1) + t) * RING) * FLW; }
+    static constexpr int ROWS = (4 * I + 2 * (I - 1) + NHC) * RING;
+};
+
+struct Lane {
+    float* sm;
+    int R[RING];   // R[j] = float offset (ring-relative) of the slot of row s-j, plus this lane's first column
+    int dl, dr;    // column offsets of the clamped west neighbour of cell c (-1 or 0) and east neighbour of c+1 (+2 or +1)
+    int c;         // first of this lane's two strip columns
+    int H;         // grid rows
+};
+
+// slot of row (s - lag + d), d in {-1,0,+1}; rows outside the grid clamp onto the border row
+__device__ __forceinline__ int slot_of(const Lane& L, int lag, int d, int r) {
+    const int j0 = lag % RING, jm = (lag + 1) % RING, jp = (lag + RING - 1) % RING;
+    if (d == 0) return L.R[j0];
+    if (d < 0) return r == 0 ? L.R[j0] : L.R[jm];
+    return r == L.H - 1 ? L.R[j0] : L.R[jp];
+}
+
+template <int I, int T>
+__device__ __forceinline__ void stage_outflow(const Lane& L, int s, int zc0, int zc1) {
+    using RG = Rings<I>;
+    constexpr int lag = 4 * T - 2;
+    const int r = s - lag;
+    const int lo = max(0, zc0 - (2 * I - 2 * T + 1)), hi = min(L.H, zc1 + (2 * I - 2 * T + 1));
+    if (r < lo || r >= hi) return;
+    const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
+    float* sm = L.sm;
+    float2 H0, HS, HN, w0, fW, fE, fS, fN;
+    float HWl, HEr;
+    if (T == 1) {
+        const float2 a = ld2(sm + RG::HC(0), o0), b = ld2(sm + RG::HC(0), os), d = ld2(sm + RG::HC(0), on);
+        H0 = make_float2(WATER0 + a.x, WATER0 + a.y);
+        HS = make_float2(WATER0 + b.x, WATER0 + b.y);
+        HN = make_float2(WATER0 + d.x, WATER0 + d.y);
+        HWl = WATER0 + sm[RG::HC(0) + o0 + L.dl];
+        HEr = WATER0 + sm[RG::HC(0) + o0 + L.dr];
+        w0 = make_float2(WATER0, WATER0);
+        fW = fE = fS = fN = make_float2(0.0f, 0.0f);
+    } else {
+        constexpr int P = T > 1 ? T - 1 : 1;
+        H0 = ld2(sm + RG::Ht(P), o0); HS = ld2(sm + RG::Ht(P), os); HN = ld2(sm + RG::Ht(P), on);
+        HWl = sm[RG::Ht(P) + o0 + L.dl]; HEr = sm[RG::Ht(P) + o0 + L.dr];
+        w0 = ld2(sm + RG::Wt(P), o0);
+        fW = ld2(sm + RG::F(P, 0), o0); fE = ld2(sm + RG::F(P, 1), o0);
+        fS = ld2(sm + RG::F(P, 2), o0); fN = ld2(sm + RG::F(P, 3), o0);
+    }
+    float oW0, oE0, oS0, oN0, oW1, oE1, oS1, oN1;
+    flow_cell(H0.x, HWl, H0.y, HS.x, HN.x, w0.x, fW.x, fE.x, fS.x, fN.x, oW0, oE0, oS0, oN0);
+    flow_cell(H0.y, H0.x, HEr, HS.y, HN.y, w0.y, fW.y, fE.y, fS.y, fN.y, oW1, oE1, oS1, oN1);
+    st2(sm + RG::F(T, 0), o0, oW0, oW1);
+    st2(sm + RG::F(T, 1), o0, oE0, oE1);
+    st2(sm + RG::F(T, 2), o0, oS0, oS1);
+    st2(sm + RG::F(T, 3), o0, oN0, oN1);
+}
+
+template <int I, int T>
+__device__ __forceinline__ void stage_water(const Lane& L, int s, int zc0, int zc1) {
+    using RG = Rings<I>;
+    constexpr int lag = 4 * T;
+    const int r = s - lag;
+    const int lo = max(0, zc0 - (2 * I - 2 * T)), hi = min(L.H, zc1 + (2 * I - 2 * T));
+    if (r < lo || r >= hi) return;
+    const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
+    float* sm = L.sm;
+    const float2 fW = ld2(sm + RG::F(T, 0), o0), fE = ld2(sm + RG::F(T, 1), o0);
+    const float2 fS = ld2(sm + RG::F(T, 2), o0), fN = ld2(sm + RG::F(T, 3), o0);
+    const float fE_l = sm[RG::F(T, 1) + o0 + L.dl], fW_r = sm[RG::F(T, 0) + o0 + L.dr];
+    const float2 fN_s = ld2(sm + RG::F(T, 3), os), fS_n = ld2(sm + RG::F(T, 2), on);
+    constexpr int P = T > 1 ? T - 1 : 1;
+    const float2 w = (T == 1) ? make_float2(WATER0, WATER0) : ld2(sm + RG::Wt(P), o0);
+    const float2 hh = ld2(sm + RG::HC(T - 1), o0);
+    const float out0 = ((fW.x + fE.x) + fS.x) + fN.x;
+    const float out1 = ((fW.y + fE.y) + fS.y) + fN.y;
+    const float in0 = ((fE_l + fW.y) + fN_s.x) + fS_n.x;
+    const float in1 = ((fE.x + fW_r) + fN_s.y) + fS_n.y;
+    const float nw0 = fmaxf(0.0f, fmaf(in0 - out0, TIMESTEP, w.x));
+    const float nw1 = fmaxf(0.0f, fmaf(in1 - out1, TIMESTEP, w.y));
+    st2(sm + RG::Wt(T), o0, nw0, nw1);
+    st2(sm + RG::Ht(T), o0, nw0 + hh.x, nw1 + hh.y);
+    if (T + 1 < I) st2(sm + RG::HC(T < I - 1 ? T : 0), o0, hh.x, hh.y);   // hand the height row to the next water stage
+}
+
+template <int I>
+__device__ __forceinline__ void stage_velocity(const Lane& L, int s, int zc0, int zc1, const WaveParams& p, int xs0) {
+    using RG = Rings<I>;
+    constexpr int lag = 4 * I;
+    const int r = s - lag;
+    if (r < zc0 || r >= zc1) return;
+    const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
+    float* sm = L.sm;
+    const float2 fW = ld2(sm + RG::F(I, 0), o0), fE = ld2(sm + RG::F(I, 1), o0);
+    const float fE_l = sm[RG::F(I, 1) + o0 + L.dl], fW_r = sm[RG::F(I, 0) + o0 + L.dr];
+    const float2 fS = ld2(sm + RG::F(I, 2), o0), fN = ld2(sm + RG::F(I, 3), o0);
+    const float2 fS_n = ld2(sm + RG::F(I, 2), on), fN_s = ld2(sm + RG::F(I, 3), os);
+    float res[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const float dl = (q ? fE.x : fE_l) - (q ? fW.y : fW.x);
+        const float dr = (q ? fE.y : fE.x) - (q ? fW_r : fW.y);
+        const float dt = (q ? fS_n.y : fS_n.x) - (q ? fN.y : fN.x);
+        const float db = (q ? fS.y : fS.x) - (q ? fN_s.y : fN_s.x);
+        const float vx = (dl + dr) * 0.5f, vy = (dt + db) * 0.5f;
+        float v = sqrtf(fmaf(vy, vy, vx * vx));
+        if (p.nrange < 1e-12f) v = 0.0f;
+        res[q] = (v - p.nmin) / p.nrange;
+    }
+    const int gx = xs0 + L.c;
+    if (L.c >= p.hx && L.c < FLW - p.hx && gx + 1 < p.W)
+        *reinterpret_cast<float2*>(p.out + (size_t)r * p.W + gx) = make_float2(res[0], res[1]);
+}
+
+template <int I>
+__device__ __forceinline__ void stage_load(const Lane& L, int s, int hlo, int hhi, const WaveParams& p, int xs0) {
+    using RG = Rings<I>;
+    if (s < hlo || s >= hhi) return;
+    const float* g = p.h + (size_t)s * p.W;
+    const int gx = xs0 + L.c;
+    float a, b;
+    if (gx >= 0 && gx + 1 < p.W) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(g + gx));
+        a = v.x; b = v.y;
+    } else {
+        a = __ldg(g + min(max(gx, 0), p.W - 1));
+        b = __ldg(g + min(max(gx + 1, 0), p.W - 1));
+    }
+    st2(L.sm + RG::HC(0), L.R[0], a, b);
+}
+
+// Static, cost-balanced roles: the 4 warps of a 64-column chunk split the 2I+1 stages of a step
+//   role 0: outflow 1,2   role 1: outflow 3,4   role 2: outflow 5 + velocity   role 3: water 1..I-1 + loader
 template <int I>
 __global__ void __launch_bounds__(FL_THREADS, 1) flow_wave_kernel(WaveParams p) {
     extern __shared__ __align__(16) float sm[];
-    const int W = p.W, H = p.H;
-    // smem layout (rows of FLW floats)
-    float* fbase = sm;                                   // [I][4][RING]   level t=1..I, field W,E,S,N
-    float* wbase = fbase + I * 4 * RING * FLW;           // [I-1][RING]    w_t, t=1..I-1
-    float* Hbase = wbase + (I - 1) * RING * FLW;         // [I-1][RING]    H_t = w_t + h
-    float* hbase = Hbase + (I - 1) * RING * FLW;         // [4I]           height rows
-    constexpr int RH = 4 * I;
-#define F_ROW(t, k, z) (fbase + ((((t) - 1) * 4 + (k)) * RING + (z) % RING) * FLW)
-#define W_ROW(t, z) (wbase + (((t) - 1) * RING + (z) % RING) * FLW)
-#define H_ROW(t, z) (Hbase + (((t) - 1) * RING + (z) % RING) * FLW)
-#define HT_ROW(z) (hbase + ((z) % RH) * FLW)
-
+    const int H = p.H;
     const int xs0 = blockIdx.x * p.swi - p.hx;           // grid x of strip column 0 (even)
     const int zc0 = blockIdx.y * p.zc, zc1 = min(zc0 + p.zc, H);
-    const int cmin = max(0, -xs0), cmax = min(FLW - 1, W - 1 - xs0);   // strip columns inside the grid
+    const int cmin = max(0, -xs0), cmax = min(FLW - 1, p.W - 1 - xs0);   // strip columns inside the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nitems = (2 * I + 1) * XCH;
+    const int role = warp & 3;
+    Lane L;
+    L.sm = sm;
+    L.c = (warp >> 2) * 64 + lane * 2;
+    L.dl = max(L.c - 1, cmin) - L.c;
+    L.dr = min(L.c + 2, cmax) - L.c;
+    L.H = H;
     const int hlo = max(0, zc0 - 2 * I), hhi = min(H, zc1 + 2 * I);
-
-    for (int s = zc0 - 2 * I; s < zc1 + 4 * I; s++) {
-        for (int item = warp; item < nitems; item += FL_WARPS) {
-            const int stage = item / XCH;                // 0 = L, 2t-1 = A_t, 2t = B_t (t < I), 2I = V
-            const int c = (item % XCH) * 64 + lane * 2;  // this lane's two columns: c, c+1
-            const int cl = max(c - 1, cmin), cr = min(c + 2, cmax);
-            if (stage == 0) {
-                // ---- L: height row s ---------------------------------------------------------------
-                if (s >= hlo && s < hhi) {
-                    const float* g = p.h + (size_t)s * W;
-                    const int gx = xs0 + c;
-                    float a, b;
-                    if (gx >= 0 && gx + 1 < W) {
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(g + gx));
-                        a = v.x; b = v.y;
-                    } else {
-                        a = __ldg(g + min(max(gx, 0), W - 1));
-                        b = __ldg(g + min(max(gx + 1, 0), W - 1));
-                    }
-                    st2(HT_ROW(s), c, a, b);
-                }
-            } else if (stage == 2 * I) {
-                // ---- V: velocity magnitude + normalise, row s - 4I -----------------------------------
-                const int r = s - 4 * I;
-                if (r >= zc0 && r < zc1) {
-                    const int rs = max(r - 1, 0), rn = min(r + 1, H - 1);
-                    const float* fWr = F_ROW(I, 0, r); const float* fEr = F_ROW(I, 1, r);
-                    const float2 fW = ld2(fWr, c), fE = ld2(fEr, c);
-                    const float fE_l = fEr[cl], fW_r = fWr[cr];
-                    const float2 fS = ld2(F_ROW(I, 2, r), c), fN = ld2(F_ROW(I, 3, r), c);
-                    const float2 fS_n = ld2(F_ROW(I, 2, rn), c), fN_s = ld2(F_ROW(I, 3, rs), c);
-                    float res[2];
+    // first step, rounded down to a multiple of RING so that slot(s) = s mod RING starts at 0
+    const int s_first = zc0 - 2 * I;
+    const int s_begin = s_first - (((s_first % RING) + RING) % RING);
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const float dl = (q ? fE.x : fE_l) - (q ? fW.y : fW.x);
-                        const float dr = (q ? fE.y : fE.x) - (q ? fW_r : fW.y);
-                        const float dt = (q ? fS_n.y : fS_n.x) - (q ? fN.y : fN.x);
-                        const float db = (q ? fS.y : fS.x) - (q ? fN_s.y : fN_s.x);
-                        const float vx = (dl + dr) * 0.5f, vy = (dt + db) * 0.5f;
-                        float v = sqrtf(fmaf(vy, vy, vx * vx));
-                        if (p.nrange < 1e-12f) v = 0.0f;
-                        res[q] = (v - p.nmin) / p.nrange;
-                    }
-                    const int gx = xs0 + c;
-                    if (c >= p.hx && c < FLW - p.hx && gx + 1 < W)
-                        *reinterpret_cast<float2*>(p.out + (size_t)r * W + gx) = make_float2(res[0], res[1]);
-                }
-            } else if (stage & 1) {
-                // ---- A_t: outflow step, row s - (4t-2) -----------------------------------------------
-                const int t = (stage + 1) >> 1;
-                const int r = s - (4 * t - 2);
-                const int lo = max(0, zc0 - (2 * I - 2 * t + 1)), hi = min(H, zc1 + (2 * I - 2 * t + 1));
-                if (r >= lo && r < hi) {
-                    const int rs = max(r - 1, 0), rn = min(r + 1, H - 1);
-                    float2 H0, HS, HN, w0, fW, fE, fS, fN;
-                    float HWl, HEr;
-                    if (t == 1) {
-                        // level 0: water == 1e-4 everywhere, flows == 0: H_0 = 1e-4 + h computed on the fly
-                        const float* hr = HT_ROW(r);
-                        const float2 a = ld2(hr, c), b = ld2(HT_ROW(rs), c), d = ld2(HT_ROW(rn), c);
-                        H0 = make_float2(WATER0 + a.x, WATER0 + a.y);
-                        HS = make_float2(WATER0 + b.x, WATER0 + b.y);
-                        HN = make_float2(WATER0 + d.x, WATER0 + d.y);
-                        HWl = WATER0 + hr[cl];
-                        HEr = WATER0 + hr[cr];
-                        w0 = make_float2(WATER0, WATER0);
-                        fW = fE = fS = fN = make_float2(0.0f, 0.0f);
-                    } else {
-                        const float* Hr = H_ROW(t - 1, r);
-                        H0 = ld2(Hr, c); HS = ld2(H_ROW(t - 1, rs), c); HN = ld2(H_ROW(t - 1, rn), c);
-                        HWl = Hr[cl]; HEr = Hr[cr];
-                        w0 = ld2(W_ROW(t - 1, r), c);
-                        fW = ld2(F_ROW(t - 1, 0, r), c); fE = ld2(F_ROW(t - 1, 1, r), c);
-                        fS = ld2(F_ROW(t - 1, 2, r), c); fN = ld2(F_ROW(t - 1, 3, r), c);
-                    }
-                    float oW0, oE0, oS0, oN0, oW1, oE1, oS1, oN1;
-                    flow_cell(H0.x, HWl, H0.y, HS.x, HN.x, w0.x, fW.x, fE.x, fS.x, fN.x, oW0, oE0, oS0, oN0);
-                    flow_cell(H0.y, H0.x, HEr, HS.y, HN.y, w0.y, fW.y, fE.y, fS.y, fN.y, oW1, oE1, oS1, oN1);
-                    st2(F_ROW(t, 0, r), c, oW0, oW1);
-                    st2(F_ROW(t, 1, r), c, oE0, oE1);
-                    st2(F_ROW(t, 2, r), c, oS0, oS1);
-                    st2(F_ROW(t, 3, r), c, oN0, oN1);
-                }
-            } else {
-                // ---- B_t: water step, row s - 4t (t < I) ---------------------------------------------
-                const int t = stage >> 1;
-                const int r = s - 4 * t;
-                const int lo = max(0, zc0 - (2 * I - 2 * t)), hi = min(H, zc1 + (2 * I - 2 * t));
-                if (r >= lo && r < hi) {
-                    const int rs = max(r - 1, 0), rn = min(r + 1, H - 1);
-                    const float* fWr = F_ROW(t, 0, r); const float* fEr = F_ROW(t, 1, r);
-                    const float2 fW = ld2(fWr, c), fE = ld2(fEr, c);
-                    const float2 fS = ld2(F_ROW(t, 2, r), c), fN = ld2(F_ROW(t, 3, r), c);
-                    const float fE_l = fEr[cl], fW_r = fWr[cr];
-                    const float2 fN_s = ld2(F_ROW(t, 3, rs), c), fS_n = ld2(F_ROW(t, 2, rn), c);
-                    const float2 w = (t == 1) ? make_float2(WATER0, WATER0) : ld2(W_ROW(t - 1, r), c);
-                    const float2 hh = ld2(HT_ROW(r), c);
-                    const float out0 = ((fW.x + fE.x) + fS.x) + fN.x;
-                    const float out1 = ((fW.y + fE.y) + fS.y) + fN.y;
-                    const float in0 = ((fE_l + fW.y) + fN_s.x) + fS_n.x;
-                    const float in1 = ((fE.x + fW_r) + fN_s.y) + fS_n.y;
-                    const float nw0 = fmaxf(0.0f, fmaf(in0 - out0, TIMESTEP, w.x));
-                    const float nw1 = fmaxf(0.0f, fmaf(in1 - out1, TIMESTEP, w.y));
-                    st2(W_ROW(t, r), c, nw0, nw1);
-                    st2(H_ROW(t, r), c, nw0 + hh.x, nw1 + hh.y);
-                }
-            }
+    for (int j = 0; j < RING; j++) L.R[j] = ((RING - j) % RING) * FLW + L.c;   // rows s_begin - j
+
+    for (int s = s_begin; s < zc1 + 4 * I; s++) {
+        if (role == 0) {
+            stage_outflow<I, 1>(L, s, zc0, zc1);
+            if (I >= 2) stage_outflow<I, (I >= 2 ? 2 : 1)>(L, s, zc0, zc1);
+        } else if (role == 1) {
+            if (I >= 3) stage_outflow<I, (I >= 3 ? 3 : 1)>(L, s, zc0, zc1);
+            if (I >= 4) stage_outflow<I, (I >= 4 ? 4 : 1)>(L, s, zc0, zc1);
+        } else if (role == 2) {
+            if (I >= 5) stage_outflow<I, (I >= 5 ? 5 : 1)>(L, s, zc0, zc1);
+            stage_velocity<I>(L, s, zc0, zc1, p, xs0);
+        } else {
+            stage_load<I>(L, s, hlo, hhi, p, xs0);
+            if (I >= 2) stage_water<I, 1>(L, s, zc0, zc1);
+            if (I >= 3) stage_water<I, (I >= 3 ? 2 : 1)>(L, s, zc0, zc1);
+            if (I >= 4) stage_water<I, (I >= 4 ? 3 : 1)>(L, s, zc0, zc1);
+            if (I >= 5) stage_water<I, (I >= 5 ? 4 : 1)>(L, s, zc0, zc1);
         }
         __syncthreads();
+        // advance the slot registers: row s+1 takes the slot row s-4 vacates
+        const int r4 = L.R[RING - 1];
+#pragma unroll
+        for (int j = RING - 1; j > 0; j--) L.R[j] = L.R[j - 1];
+        L.R[0] = r4;
     }
-#undef F_ROW
-#undef W_ROW
-#undef H_ROW
-#undef HT_ROW
 }
 
-size_t wave_smem_bytes(int I) { return (size_t)(20 * I + 10 * (I - 1) + 4 * I) * FLW * sizeof(float); }
+size_t wave_smem_bytes(int I) {
+    const int nhc = I - 1 > 1 ? I - 1 : 1;
+    return (size_t)(4 * I + 2 * (I - 1) + nhc) * RING * FLW * sizeof(float);
+}
 
 }  // namespace
 
