@@ -163,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -307,7 +307,7 @@ def run_ours(args):
         "halo_bytes_per_step": int(chain.bytes_exchanged // max(1, args.steps + args.warmup)),
         "clocks": sampler.report() if sampler else None,
     }
-    print(json.dumps(line))
+    print_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -378,6 +378,15 @@ def run_e2e(args, nz, torch, dist, chain, cfg, rank, world, barrier, sampler):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global print_line
+    def print_line(obj):
+        out.write(json.dumps(obj) + "\n")
+        out.flush()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -50,10 +50,12 @@ __global__ void __launch_bounds__(TX) flow_step_kernel(const float* __restrict__
     const float flS = fmaxf(0.0f, (FIRST ? 0.0f : f.fS[i]) + dS);
     const float flN = fmaxf(0.0f, (FIRST ? 0.0f : f.fN[i]) + dN);
     const float sum_ = (flW + flE) + (flS + flN);  // math.csum(float4)
+    // clamp(w0 / (sum*dt), 0, 1) without dividing when the clamp decides (see flowwave_kernels.cu flow_cell)
+    const float d = sum_ * TIMESTEP;
     float K = 0.0f;
     if (sum_ > 0.0f) {
-        K = w0 / (sum_ * TIMESTEP);
-        K = fminf(fmaxf(K, 0.0f), 1.0f);
+        if (w0 >= d) K = 1.0f;
+        else if (w0 > 0.0f) K = fminf(w0 / d, 1.0f);
     }
     // sum_ <= 0 means every flow is 0 already (they are clamped at 0), so flow*0 == the reference's explicit 0
     f.fW[i] = sum_ > 0.0f ? flW * K : 0.0f;

@@ -1,40 +1,41 @@
 // flowwave_kernels.cu — the whole flow map (fill, I x (outflow, water), velocity, normalise) in ONE launch.
 //
-// Same arithmetic, cell for cell, as flow_kernels.cu / the flow map of oracle/noize_oracle.cpp (FlowMapComponents.cs:20-165,
-// FlowMapStage.cs:124-195).  What changes is where the state lives.
+// Same arithmetic, cell for cell, as flow_kernels.cu / the flow map of oracle/noize_oracle.cpp
+// (FlowMapComponents.cs:20-165, FlowMapStage.cs:124-195).  What changes is where the state lives.
 //
 // Per-iteration kernels stream water + 4 flow fields through HBM every iteration (~44 B/cell/iteration,
 // 61 GB at 16384^2 x 5).  But water and flows are DERIVED from the height field, so with all iterations
 // fused only 4 B/cell are read and 4 B/cell written.  A square smem tile cannot hold it (24 B/cell of
-// state, 2I+.. halo on four sides), so the kernel streams instead (wavefront / time-skewed blocking):
+// state, 2I halo on four sides), so the kernel streams instead (wavefront / time-skewed blocking):
 //
-//   a CTA owns a strip of FLW = 256 columns (2I halo columns each side) and walks DOWN a chunk of rows.
+//   a CTA owns a strip of FLW = 128 columns (2I halo columns each side) and walks DOWN a chunk of rows.
 //   At step s it works on one row per pipeline stage, each stage lagging the previous one by 2 rows so that
 //   everything a stage reads was produced in an EARLIER step (one __syncthreads per step):
-//       L    : load height row s                                   (global -> smem ring of 4I rows)
+//       L    : load height row s                                   (global -> smem)
 //       A_t  : outflow step of level t on row s-(4t-2)   reads H_{t-1} = w_{t-1}+h (3 rows), w_{t-1}, f_{t-1}
-//       B_t  : water   step of level t on row s-4t       reads f_t (3 rows), w_{t-1};  writes w_t and H_t
-//       V    : velocity + normalise      on row s-4I     reads f_I (3 rows);           writes the result row
-//   Each level keeps a ring of 5 rows per field (a row is last read 4 steps after it was written).
-//   State per CTA: (20 I + 10 (I-1) + 4 I) rows x 1 KB = 160 KB for I = 5: one 512-thread CTA per SM.
+//       B_t  : water   step of level t on row s-4t       reads f_t (3 rows), w_{t-1}, h;  writes w_t, H_t
+//       V    : velocity + normalise      on row s-4I     reads f_I (3 rows);              writes the result row
+//   Every field of every level is a ring of 5 rows (a row is last read 4 steps after it was written).
+//   State per CTA: 5 x (4I + 3(I-1)) rows x 512 B = 80 KB for I = 5: two 256-thread CTAs per SM, so one CTA computes
+//   while the other waits at its barrier (measured better than one 512-thread CTA on a 256-column strip).
 //
-// Every warp takes (stage, 64-column chunk) work items round-robin; a lane owns 2 adjacent columns, so
-// rows are read with LDS.64 and only the two outer neighbours are scalar loads.
+// Warps are specialised: warp = role; a lane owns 4 adjacent columns (LDS.128 / STS.128, only the
+// two outer neighbours are scalar loads).  Roles are a static, cost-balanced split of the 2I+1 stages.  The
+// byte offsets of the 5 ring slots rotate through 5 registers, so no modulo arithmetic is executed.
 //
 // Clamp-to-edge (TileData.cs:72-77) is applied where the reference applies it: neighbour column/row
 // indices are clamped to the GRID, so a border cell reads its own current-level value.  At strip/chunk
 // edges that are not grid edges the clamp yields garbage that advances one cell per stage and stays inside
-// the 2I-wide halo.
+// the halo.
 #include "nz_common.cuh"
 
 namespace nz {
 namespace {
 
-constexpr int FLW = 256;          // strip width in floats, halo included
-constexpr int FL_THREADS = 512;
-constexpr int FL_WARPS = FL_THREADS / 32;
+constexpr int FLW = 128;          // strip width in floats, halo included
+constexpr int FL_THREADS = 256;
 constexpr int RING = 5;
-constexpr int XCH = FLW / 64;     // 64-column chunks per row
+constexpr int VW = 4;             // columns per lane
 constexpr int FLOW_WAVE_MAX_I = 5;
 constexpr float TIMESTEP = 0.2f;
 constexpr float WATER0 = 0.0001f;  // FillArrayJob value, FlowMapStage.cs:129
@@ -42,15 +43,33 @@ constexpr float WATER0 = 0.0001f;  // FillArrayJob value, FlowMapStage.cs:129
 struct WaveParams {
     const float* h;
     float* out;
-    int W, H, I;
+    int W, H;
     int zc;        // rows per chunk
-    int swi;       // interior columns per strip = FLW - 2*HX
-    int hx;        // halo columns each side (2I rounded up to even)
+    int swi;       // interior columns per strip = FLW - 2*hx
+    int hx;        // halo columns each side (2I rounded up to a multiple of 4)
     float nmin, nrange;
+    float nsign;   // copysign(1, nrange)
+    int zero_ok;   // nrange is finite and non-zero: 0/nrange == 0*nsign
 };
 
-__device__ __forceinline__ float2 ld2(const float* row, int c) { return *reinterpret_cast<const float2*>(row + c); }
-__device__ __forceinline__ void st2(float* row, int c, float a, float b) { *reinterpret_cast<float2*>(row + c) = make_float2(a, b); }
+struct V4 {
+    float v[VW];
+};
+__device__ __forceinline__ V4 ld4(const float* base, int off) {
+    const float4 t = *reinterpret_cast<const float4*>(base + off);
+    V4 r;
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+}
+__device__ __forceinline__ void st4(float* base, int off, const V4& a) {
+    *reinterpret_cast<float4*>(base + off) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ V4 splat(float x) {
+    V4 r;
+#pragma unroll
+    for (int q = 0; q < VW; q++) r.v[q] = x;
+    return r;
+}
 
 // ComputeFlowStep.CalculateCell for one cell (W,E,S,N order; S = z-1, N = z+1)
 __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS, float HN, float w0, float fW, float fE,
@@ -60,10 +79,14 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
     const float flS = fmaxf(0.0f, fS + (H0 - HS));
     const float flN = fmaxf(0.0f, fN + (H0 - HN));
     const float sum_ = (flW + flE) + (flS + flN);
+    // K = clamp(w0 / (sum*dt), 0, 1).  The IEEE division's slow path (zero / denormal operands) costs ~60
+    // instructions, and drained cells (w0 == 0) are common, so the two clamped outcomes are decided without
+    // dividing: w0 >= d  =>  fl(w0/d) >= 1  => 1 ;  w0 <= 0  =>  quotient <= 0  => 0.  Same bits as the plain form.
+    const float d = sum_ * TIMESTEP;
     float K = 0.0f;
     if (sum_ > 0.0f) {
-        K = w0 / (sum_ * TIMESTEP);
-        K = fminf(fmaxf(K, 0.0f), 1.0f);
+        if (w0 >= d) K = 1.0f;
+        else if (w0 > 0.0f) K = fminf(w0 / d, 1.0f);
     }
     const bool pos = sum_ > 0.0f;
     oW = pos ? flW * K : 0.0f;
@@ -91,8 +114,8 @@ template <int I> struct Rings {
 struct Lane {
     float* sm;
     int R[RING];   // R[j] = float offset (ring-relative) of the slot of row s-j, plus this lane's first column
-    int dl, dr;    // column offsets of the clamped west neighbour of cell c (-1 or 0) and east neighbour of c+1 (+2 or +1)
-    int c;         // first of this lane's two strip columns
+    int dl, dr;    // offsets (from this lane's first column) of the clamped west / east outer neighbours
+    int c;         // first of this lane's VW strip columns
     int H;         // grid rows
 };
 
@@ -113,32 +136,38 @@ __device__ __forceinline__ void stage_outflow(const Lane& L, int s, int zc0, int
     if (r < lo || r >= hi) return;
     const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
     float* sm = L.sm;
-    float2 H0, HS, HN, w0, fW, fE, fS, fN;
+    V4 H0, HS, HN, w0, fW, fE, fS, fN;
     float HWl, HEr;
     if (T == 1) {
-        const float2 a = ld2(sm + RG::HC(0), o0), b = ld2(sm + RG::HC(0), os), d = ld2(sm + RG::HC(0), on);
-        H0 = make_float2(WATER0 + a.x, WATER0 + a.y);
-        HS = make_float2(WATER0 + b.x, WATER0 + b.y);
-        HN = make_float2(WATER0 + d.x, WATER0 + d.y);
+        // level 0: water == 1e-4 everywhere, flows == 0: H_0 = 1e-4 + h computed on the fly
+        const V4 a = ld4(sm + RG::HC(0), o0), b = ld4(sm + RG::HC(0), os), d = ld4(sm + RG::HC(0), on);
+#pragma unroll
+        for (int q = 0; q < VW; q++) {
+            H0.v[q] = WATER0 + a.v[q];
+            HS.v[q] = WATER0 + b.v[q];
+            HN.v[q] = WATER0 + d.v[q];
+        }
         HWl = WATER0 + sm[RG::HC(0) + o0 + L.dl];
         HEr = WATER0 + sm[RG::HC(0) + o0 + L.dr];
-        w0 = make_float2(WATER0, WATER0);
-        fW = fE = fS = fN = make_float2(0.0f, 0.0f);
+        w0 = splat(WATER0);
+        fW = fE = fS = fN = splat(0.0f);
     } else {
         constexpr int P = T > 1 ? T - 1 : 1;
-        H0 = ld2(sm + RG::Ht(P), o0); HS = ld2(sm + RG::Ht(P), os); HN = ld2(sm + RG::Ht(P), on);
+        H0 = ld4(sm + RG::Ht(P), o0); HS = ld4(sm + RG::Ht(P), os); HN = ld4(sm + RG::Ht(P), on);
         HWl = sm[RG::Ht(P) + o0 + L.dl]; HEr = sm[RG::Ht(P) + o0 + L.dr];
-        w0 = ld2(sm + RG::Wt(P), o0);
-        fW = ld2(sm + RG::F(P, 0), o0); fE = ld2(sm + RG::F(P, 1), o0);
-        fS = ld2(sm + RG::F(P, 2), o0); fN = ld2(sm + RG::F(P, 3), o0);
+        w0 = ld4(sm + RG::Wt(P), o0);
+        fW = ld4(sm + RG::F(P, 0), o0); fE = ld4(sm + RG::F(P, 1), o0);
+        fS = ld4(sm + RG::F(P, 2), o0); fN = ld4(sm + RG::F(P, 3), o0);
     }
-    float oW0, oE0, oS0, oN0, oW1, oE1, oS1, oN1;
-    flow_cell(H0.x, HWl, H0.y, HS.x, HN.x, w0.x, fW.x, fE.x, fS.x, fN.x, oW0, oE0, oS0, oN0);
-    flow_cell(H0.y, H0.x, HEr, HS.y, HN.y, w0.y, fW.y, fE.y, fS.y, fN.y, oW1, oE1, oS1, oN1);
-    st2(sm + RG::F(T, 0), o0, oW0, oW1);
-    st2(sm + RG::F(T, 1), o0, oE0, oE1);
-    st2(sm + RG::F(T, 2), o0, oS0, oS1);
-    st2(sm + RG::F(T, 3), o0, oN0, oN1);
+    V4 oW, oE, oS, oN;
+#pragma unroll
+    for (int q = 0; q < VW; q++)
+        flow_cell(H0.v[q], q == 0 ? HWl : H0.v[q > 0 ? q - 1 : 0], q == VW - 1 ? HEr : H0.v[q < VW - 1 ? q + 1 : 0], HS.v[q],
+                  HN.v[q], w0.v[q], fW.v[q], fE.v[q], fS.v[q], fN.v[q], oW.v[q], oE.v[q], oS.v[q], oN.v[q]);
+    st4(sm + RG::F(T, 0), o0, oW);
+    st4(sm + RG::F(T, 1), o0, oE);
+    st4(sm + RG::F(T, 2), o0, oS);
+    st4(sm + RG::F(T, 3), o0, oN);
 }
 
 template <int I, int T>
@@ -150,22 +179,24 @@ __device__ __forceinline__ void stage_water(const Lane& L, int s, int zc0, int z
     if (r < lo || r >= hi) return;
     const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
     float* sm = L.sm;
-    const float2 fW = ld2(sm + RG::F(T, 0), o0), fE = ld2(sm + RG::F(T, 1), o0);
-    const float2 fS = ld2(sm + RG::F(T, 2), o0), fN = ld2(sm + RG::F(T, 3), o0);
+    const V4 fW = ld4(sm + RG::F(T, 0), o0), fE = ld4(sm + RG::F(T, 1), o0);
+    const V4 fS = ld4(sm + RG::F(T, 2), o0), fN = ld4(sm + RG::F(T, 3), o0);
     const float fE_l = sm[RG::F(T, 1) + o0 + L.dl], fW_r = sm[RG::F(T, 0) + o0 + L.dr];
-    const float2 fN_s = ld2(sm + RG::F(T, 3), os), fS_n = ld2(sm + RG::F(T, 2), on);
+    const V4 fN_s = ld4(sm + RG::F(T, 3), os), fS_n = ld4(sm + RG::F(T, 2), on);
     constexpr int P = T > 1 ? T - 1 : 1;
-    const float2 w = (T == 1) ? make_float2(WATER0, WATER0) : ld2(sm + RG::Wt(P), o0);
-    const float2 hh = ld2(sm + RG::HC(T - 1), o0);
-    const float out0 = ((fW.x + fE.x) + fS.x) + fN.x;
-    const float out1 = ((fW.y + fE.y) + fS.y) + fN.y;
-    const float in0 = ((fE_l + fW.y) + fN_s.x) + fS_n.x;
-    const float in1 = ((fE.x + fW_r) + fN_s.y) + fS_n.y;
-    const float nw0 = fmaxf(0.0f, fmaf(in0 - out0, TIMESTEP, w.x));
-    const float nw1 = fmaxf(0.0f, fmaf(in1 - out1, TIMESTEP, w.y));
-    st2(sm + RG::Wt(T), o0, nw0, nw1);
-    st2(sm + RG::Ht(T), o0, nw0 + hh.x, nw1 + hh.y);
-    if (T + 1 < I) st2(sm + RG::HC(T < I - 1 ? T : 0), o0, hh.x, hh.y);   // hand the height row to the next water stage
+    const V4 w = (T == 1) ? splat(WATER0) : ld4(sm + RG::Wt(P), o0);
+    const V4 hh = ld4(sm + RG::HC(T - 1), o0);
+    V4 nw, nH;
+#pragma unroll
+    for (int q = 0; q < VW; q++) {
+        const float out = ((fW.v[q] + fE.v[q]) + fS.v[q]) + fN.v[q];
+        const float in = (((q == 0 ? fE_l : fE.v[q > 0 ? q - 1 : 0]) + (q == VW - 1 ? fW_r : fW.v[q < VW - 1 ? q + 1 : 0])) + fN_s.v[q]) + fS_n.v[q];
+        nw.v[q] = fmaxf(0.0f, fmaf(in - out, TIMESTEP, w.v[q]));
+        nH.v[q] = nw.v[q] + hh.v[q];
+    }
+    st4(sm + RG::Wt(T), o0, nw);
+    st4(sm + RG::Ht(T), o0, nH);
+    if (T + 1 < I) st4(sm + RG::HC(T < I - 1 ? T : 0), o0, hh);   // hand the height row to the next water stage
 }
 
 template <int I>
@@ -176,60 +207,65 @@ __device__ __forceinline__ void stage_velocity(const Lane& L, int s, int zc0, in
     if (r < zc0 || r >= zc1) return;
     const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
     float* sm = L.sm;
-    const float2 fW = ld2(sm + RG::F(I, 0), o0), fE = ld2(sm + RG::F(I, 1), o0);
+    const V4 fW = ld4(sm + RG::F(I, 0), o0), fE = ld4(sm + RG::F(I, 1), o0);
     const float fE_l = sm[RG::F(I, 1) + o0 + L.dl], fW_r = sm[RG::F(I, 0) + o0 + L.dr];
-    const float2 fS = ld2(sm + RG::F(I, 2), o0), fN = ld2(sm + RG::F(I, 3), o0);
-    const float2 fS_n = ld2(sm + RG::F(I, 2), on), fN_s = ld2(sm + RG::F(I, 3), os);
-    float res[2];
+    const V4 fS = ld4(sm + RG::F(I, 2), o0), fN = ld4(sm + RG::F(I, 3), o0);
+    const V4 fS_n = ld4(sm + RG::F(I, 2), on), fN_s = ld4(sm + RG::F(I, 3), os);
+    V4 res;
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const float dl = (q ? fE.x : fE_l) - (q ? fW.y : fW.x);
-        const float dr = (q ? fE.y : fE.x) - (q ? fW_r : fW.y);
-        const float dt = (q ? fS_n.y : fS_n.x) - (q ? fN.y : fN.x);
-        const float db = (q ? fS.y : fS.x) - (q ? fN_s.y : fN_s.x);
+    for (int q = 0; q < VW; q++) {
+        const float dl = (q == 0 ? fE_l : fE.v[q > 0 ? q - 1 : 0]) - fW.v[q];
+        const float dr = fE.v[q] - (q == VW - 1 ? fW_r : fW.v[q < VW - 1 ? q + 1 : 0]);
+        const float dt = fS_n.v[q] - fN.v[q];
+        const float db = fS.v[q] - fN_s.v[q];
         const float vx = (dl + dr) * 0.5f, vy = (dt + db) * 0.5f;
         float v = sqrtf(fmaf(vy, vy, vx * vx));
         if (p.nrange < 1e-12f) v = 0.0f;
-        res[q] = (v - p.nmin) / p.nrange;
+        const float t = v - p.nmin;
+        // still water (t == +-0) is common and 0/x takes the division's slow path; 0/x == 0 * sign(x) for finite x != 0
+        res.v[q] = (t == 0.0f && p.zero_ok) ? t * p.nsign : t / p.nrange;
     }
     const int gx = xs0 + L.c;
-    if (L.c >= p.hx && L.c < FLW - p.hx && gx + 1 < p.W)
-        *reinterpret_cast<float2*>(p.out + (size_t)r * p.W + gx) = make_float2(res[0], res[1]);
+    if (L.c >= p.hx && L.c < FLW - p.hx && gx + VW - 1 < p.W)
+        *reinterpret_cast<float4*>(p.out + (size_t)r * p.W + gx) = make_float4(res.v[0], res.v[1], res.v[2], res.v[3]);
 }
 
-template <int I>
-__device__ __forceinline__ void stage_load(const Lane& L, int s, int hlo, int hhi, const WaveParams& p, int xs0) {
-    using RG = Rings<I>;
-    if (s < hlo || s >= hhi) return;
-    const float* g = p.h + (size_t)s * p.W;
-    const int gx = xs0 + L.c;
-    float a, b;
-    if (gx >= 0 && gx + 1 < p.W) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(g + gx));
-        a = v.x; b = v.y;
-    } else {
-        a = __ldg(g + min(max(gx, 0), p.W - 1));
-        b = __ldg(g + min(max(gx + 1, 0), p.W - 1));
+// Loader: the global read of a height row has ~1 us of latency, far more than a step takes, so the row that is
+// stored to shared memory at step s was requested PF steps earlier and waited in registers.
+constexpr int PF = 4;
+__device__ __forceinline__ V4 load_row(const Lane& L, int row, int hlo, int hhi, const WaveParams& p, int xs0) {
+    V4 a = splat(0.0f);
+    if (row >= hlo && row < hhi) {
+        const float* g = p.h + (size_t)row * p.W;
+        const int gx = xs0 + L.c;
+        if (gx >= 0 && gx + VW - 1 < p.W) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(g + gx));
+            a.v[0] = t.x; a.v[1] = t.y; a.v[2] = t.z; a.v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < VW; q++) a.v[q] = __ldg(g + min(max(gx + q, 0), p.W - 1));
+        }
     }
-    st2(L.sm + RG::HC(0), L.R[0], a, b);
+    return a;
 }
 
-// Static, cost-balanced roles: the 4 warps of a 64-column chunk split the 2I+1 stages of a step
-//   role 0: outflow 1,2   role 1: outflow 3,4   role 2: outflow 5 + velocity   role 3: water 1..I-1 + loader
+// Static, cost-balanced roles, one warp each (32 lanes x 4 columns = the 128-column strip).
+//   role 0..4: outflow of level role+1      role 5: velocity
+//   role 6: loader + water 1,2              role 7: water 3,4
 template <int I>
-__global__ void __launch_bounds__(FL_THREADS, 1) flow_wave_kernel(WaveParams p) {
+__global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) {
     extern __shared__ __align__(16) float sm[];
     const int H = p.H;
-    const int xs0 = blockIdx.x * p.swi - p.hx;           // grid x of strip column 0 (even)
+    const int xs0 = blockIdx.x * p.swi - p.hx;           // grid x of strip column 0 (multiple of 4)
     const int zc0 = blockIdx.y * p.zc, zc1 = min(zc0 + p.zc, H);
     const int cmin = max(0, -xs0), cmax = min(FLW - 1, p.W - 1 - xs0);   // strip columns inside the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = warp & 3;
+    const int role = warp;
     Lane L;
     L.sm = sm;
-    L.c = (warp >> 2) * 64 + lane * 2;
+    L.c = lane * VW;
     L.dl = max(L.c - 1, cmin) - L.c;
-    L.dr = min(L.c + 2, cmax) - L.c;
+    L.dr = min(L.c + VW, cmax) - L.c;
     L.H = H;
     const int hlo = max(0, zc0 - 2 * I), hhi = min(H, zc1 + 2 * I);
     // first step, rounded down to a multiple of RING so that slot(s) = s mod RING starts at 0
@@ -238,22 +274,32 @@ __global__ void __launch_bounds__(FL_THREADS, 1) flow_wave_kernel(WaveParams p) 
 #pragma unroll
     for (int j = 0; j < RING; j++) L.R[j] = ((RING - j) % RING) * FLW + L.c;   // rows s_begin - j
 
+    V4 pf[PF];
+    if (role == 6) {
+#pragma unroll
+        for (int j = 0; j < PF; j++) pf[j] = load_row(L, s_begin + j, hlo, hhi, p, xs0);
+    }
+
     for (int s = s_begin; s < zc1 + 4 * I; s++) {
-        if (role == 0) {
-            stage_outflow<I, 1>(L, s, zc0, zc1);
-            if (I >= 2) stage_outflow<I, (I >= 2 ? 2 : 1)>(L, s, zc0, zc1);
-        } else if (role == 1) {
-            if (I >= 3) stage_outflow<I, (I >= 3 ? 3 : 1)>(L, s, zc0, zc1);
-            if (I >= 4) stage_outflow<I, (I >= 4 ? 4 : 1)>(L, s, zc0, zc1);
-        } else if (role == 2) {
-            if (I >= 5) stage_outflow<I, (I >= 5 ? 5 : 1)>(L, s, zc0, zc1);
-            stage_velocity<I>(L, s, zc0, zc1, p, xs0);
-        } else {
-            stage_load<I>(L, s, hlo, hhi, p, xs0);
-            if (I >= 2) stage_water<I, 1>(L, s, zc0, zc1);
-            if (I >= 3) stage_water<I, (I >= 3 ? 2 : 1)>(L, s, zc0, zc1);
-            if (I >= 4) stage_water<I, (I >= 4 ? 3 : 1)>(L, s, zc0, zc1);
-            if (I >= 5) stage_water<I, (I >= 5 ? 4 : 1)>(L, s, zc0, zc1);
+        switch (role) {
+            case 0: stage_outflow<I, 1>(L, s, zc0, zc1); break;
+            case 1: if (I >= 2) stage_outflow<I, (I >= 2 ? 2 : 1)>(L, s, zc0, zc1); break;
+            case 2: if (I >= 3) stage_outflow<I, (I >= 3 ? 3 : 1)>(L, s, zc0, zc1); break;
+            case 3: if (I >= 4) stage_outflow<I, (I >= 4 ? 4 : 1)>(L, s, zc0, zc1); break;
+            case 4: if (I >= 5) stage_outflow<I, (I >= 5 ? 5 : 1)>(L, s, zc0, zc1); break;
+            case 5: stage_velocity<I>(L, s, zc0, zc1, p, xs0); break;
+            case 6:
+                st4(sm + Rings<I>::HC(0), L.R[0], pf[0]);          // row s, requested PF steps ago
+#pragma unroll
+                for (int j = 0; j + 1 < PF; j++) pf[j] = pf[j + 1];
+                pf[PF - 1] = load_row(L, s + PF, hlo, hhi, p, xs0);
+                if (I >= 2) stage_water<I, 1>(L, s, zc0, zc1);
+                if (I >= 3) stage_water<I, (I >= 3 ? 2 : 1)>(L, s, zc0, zc1);
+                break;
+            default:
+                if (I >= 4) stage_water<I, (I >= 4 ? 3 : 1)>(L, s, zc0, zc1);
+                if (I >= 5) stage_water<I, (I >= 5 ? 4 : 1)>(L, s, zc0, zc1);
+                break;
         }
         __syncthreads();
         // advance the slot registers: row s+1 takes the slot row s-4 vacates
@@ -271,9 +317,10 @@ size_t wave_smem_bytes(int I) {
 
 }  // namespace
 
+// a, b: the two grid pointers (may be null when only the shape is being asked about)
 bool flow_wave_supported(int width, int rows, int iterations, const void* a, const void* b) {
-    return iterations >= 1 && iterations <= FLOW_WAVE_MAX_I && (width & 1) == 0 && rows >= 1 &&
-           (((uintptr_t)a | (uintptr_t)b) & 7) == 0;
+    return iterations >= 1 && iterations <= FLOW_WAVE_MAX_I && (width & 3) == 0 && rows >= 1 &&
+           (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
 }
 
 // d_out must not alias d_height
@@ -290,11 +337,13 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
     }
     const int I = iterations;
     WaveParams p;
-    p.h = d_height; p.out = d_out; p.W = width; p.H = rows; p.I = I;
-    p.hx = (2 * I + 1) & ~1;
+    p.h = d_height; p.out = d_out; p.W = width; p.H = rows;
+    p.hx = (2 * I + 3) & ~3;
     p.swi = FLW - 2 * p.hx;
     p.nmin = norm_min;
     p.nrange = norm_max - norm_min;
+    p.nsign = copysignf(1.0f, p.nrange);
+    p.zero_ok = (p.nrange != 0.0f) && isfinite(p.nrange);
     const int strips = cdiv(width, p.swi);
     // rows per chunk: long enough to amortise the 6I-row pipeline fill, and a CTA count that fills whole waves
     int sms = 148;
@@ -306,7 +355,7 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
         if (zc < 64 && nz > 1) break;
         const long long ctas = (long long)strips * cdiv(rows, zc);
         const long long waves = (ctas + sms - 1) / sms;
-        const double cost = (double)waves * (zc + 6 * I);   // steps executed by the busiest SM
+        const double cost = (double)waves * (zc + 6 * I + RING);   // steps executed by the busiest SM
         if (cost < best_cost) { best_cost = cost; best_nz = nz; }
     }
     p.zc = cdiv(rows, best_nz);

@@ -54,10 +54,31 @@ __device__ __forceinline__ float permute_centered(float x) {
     return fmaf(-289.0f, q, u);
 }
 
+// Gradient fold of one hash value p in [0,288]: x = 2*frac(p/41) - 1, h = |x| - 0.5, a0 = x - floor(x + 0.5).
+// It is a pure function of p, so the simplex kernel evaluates it once per CTA for all 290 values into shared
+// memory (build_gradient_table) and the octave loop replaces 8 instructions (one of them an XU floor) per
+// corner by a conversion and one LDS.64.  Same operations, same bits.
+constexpr int NZ_GTAB = 290;
+__device__ __forceinline__ float2 gradient_fold(float p) {
+    const float gx = fmaf(2.0f, fracf_(p * 0.024390243902439f), -1.0f);
+    const float h = fabsf(gx) - 0.5f;
+    const float a0 = gx - ((gx + NZ_MAGIC) - NZ_MAGIC);
+    return make_float2(a0, h);
+}
+__device__ __forceinline__ void build_gradient_table(float2* gtab) {
+    for (int i = threadIdx.x; i < NZ_GTAB; i += blockDim.x) gtab[i] = gradient_fold((float)i);
+    __syncthreads();
+}
+__device__ __forceinline__ float2 gradient_lookup(const float2* gtab, float p) {
+    // p is an exact integer in [0,288] wherever the hash is exact; saturate so that garbage coordinates
+    // (lattice index beyond 2^22) can never index outside the table
+    return gtab[min(__float2uint_rz(p), (unsigned)(NZ_GTAB - 1))];
+}
+
 // returns dot(m, g), i.e. snoise(float2) / 130 (the getter folds the factor, see basis_value)
-__device__ __forceinline__ float snoise2_raw(float vx, float vy) {
+__device__ __forceinline__ float snoise2_raw(float vx, float vy, const float2* gtab) {
     const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
-    const float Cz = -0.577350269189626f, Cw = 0.024390243902439f;
+    const float Cz = -0.577350269189626f;
     float s = dot2(vx, vy, Cy, Cy);
     float ix = floorf(vx + s), iy = floorf(vy + s);
     float t = dot2(ix, iy, Cx, Cx);
@@ -69,20 +90,18 @@ __device__ __forceinline__ float snoise2_raw(float vx, float vy) {
     ix = mod289(ix);
     iy = mod289(iy);
     float py0 = permute_centered(iy), py1 = permute_centered(iy + 1.0f);
-    float p0 = permute(py0 + ix);
-    float p1 = permute((xgty ? py0 : py1) + ix + i1x);
-    float p2 = permute(py1 + ix + 1.0f);
+    const float hA = py0 + ix, hB = py1 + ix;     // (py + ix) + i1x with i1x in {0,1}: pick, do not recompute
+    float p0 = permute(hA);
+    float p1 = permute(xgty ? hA + 1.0f : hB);
+    float p2 = permute(hB + 1.0f);
     float m0 = fmaxf(fmaf(-x0y, x0y, fmaf(-x0x, x0x, 0.5f)), 0.0f);
     float m1 = fmaxf(fmaf(-x1y, x1y, fmaf(-x1x, x1x, 0.5f)), 0.0f);
     float m2 = fmaxf(fmaf(-x2y, x2y, fmaf(-x2x, x2x, 0.5f)), 0.0f);
     m0 = m0 * m0; m0 = m0 * m0;
     m1 = m1 * m1; m1 = m1 * m1;
     m2 = m2 * m2; m2 = m2 * m2;
-    float gx0 = fmaf(2.0f, fracf_(p0 * Cw), -1.0f), gx1 = fmaf(2.0f, fracf_(p1 * Cw), -1.0f),
-          gx2 = fmaf(2.0f, fracf_(p2 * Cw), -1.0f);
-    float h0 = fabsf(gx0) - 0.5f, h1 = fabsf(gx1) - 0.5f, h2 = fabsf(gx2) - 0.5f;
-    float a0 = gx0 - ((gx0 + NZ_MAGIC) - NZ_MAGIC), a1 = gx1 - ((gx1 + NZ_MAGIC) - NZ_MAGIC),
-          a2 = gx2 - ((gx2 + NZ_MAGIC) - NZ_MAGIC);
+    const float2 gr0 = gradient_lookup(gtab, p0), gr1 = gradient_lookup(gtab, p1), gr2 = gradient_lookup(gtab, p2);
+    const float a0 = gr0.x, h0 = gr0.y, a1 = gr1.x, h1 = gr1.y, a2 = gr2.x, h2 = gr2.y;
     m0 = m0 * taylorInvSqrt(fmaf(h0, h0, a0 * a0));
     m1 = m1 * taylorInvSqrt(fmaf(h1, h1, a1 * a1));
     m2 = m2 * taylorInvSqrt(fmaf(h2, h2, a2 * a2));
@@ -277,7 +296,7 @@ __device__ float cnoise3(float Px, float Py, float Pz) {
 
 // ---- basis getters, Fractal.cs:141-278 ----------------------------------------------------------
 template <int TYPE>
-__device__ __forceinline__ float basis_value(float x, float z) {
+__device__ __forceinline__ float basis_value(float x, float z, const float2* gtab) {
     if (TYPE == NZ_NOISE_SIN) {
         float vx = fmaf(0.5f, sinf(x), 0.5f), vz = fmaf(0.5f, sinf(z), 0.5f);
         return vx * vz;
@@ -286,7 +305,7 @@ __device__ __forceinline__ float basis_value(float x, float z) {
     } else if (TYPE == NZ_NOISE_PERIODIC_PERLIN) {
         return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.0f));
     } else if (TYPE == NZ_NOISE_SIMPLEX) {
-        return fmaf(65.0f, snoise2_raw(x, z), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
+        return fmaf(65.0f, snoise2_raw(x, z, gtab), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
     } else if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) {
         return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.62f));
     } else if (TYPE == NZ_NOISE_CELLULAR) {
@@ -305,6 +324,8 @@ constexpr int NZ_FBM_THREADS = 128;
 
 template <int TYPE, int CELLS>
 __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__ dst, FractalParams p) {
+    __shared__ float2 gtab[TYPE == NZ_NOISE_SIMPLEX ? NZ_GTAB : 1];
+    if (TYPE == NZ_NOISE_SIMPLEX) build_gradient_table(gtab);
     const int r = blockIdx.y;
     const int xbase = blockIdx.x * (NZ_FBM_THREADS * CELLS) + threadIdx.x;
     const float zi = ((float)(p.z_first + r) + p.posz) / p.noise_size;
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
     for (int i = 0; i < p.octaves; i++) {
         const float zV = f * zi;
 #pragma unroll
-        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE>(f * xi[c], zV), t[c]);
+        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE>(f * xi[c], zV, gtab), t[c]);
         detune += p.detune_rate;
         f *= (p.stepdown - detune);
         a *= p.G;
@@ -361,7 +382,7 @@ int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cud
             // cells per thread is a tuning knob (NZ_FBM_CELLS=1|2|4 overrides the default while profiling)
             static const int cells = [] {
                 const char* e = getenv("NZ_FBM_CELLS");
-                return e ? atoi(e) : 2;
+                return e ? atoi(e) : 4;
             }();
             if (cells == 1) return launch_typed<NZ_NOISE_SIMPLEX, 1>(d_dst, p, s);
             if (cells == 4) return launch_typed<NZ_NOISE_SIMPLEX, 4>(d_dst, p, s);

@@ -30,7 +30,7 @@ namespace nz {
 namespace {
 
 constexpr int FW = 128;       // tile width  (floats), halo included
-constexpr int FH = 96;        // tile height (rows),   halo included
+constexpr int FH = 64;        // tile height (rows),   halo included
 constexpr int HALO = 8;
 constexpr int OW = FW - 2 * HALO;  // 112
 constexpr int OH = FH - 2 * HALO;  // 80
@@ -75,7 +75,7 @@ __device__ __forceinline__ float2 xrow(const float* __restrict__ in, int row, in
 }
 
 template <int R, bool SCALE>
-__global__ void __launch_bounds__(FTHREADS, 2)
+__global__ void __launch_bounds__(FTHREADS, 3)
 sep_fused_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, int T, float factor,
                  TapsR<R> kx, TapsR<R> kz, int force_scalar) {
     extern __shared__ __align__(16) float smem[];
