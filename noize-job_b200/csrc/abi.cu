@@ -323,6 +323,18 @@ static int32_t fractal_params(FractalParams* p, int width, int rows, int z_first
     p->detune_rate = detune;
     p->G = exp2f(-hurst);                                // Fractal.cs:118
     p->norm = nz_fractal_norm_value(hurst, octaves);     // Fractal.cs:31-40
+    // bound on the simplex lattice index |floor(v + (vx+vy)*0.366)| <= 1.74*max|v| over the tile and all octaves
+    {
+        double f = 1.0, fmax = 1.0, det = 0.0;
+        for (int i = 0; i < octaves; i++) {
+            det += detune;
+            f *= ((double)stepdown - det);
+            if (fabs(f) > fmax) fmax = fabs(f);
+        }
+        const double cx = fabs((double)xpos) + width, cz = fabs((double)zpos) + fabs((double)z_first) + rows;
+        const double vmax = fmax * (cx > cz ? cx : cz) / fabs((double)noise_size);
+        p->fast_hash = (1.74 * vmax + 2.0) < 2097152.0;   // also false for NaN/inf parameters
+    }
     return NZ_OK;
 }
 

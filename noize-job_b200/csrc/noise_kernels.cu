@@ -76,6 +76,7 @@ __device__ __forceinline__ float2 gradient_lookup(const float2* gtab, float p) {
 }
 
 // returns dot(m, g), i.e. snoise(float2) / 130 (the getter folds the factor, see basis_value)
+template <bool FAST>
 __device__ __forceinline__ float snoise2_raw(float vx, float vy, const float2* gtab) {
     const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
     const float Cz = -0.577350269189626f;
@@ -87,8 +88,15 @@ __device__ __forceinline__ float snoise2_raw(float vx, float vy, const float2* g
     float i1x = xgty ? 1.0f : 0.0f, i1y = xgty ? 0.0f : 1.0f;
     float x1x = x0x + Cx - i1x, x1y = x0y + Cx - i1y;
     float x2x = x0x + Cz, x2y = x0y + Cz;
-    ix = mod289(ix);
-    iy = mod289(iy);
+    if (FAST) {
+        // lattice indices below 2^21 (the host checks the tile): the centred residue is congruent to the
+        // canonical one and saves two more XU floors; the outer hash canonicalises
+        ix = fmaf(-289.0f, fmaf(ix, 1.0f / 289.0f, NZ_MAGIC) - NZ_MAGIC, ix);
+        iy = fmaf(-289.0f, fmaf(iy, 1.0f / 289.0f, NZ_MAGIC) - NZ_MAGIC, iy);
+    } else {
+        ix = mod289(ix);
+        iy = mod289(iy);
+    }
     float py0 = permute_centered(iy), py1 = permute_centered(iy + 1.0f);
     const float hA = py0 + ix, hB = py1 + ix;     // (py + ix) + i1x with i1x in {0,1}: pick, do not recompute
     float p0 = permute(hA);
@@ -295,7 +303,7 @@ __device__ float cnoise3(float Px, float Py, float Pz) {
 }
 
 // ---- basis getters, Fractal.cs:141-278 ----------------------------------------------------------
-template <int TYPE>
+template <int TYPE, bool FAST>
 __device__ __forceinline__ float basis_value(float x, float z, const float2* gtab) {
     if (TYPE == NZ_NOISE_SIN) {
         float vx = fmaf(0.5f, sinf(x), 0.5f), vz = fmaf(0.5f, sinf(z), 0.5f);
@@ -305,7 +313,7 @@ __device__ __forceinline__ float basis_value(float x, float z, const float2* gta
     } else if (TYPE == NZ_NOISE_PERIODIC_PERLIN) {
         return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.0f));
     } else if (TYPE == NZ_NOISE_SIMPLEX) {
-        return fmaf(65.0f, snoise2_raw(x, z, gtab), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
+        return fmaf(65.0f, snoise2_raw<FAST>(x, z, gtab), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
     } else if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) {
         return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.62f));
     } else if (TYPE == NZ_NOISE_CELLULAR) {
@@ -322,7 +330,7 @@ __device__ __forceinline__ float basis_value(float x, float z, const float2* gta
 // ---- the fBm kernel: FractalGenerator.NoiseValue / Execute, Fractal.cs:114-138 -------------------
 constexpr int NZ_FBM_THREADS = 128;
 
-template <int TYPE, int CELLS>
+template <int TYPE, int CELLS, bool FAST>
 __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__ dst, FractalParams p) {
     __shared__ float2 gtab[TYPE == NZ_NOISE_SIMPLEX ? NZ_GTAB : 1];
     if (TYPE == NZ_NOISE_SIMPLEX) build_gradient_table(gtab);
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
     for (int i = 0; i < p.octaves; i++) {
         const float zV = f * zi;
 #pragma unroll
-        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE>(f * xi[c], zV, gtab), t[c]);
+        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE, FAST>(f * xi[c], zV, gtab), t[c]);
         detune += p.detune_rate;
         f *= (p.stepdown - detune);
         a *= p.G;
@@ -355,7 +363,10 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
 template <int TYPE, int CELLS>
 int32_t launch_typed(float* d_dst, const FractalParams& p, cudaStream_t s) {
     dim3 grid(cdiv(p.width, NZ_FBM_THREADS * CELLS), p.rows);
-    fbm_kernel<TYPE, CELLS><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
+    if (TYPE == NZ_NOISE_SIMPLEX && p.fast_hash)
+        fbm_kernel<TYPE, CELLS, true><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
+    else
+        fbm_kernel<TYPE, CELLS, false><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
     NZ_LAUNCHED();
     return NZ_OK;
 }

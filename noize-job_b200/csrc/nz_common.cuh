@@ -51,6 +51,7 @@ struct FractalParams {
     float start_amp, stepdown, detune_rate;
     float G;     // exp2f(-hurst), computed on the host with the same libm call the oracle uses
     float norm;  // CalcFractalNormValue
+    int fast_hash;  // every lattice index of this launch is below 2^21 (simplex may use the magic-number residue)
 };
 int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
 

@@ -353,3 +353,10 @@ def test_kernels_actually_launch(nz):
     assert nz.host.kernel_launch_count() == before + 1
     t = nz.host.last_timing()
     assert t["kernel_launches"] == 1 and t["ms_kernel"] > 0
+
+
+def test_simplex_beyond_the_fast_hash_domain_uses_the_exact_residue(nz, oracle):
+    # lattice indices above 2^21 switch the kernel to the float-floor mod289 (same as the oracle)
+    got = gpu_fractal(nz, 64, 3, 30000, 30000, octaves=24, noise_size=5, stepdown=2.2)
+    ref = ref_fractal(oracle, 64, 3, 30000, 30000, octaves=24, noise_size=5, stepdown=2.2)
+    assert np.abs(got - ref).max() <= TOL_NOISE
