@@ -131,6 +131,44 @@ __global__ void __launch_bounds__(MTHREADS) min_window_kernel(const float* __res
     }
 }
 
+// Register/shuffle variant for small windows (N <= 8, the "Value Erosion x5" of the README is N = 5).  A lane owns one
+// column and walks down a chunk of rows keeping the last N+1 loaded values in registers (Z window), then takes the
+// trailing X window across lanes by log-step doubling with shuffles.  A warp's 32 lanes overlap the previous warp's by
+// N columns, so no shared memory and no block synchronisation is needed; loads and stores are row-contiguous.
+constexpr int MWALK_ROWS = 128, MWALK_THREADS = 256, MWALK_MAX_N = 8;
+
+template <int N>
+__global__ void __launch_bounds__(MWALK_THREADS) min_walk_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                 int width, int rows) {
+    constexpr int USE = 32 - N;                                   // columns a warp actually produces
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wx0 = (blockIdx.x * (MWALK_THREADS / 32) + warp) * USE;  // first produced column of this warp
+    const int x = wx0 - N + lane;                                  // this lane's column (may be < 0: clamp)
+    if (wx0 >= width) return;
+    const int xc = clampi(x, 0, width - 1);
+    const int z0 = blockIdx.y * MWALK_ROWS, z1 = min(z0 + MWALK_ROWS, rows);
+    float win[N + 1];   // win[j] = value of row (z - N + j), clamped at row 0
+#pragma unroll
+    for (int j = 0; j < N; j++) win[j + 1] = __ldg(src + (size_t)max(z0 - N + j, 0) * width + xc);
+    for (int z = z0; z < z1; z++) {
+#pragma unroll
+        for (int j = 0; j < N; j++) win[j] = win[j + 1];
+        win[N] = __ldg(src + (size_t)z * width + xc);
+        float m = win[0];
+#pragma unroll
+        for (int j = 1; j <= N; j++) m = fminf(m, win[j]);
+        // trailing window of N+1 lanes: doubling, then one shifted combine
+        int span = 1;   // m currently covers `span` trailing lanes
+#pragma unroll
+        for (int k = 1; 2 * k <= N + 1; k *= 2) {
+            m = fminf(m, __shfl_up_sync(0xffffffffu, m, k));
+            span = 2 * k;
+        }
+        if (span < N + 1) m = fminf(m, __shfl_up_sync(0xffffffffu, m, N + 1 - span));
+        if (lane >= N && x < width) dst[(size_t)z * width + x] = m;
+    }
+}
+
 // fallback for n > MIN_FUSED_MAX_N: separable X window then Z window through HBM
 __global__ void __launch_bounds__(TX) min_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
                                                    int rows, int n) {
@@ -209,6 +247,26 @@ int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int
     NZ_REQUIRE(d_data && d_tmp, "min_erosion: null device buffer");
     NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "min_erosion: bad arguments");
     if (iterations > MIN_FUSED_MAX_N) NZ_REQUIRE(rows <= 65535, "min_erosion: too many rows");
+    if (iterations > 0 && iterations <= MWALK_MAX_N) {
+        dim3 grid(cdiv(width, (MWALK_THREADS / 32) * (32 - iterations)), cdiv(rows, MWALK_ROWS));
+        switch (iterations) {
+            case 1: min_walk_kernel<1><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            case 2: min_walk_kernel<2><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            case 3: min_walk_kernel<3><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            case 4: min_walk_kernel<4><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            case 5: min_walk_kernel<5><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            case 6: min_walk_kernel<6><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            case 7: min_walk_kernel<7><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+            default: min_walk_kernel<8><<<grid, MWALK_THREADS, 0, s>>>(d_data, d_tmp, width, rows); break;
+        }
+        NZ_LAUNCHED();
+        if (d_result) {
+            *d_result = d_tmp;
+        } else {
+            NZ_CUDA(cudaMemcpyAsync(d_data, d_tmp, (size_t)width * rows * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+        return NZ_OK;
+    }
     if (iterations > 0 && iterations <= MIN_FUSED_MAX_N) {
         const int n = iterations;
         const size_t smem = ((size_t)(MH + n) * (MW + n) + (size_t)(MH + n) * MW) * sizeof(float);

@@ -165,7 +165,7 @@ def test_rectangular_window_equals_full_interior_bitwise(nz, torch_cuda):
 # ---------------------------------------------------------------------------------------------
 # value erosion
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("res,iters", [(512, 5), (100, 1), (33, 12), (3, 5), (1, 1)])
+@pytest.mark.parametrize("res,iters", [(512, 5), (100, 1), (33, 12), (3, 5), (1, 1), (300, 8), (77, 3), (260, 9), (64, 2)])
 def test_min_erosion_bit_exact(nz, oracle, res, iters):
     a = rand_grid(res)
     got = a.copy().ravel()
