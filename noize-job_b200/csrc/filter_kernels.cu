@@ -205,7 +205,12 @@ int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int k
     NZ_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= NZ_MAX_KERNEL_WIDTH, "separable: ksize %d must be odd and <= %d",
                ksize, NZ_MAX_KERNEL_WIDTH);
     NZ_REQUIRE(iterations >= 0 && kx && kz, "separable: bad iterations/taps");
-    if (separable_fused_supported(ksize) && iterations > 0)
+    // NZ_SEP_PATH=fused|generic forces the older paths (the tests compare all three bit for bit)
+    const char* force = getenv("NZ_SEP_PATH");
+    const bool want_generic = force && force[0] == 'g', want_fused = force && force[0] == 'f';
+    if (!want_generic && !want_fused && iterations > 0 && separable_walk_supported(width, ksize, d_data, d_tmp))
+        return launch_separable_walk(d_data, d_tmp, width, rows, ksize, kx, kz, factor, iterations, d_result, s);
+    if (!want_generic && separable_fused_supported(ksize) && iterations > 0)
         return launch_separable_fused(d_data, d_tmp, width, rows, ksize, kx, kz, factor, iterations, d_result, s);
     Taps tx, tz;
     for (int i = 0; i < NZ_MAX_KERNEL_WIDTH; i++) {

@@ -57,6 +57,9 @@ int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cud
 
 int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
                          const float* kz, float factor, int iterations, float** d_result, cudaStream_t s);
+bool separable_walk_supported(int width, int ksize, const void* a, const void* b);
+int32_t launch_separable_walk(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
+                              const float* kz, float factor, int iterations, float** d_result, cudaStream_t s);
 bool separable_fused_supported(int ksize);
 int32_t launch_separable_fused(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
                                const float* kz, float factor, int iterations, float** d_result, cudaStream_t s);

@@ -1,0 +1,218 @@
+// sepwalk_kernels.cu — separable filter, T iterations per launch, entirely in registers (no shared memory).
+//
+// Same arithmetic and clamp semantics as filter_kernels.cu / sepfused_kernels.cu:
+//   X: total = 0; for k=-r..r  total = fma(src(x+k,z), K[r+k], total); out = total*factor
+//   Z: total = 0; for k=r..-r  total = fma(src(x,z+k), K[r-k], total); out = total*factor
+// (KernelSampleX/ZOperator, Filter/Kernel/KernelOperators.cs:31-65; clamp Pipeline/Tiles/TileData.cs:72-77;
+//  iteration loop Filter/KernelFilterStage.cs:31-43).
+//
+// A WARP owns a 128-column strip (lane = 4 adjacent columns) and streams down a chunk of rows.  Each of the
+// T fused iterations is a pipeline stage living in registers: it receives one row per step, takes the X pass
+// with its lane neighbours' values (2r warp shuffles), pushes the result into a (2r+1)-row register window and
+// emits the Z pass of the window's centre row, which is the next stage's input r rows behind.  After T
+// stages the row r*T behind the one just loaded is stored.  Nothing is synchronised across warps; the only
+// memory traffic is one coalesced 512-byte row load and one row store per step: 8 B/cell per T iterations.
+//
+// Redundancy: r*T halo columns each side of the strip (112 of 128 columns useful for Gauss5 x 4) and r*T
+// warm-up rows per chunk.  Against the shared-memory tile kernel this removes all LDS/STS, both tile phases
+// and every __syncthreads; per cell-iteration it issues 2(2r+1) FFMA + ~2r/2 SHFL.
+//
+// Clamp-to-edge: input rows are loaded with clamped columns; after every stage the lanes outside the grid
+// take the edge lane's value (one shuffle, border warps only), and at the top/bottom of the grid a stage's
+// window is filled with / keeps repeating the X pass of its first / last row.  That is exactly "an
+// out-of-range neighbour reads the edge cell's current-iteration value".
+#include "nz_common.cuh"
+
+namespace nz {
+namespace {
+
+constexpr int VW = 4;
+constexpr int STRIP = 32 * VW;       // 128 columns per warp
+constexpr int WALK_WARPS = 4;        // warps (strips) per CTA
+constexpr int WALK_ZC = 256;         // rows per chunk
+
+template <int R>
+struct TapsW {
+    float k[2 * R + 1];
+};
+
+template <int R, int T, bool SCALE>
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz) {
+    constexpr int KS = 2 * R + 1;
+    constexpr int HALO = (R * T + 3) & ~3;       // multiple of 4: strips and their useful part start on a lane boundary
+    constexpr int USE = STRIP - 2 * HALO;
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
+    const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
+    if (wx0 + HALO >= W) return;                 // whole warp: nothing to produce
+    const int gx = wx0 + VW * lane;
+    const bool has_left = wx0 < 0, has_right = wx0 + STRIP > W;
+    const bool interior = !has_left && !has_right;
+    const int L0 = has_left ? (-wx0) / VW : 0;                 // lane whose element 0 is grid column 0
+    const int L1 = has_right ? (W - 1 - wx0) / VW : 31;        // lane whose element 3 is grid column W-1
+    const int zc0 = blockIdx.y * WALK_ZC, zc1 = min(zc0 + WALK_ZC, H);
+    int rs = max(zc0 - R * T, 0);
+    rs -= rs % KS;                                             // first input row, phase 0
+    const int r_end = min(zc1 - 1 + R * T, H - 1 + R * T);     // last (virtual) input row
+
+    auto load_row = [&](int r, float (&v)[VW]) {
+        const float* g = src + (size_t)min(r, H - 1) * W;
+        if (interior) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(g + gx));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < VW; q++) v[q] = __ldg(g + min(max(gx + q, 0), W - 1));
+        }
+    };
+
+    float win[T][KS][VW];
+    float nxt[VW];
+    load_row(rs, nxt);
+
+    for (int base = rs; base <= r_end; base += KS) {
+#pragma unroll
+        for (int u = 0; u < KS; u++) {
+            const int r0 = base + u;
+            if (r0 <= r_end) {
+                float v[VW];
+#pragma unroll
+                for (int q = 0; q < VW; q++) v[q] = nxt[q];
+                if (r0 < r_end) load_row(r0 + 1, nxt);          // prefetch the next row
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const int rt = r0 - R * t;                  // row this stage receives; phase is static:
+                    const int P = ((u - R * t) % KS + KS) % KS;
+                    if (rt >= 0) {
+                        float xp[VW];
+                        if (rt <= H - 1) {
+                            // X pass: a[] = columns gx-R .. gx+3+R
+                            float a[VW + 2 * R];
+#pragma unroll
+                            for (int i = 0; i < R; i++) {
+                                a[i] = __shfl_up_sync(0xffffffffu, v[VW - R + i], 1);
+                                a[VW + R + i] = __shfl_down_sync(0xffffffffu, v[i], 1);
+                            }
+#pragma unroll
+                            for (int q = 0; q < VW; q++) a[R + q] = v[q];
+#pragma unroll
+                            for (int q = 0; q < VW; q++) {
+                                float tot = 0.0f;
+#pragma unroll
+                                for (int k = 0; k < KS; k++) tot = fmaf(a[q + k], kx.k[k], tot);
+                                xp[q] = SCALE ? tot * factor : tot;
+                            }
+                        } else {
+                            // below the grid: the row is a replica of the last one
+#pragma unroll
+                            for (int q = 0; q < VW; q++) xp[q] = win[t][(P + KS - 1) % KS][q];
+                        }
+                        if (rt == 0) {
+                            // above the grid: every row is a replica of row 0
+#pragma unroll
+                            for (int j = 0; j < KS; j++)
+#pragma unroll
+                                for (int q = 0; q < VW; q++) win[t][j][q] = xp[q];
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < VW; q++) win[t][P][q] = xp[q];
+                        }
+                        // Z pass of row rt-R: taps j = 0..2R pair K[j] with row rt-j (descending k of the reference)
+#pragma unroll
+                        for (int q = 0; q < VW; q++) {
+                            float tot = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < KS; j++) tot = fmaf(win[t][(P - j + 2 * KS) % KS][q], kz.k[j], tot);
+                            v[q] = SCALE ? tot * factor : tot;
+                        }
+                        if (has_left) {
+                            const float e = __shfl_sync(0xffffffffu, v[0], L0);
+                            if (lane < L0) {
+#pragma unroll
+                                for (int q = 0; q < VW; q++) v[q] = e;
+                            }
+                        }
+                        if (has_right) {
+                            const float e = __shfl_sync(0xffffffffu, v[VW - 1], L1);
+                            if (lane > L1) {
+#pragma unroll
+                                for (int q = 0; q < VW; q++) v[q] = e;
+                            }
+                        }
+                    }
+                }
+                const int rT = r0 - R * T;
+                if (rT >= zc0 && rT < zc1 && VW * lane >= HALO && VW * lane < HALO + USE && gx < W)
+                    *reinterpret_cast<float4*>(dst + (size_t)rT * W + gx) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+template <int R, int T>
+int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const float* kx, const float* kz, float factor,
+                       cudaStream_t s) {
+    TapsW<R> tx, tz;
+    for (int i = 0; i < 2 * R + 1; i++) {
+        tx.k[i] = kx[i];
+        tz.k[i] = kz[i];
+    }
+    constexpr int HALO = (R * T + 3) & ~3;
+    constexpr int USE = STRIP - 2 * HALO;
+    dim3 grid(cdiv(cdiv(width, USE), WALK_WARPS), cdiv(rows, WALK_ZC));
+    if (factor == 1.0f)
+        sep_walk_kernel<R, T, false><<<grid, WALK_WARPS * 32, 0, s>>>(in, out, width, rows, factor, tx, tz);
+    else
+        sep_walk_kernel<R, T, true><<<grid, WALK_WARPS * 32, 0, s>>>(in, out, width, rows, factor, tx, tz);
+    NZ_LAUNCHED();
+    return NZ_OK;
+}
+
+template <int R>
+int32_t launch_walk_r(float* d_data, float* d_tmp, int width, int rows, const float* kx, const float* kz, float factor,
+                      int iterations, float** d_result, cudaStream_t s) {
+    constexpr int TMAX = R <= 2 ? 4 : 2;   // register windows: T*(2R+1)*4 floats per lane
+    const int launches = (iterations + TMAX - 1) / TMAX;
+    float *cur = d_data, *other = d_tmp;
+    int left = iterations;
+    for (int l = 0; l < launches; l++) {
+        const int T = (left + (launches - l) - 1) / (launches - l);
+        int32_t rc;
+        switch (T) {
+            case 1: rc = launch_walk_rt<R, 1>(cur, other, width, rows, kx, kz, factor, s); break;
+            case 2: rc = launch_walk_rt<R, 2>(cur, other, width, rows, kx, kz, factor, s); break;
+            case 3: rc = launch_walk_rt<R, 3>(cur, other, width, rows, kx, kz, factor, s); break;
+            default: rc = launch_walk_rt<R, 4>(cur, other, width, rows, kx, kz, factor, s); break;
+        }
+        if (rc != NZ_OK) return rc;
+        left -= T;
+        float* t = cur; cur = other; other = t;
+    }
+    if (d_result) {
+        *d_result = cur;
+    } else if (cur != d_data) {
+        NZ_CUDA(cudaMemcpyAsync(d_data, cur, (size_t)width * rows * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return NZ_OK;
+}
+
+}  // namespace
+
+bool separable_walk_supported(int width, int ksize, const void* a, const void* b) {
+    return ksize >= 3 && ksize <= 9 && (ksize & 1) && (width & 3) == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
+int32_t launch_separable_walk(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
+                              const float* kz, float factor, int iterations, float** d_result, cudaStream_t s) {
+    switch (ksize) {
+        case 3: return launch_walk_r<1>(d_data, d_tmp, width, rows, kx, kz, factor, iterations, d_result, s);
+        case 5: return launch_walk_r<2>(d_data, d_tmp, width, rows, kx, kz, factor, iterations, d_result, s);
+        case 7: return launch_walk_r<3>(d_data, d_tmp, width, rows, kx, kz, factor, iterations, d_result, s);
+        case 9: return launch_walk_r<4>(d_data, d_tmp, width, rows, kx, kz, factor, iterations, d_result, s);
+    }
+    set_error("separable_walk: unsupported ksize %d", ksize);
+    return NZ_E_UNSUPPORTED;
+}
+
+}  // namespace nz

@@ -360,3 +360,20 @@ def test_simplex_beyond_the_fast_hash_domain_uses_the_exact_residue(nz, oracle):
     got = gpu_fractal(nz, 64, 3, 30000, 30000, octaves=24, noise_size=5, stepdown=2.2)
     ref = ref_fractal(oracle, 64, 3, 30000, 30000, octaves=24, noise_size=5, stepdown=2.2)
     assert np.abs(got - ref).max() <= TOL_NOISE
+
+
+@pytest.mark.parametrize("rows,width,ftype,iters", [(700, 600, 2, 17), (300, 1000, 3, 7), (97, 236, 0, 3), (40, 20, 1, 2),
+                                                    (513, 472, 6, 4), (33, 4, 2, 5), (260, 128, 8, 3), (130, 132, 9, 1)])
+def test_separable_paths_agree_bitwise(nz, torch_cuda, monkeypatch, rows, width, ftype, iters):
+    """Register-walk kernel vs shared-memory tile kernel vs one-pass-per-launch kernels: same bits, on strip,
+    chunk and grid borders."""
+    torch = torch_cuda
+    a = torch.from_numpy(rand_grid(rows, width)).cuda()
+    walk = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    monkeypatch.setenv("NZ_SEP_PATH", "fused")
+    fused = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    monkeypatch.setenv("NZ_SEP_PATH", "generic")
+    plain = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(fused, plain)
+    assert torch.equal(walk, plain)
