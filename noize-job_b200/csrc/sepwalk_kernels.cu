@@ -36,28 +36,39 @@ struct TapsW {
     float k[2 * R + 1];
 };
 
-template <int R, int T, bool SCALE>
-__global__ void __launch_bounds__(WALK_WARPS * 32)
-sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz) {
+constexpr int PFR = 16;              // rows of the per-warp cp.async landing ring (PFR-1 in flight)
+
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 ld_shared_f4(unsigned smem_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
+    return v;
+}
+
+// BORDER = false is the steady-state body for warps whose strip and chunk touch no grid border: no clamp logic.
+template <int R, int T, bool SCALE, bool BORDER>
+__device__ __forceinline__ void walk_body(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor,
+                                          const TapsW<R>& kx, const TapsW<R>& kz, int wx0, int zc0, int zc1, unsigned ring_base) {
     constexpr int KS = 2 * R + 1;
     constexpr int HALO = (R * T + 3) & ~3;       // multiple of 4: strips and their useful part start on a lane boundary
     constexpr int USE = STRIP - 2 * HALO;
     const int lane = threadIdx.x & 31;
-    const int strip = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
-    const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
-    if (wx0 + HALO >= W) return;                 // whole warp: nothing to produce
     const int gx = wx0 + VW * lane;
-    const bool has_left = wx0 < 0, has_right = wx0 + STRIP > W;
+    const bool has_left = BORDER && wx0 < 0, has_right = BORDER && wx0 + STRIP > W;
     const bool interior = !has_left && !has_right;
     const int L0 = has_left ? (-wx0) / VW : 0;                 // lane whose element 0 is grid column 0
     const int L1 = has_right ? (W - 1 - wx0) / VW : 31;        // lane whose element 3 is grid column W-1
-    const int zc0 = blockIdx.y * WALK_ZC, zc1 = min(zc0 + WALK_ZC, H);
     int rs = max(zc0 - R * T, 0);
     rs -= rs % KS;                                             // first input row, phase 0
     const int r_end = min(zc1 - 1 + R * T, H - 1 + R * T);     // last (virtual) input row
 
     auto load_row = [&](int r, float (&v)[VW]) {
-        const float* g = src + (size_t)min(r, H - 1) * W;
+        const float* g = src + (size_t)(BORDER ? min(r, H - 1) : r) * W;
         if (interior) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(g + gx));
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -68,8 +79,22 @@ sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, i
     };
 
     float win[T][KS][VW];
+    // Memory-level parallelism.  One 512-byte row per step per warp is far too little in flight for HBM (Little's
+    // law: ~12 warps x 148 SMs x 512 B / ~2 us of loaded latency ~ 0.5 TB/s).  The steady-state body therefore
+    // requests rows PFR-1 steps ahead with cp.async into a per-lane private landing zone in shared memory (each
+    // lane writes and later reads its own 16 bytes per row, so no cross-lane synchronisation is needed); border
+    // warps (clamped addresses) keep the simple one-row register prefetch.
     float nxt[VW];
-    load_row(rs, nxt);
+    const unsigned ring_lane = ring_base + (unsigned)(lane * VW * sizeof(float));   // shared-space byte address
+    if (BORDER) {
+        load_row(rs, nxt);
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < PFR - 1; j++) {
+            if (rs + j <= r_end) cp_async16(ring_lane + ((rs + j) & (PFR - 1)) * (STRIP * 4), src + (size_t)(rs + j) * W + gx);
+            cp_async_commit();
+        }
+    }
 
     for (int base = rs; base <= r_end; base += KS) {
 #pragma unroll
@@ -77,16 +102,25 @@ sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, i
             const int r0 = base + u;
             if (r0 <= r_end) {
                 float v[VW];
+                if (BORDER) {
 #pragma unroll
-                for (int q = 0; q < VW; q++) v[q] = nxt[q];
-                if (r0 < r_end) load_row(r0 + 1, nxt);          // prefetch the next row
+                    for (int q = 0; q < VW; q++) v[q] = nxt[q];
+                    if (r0 < r_end) load_row(r0 + 1, nxt);
+                } else {
+                    const int ra = r0 + PFR - 1;                     // row requested now, consumed PFR-1 steps later
+                    if (ra <= r_end) cp_async16(ring_lane + (ra & (PFR - 1)) * (STRIP * 4), src + (size_t)ra * W + gx);
+                    cp_async_commit();
+                    cp_async_wait<PFR - 1>();                        // the group of row r0 has landed
+                    const float4 t4 = ld_shared_f4(ring_lane + (r0 & (PFR - 1)) * (STRIP * 4));
+                    v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+                }
 #pragma unroll
                 for (int t = 0; t < T; t++) {
                     const int rt = r0 - R * t;                  // row this stage receives; phase is static:
                     const int P = ((u - R * t) % KS + KS) % KS;
-                    if (rt >= 0) {
+                    if (!BORDER || rt >= 0) {
                         float xp[VW];
-                        if (rt <= H - 1) {
+                        if (!BORDER || rt <= H - 1) {
                             // X pass: a[] = columns gx-R .. gx+3+R
                             float a[VW + 2 * R];
 #pragma unroll
@@ -108,7 +142,7 @@ sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, i
 #pragma unroll
                             for (int q = 0; q < VW; q++) xp[q] = win[t][(P + KS - 1) % KS][q];
                         }
-                        if (rt == 0) {
+                        if (BORDER && rt == 0) {
                             // above the grid: every row is a replica of row 0
 #pragma unroll
                             for (int j = 0; j < KS; j++)
@@ -148,6 +182,25 @@ sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, i
             }
         }
     }
+}
+
+template <int R, int T, bool SCALE>
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz) {
+    constexpr int HALO = (R * T + 3) & ~3;
+    constexpr int USE = STRIP - 2 * HALO;
+    const int strip = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
+    const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
+    if (wx0 + HALO >= W) return;                 // whole warp: nothing to produce
+    const int zc0 = blockIdx.y * WALK_ZC, zc1 = min(zc0 + WALK_ZC, H);
+    // steady state: the strip lies inside the grid and so does the chunk with its warm-up and drain rows
+    const bool plain = wx0 >= 0 && wx0 + STRIP <= W && zc0 - R * T - (2 * R + 1) > 0 && zc1 - 1 + R * T <= H - 1;
+    __shared__ __align__(16) float ring[WALK_WARPS][PFR][STRIP];
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[threadIdx.x >> 5][0][0]);
+    if (plain)
+        walk_body<R, T, SCALE, false>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+    else
+        walk_body<R, T, SCALE, true>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
 }
 
 template <int R, int T>
