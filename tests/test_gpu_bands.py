@@ -1,0 +1,91 @@
+"""Row bands on real GPUs: the banded chain must equal the single-band chain bit for bit.
+
+* one GPU is enough for the `recompute` mode (no communication): the ranks of a virtual world run one after
+  another on cuda:0;
+* the `exchange` mode (NCCL halo exchange) runs when the box has >= 2 GPUs, one process per GPU.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(bands, N):
+    return bands.ChainConfig(N=N, noise_size=170, filter_iterations=6, flow_iterations=3, erosion_iterations=4)
+
+
+def _single(nz, bands, N):
+    import torch
+    chain = bands.BandChain(_cfg(bands, N), bands.CudaEngine())
+    chain.run()
+    torch.cuda.synchronize()
+    return chain.owned().clone(), chain.vtx.clone(), chain.idx.clone()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_recompute_bands_equal_single_grid_bitwise(nz, world):
+    import torch
+    from noize_job_b200 import bands
+    N = 512
+    ref, rv, ri = _single(nz, bands, N)
+    R = N - 8
+    for rank in range(world):
+        chain = bands.BandChain(_cfg(bands, N), bands.CudaEngine(), rank, world, None, mode="recompute")
+        chain.run()
+        torch.cuda.synchronize()
+        assert torch.equal(chain.owned(), ref[chain.z0:chain.z1]), f"rank {rank}/{world}: heightmap band differs"
+        assert torch.equal(chain.vtx, rv[chain.vz0 * (R + 1):chain.vz1 * (R + 1)])
+        t0 = max(chain.vz0, 1)
+        n = 6 * R * (chain.vz1 - t0)
+        assert torch.equal(chain.idx[:n], ri[6 * R * (t0 - 1):6 * R * (chain.vz1 - 1)])
+
+
+def test_single_band_chain_matches_oracle(nz, oracle):
+    import torch
+    from noize_job_b200 import bands
+    N = 256
+    cfg = _cfg(bands, N)
+    got, _, _ = _single(nz, bands, N)
+    ref = oracle.fractal(N, N, 3, 0.4, octaves=13, noise_size=170)
+    ref = oracle.min_erosion(oracle.flowmap(oracle.kernel_filter(ref, 2, 6), 3, 0.0, 0.005), 4)
+    assert np.abs(got.cpu().numpy() - ref).max() <= 5e-5 * max(1.0, np.abs(ref).max())
+
+
+def _nccl_worker(rank, world, port, N, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    import noize_job_b200 as nz
+    from noize_job_b200 import bands
+    nz.host.init(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ref, rv, ri = _single(nz, bands, N)
+        chain = bands.BandChain(_cfg(bands, N), bands.CudaEngine(), rank, world, dist, mode="exchange")
+        chain.run()
+        torch.cuda.synchronize()
+        R = N - 8
+        assert torch.equal(chain.owned(), ref[chain.z0:chain.z1]), f"rank {rank}: heightmap band differs"
+        assert torch.equal(chain.vtx, rv[chain.vz0 * (R + 1):chain.vz1 * (R + 1)])
+        assert chain.bytes_exchanged > 0
+        open(os.path.join(out_dir, f"ok_{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_halo_exchange_bands_equal_single_grid_bitwise(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(world, port, 512, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok_{r}").exists() for r in range(world))
