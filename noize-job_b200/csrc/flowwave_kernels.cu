@@ -354,8 +354,10 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
         const int zc = cdiv(rows, nz);
         if (zc < 64 && nz > 1) break;
         const long long ctas = (long long)strips * cdiv(rows, zc);
-        const long long waves = (ctas + sms - 1) / sms;
-        const double cost = (double)waves * (zc + 6 * I + RING);   // steps executed by the busiest SM
+        const long long slots = 2LL * sms;                // two CTAs are resident per SM and hide each other's barrier waits
+        const long long waves = (ctas + slots - 1) / slots;
+        // steps executed by the busiest SM slot; a lone CTA on an SM runs its steps ~1.7x slower than one of a pair
+        const double cost = (double)waves * (zc + 6 * I + RING) * (ctas < slots ? 1.7 : 1.0);
         if (cost < best_cost) { best_cost = cost; best_nz = nz; }
     }
     p.zc = cdiv(rows, best_nz);
