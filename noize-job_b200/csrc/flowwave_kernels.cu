@@ -16,10 +16,11 @@
 //       B_t  : water   step of level t on row s-4t       reads f_t (3 rows), w_{t-1}, h;  writes w_t, H_t
 //       V    : velocity + normalise      on row s-4I     reads f_I (3 rows);              writes the result row
 //   Every field of every level is a ring of 5 rows (a row is last read 4 steps after it was written).
-//   State per CTA: 5 x (4I + 3(I-1)) rows x 512 B = 80 KB for I = 5: two 256-thread CTAs per SM, so one CTA computes
-//   while the other waits at its barrier (measured better than one 512-thread CTA on a 256-column strip).
+//   State per CTA: 5 x (4I + 3(I-1)) rows x 512 B = 80 KB for I = 5: two 512-thread CTAs per SM, so one CTA computes
+//   while the other waits at its barrier.  A step costs about (instructions of the busiest warp) x ~5 cycles, so the
+//   stages are split over as many warps as the register file allows: two 512-thread CTAs per SM at 56 registers.
 //
-// Warps are specialised: warp = role; a lane owns 4 adjacent columns (LDS.128 / STS.128, only the
+// Warps are specialised: two warps per role (64 columns each); a lane owns 2 adjacent columns (LDS.64 / STS.64, only the
 // two outer neighbours are scalar loads).  Roles are a static, cost-balanced split of the 2I+1 stages.  The
 // byte offsets of the 5 ring slots rotate through 5 registers, so no modulo arithmetic is executed.
 //
@@ -33,9 +34,9 @@ namespace nz {
 namespace {
 
 constexpr int FLW = 128;          // strip width in floats, halo included
-constexpr int FL_THREADS = 256;
+constexpr int FL_THREADS = 512;
 constexpr int RING = 5;
-constexpr int VW = 4;             // columns per lane
+constexpr int VW = 2;             // columns per lane
 constexpr int FLOW_WAVE_MAX_I = 5;
 constexpr float TIMESTEP = 0.2f;
 constexpr float WATER0 = 0.0001f;  // FillArrayJob value, FlowMapStage.cs:129
@@ -56,13 +57,13 @@ struct V4 {
     float v[VW];
 };
 __device__ __forceinline__ V4 ld4(const float* base, int off) {
-    const float4 t = *reinterpret_cast<const float4*>(base + off);
+    const float2 t = *reinterpret_cast<const float2*>(base + off);
     V4 r;
-    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    r.v[0] = t.x; r.v[1] = t.y;
     return r;
 }
 __device__ __forceinline__ void st4(float* base, int off, const V4& a) {
-    *reinterpret_cast<float4*>(base + off) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    *reinterpret_cast<float2*>(base + off) = make_float2(a.v[0], a.v[1]);
 }
 __device__ __forceinline__ V4 splat(float x) {
     V4 r;
@@ -227,7 +228,7 @@ __device__ __forceinline__ void stage_velocity(const Lane& L, int s, int zc0, in
     }
     const int gx = xs0 + L.c;
     if (L.c >= p.hx && L.c < FLW - p.hx && gx + VW - 1 < p.W)
-        *reinterpret_cast<float4*>(p.out + (size_t)r * p.W + gx) = make_float4(res.v[0], res.v[1], res.v[2], res.v[3]);
+        *reinterpret_cast<float2*>(p.out + (size_t)r * p.W + gx) = make_float2(res.v[0], res.v[1]);
 }
 
 // Loader: the global read of a height row has ~1 us of latency, far more than a step takes, so the row that is
@@ -239,8 +240,8 @@ __device__ __forceinline__ V4 load_row(const Lane& L, int row, int hlo, int hhi,
         const float* g = p.h + (size_t)row * p.W;
         const int gx = xs0 + L.c;
         if (gx >= 0 && gx + VW - 1 < p.W) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(g + gx));
-            a.v[0] = t.x; a.v[1] = t.y; a.v[2] = t.z; a.v[3] = t.w;
+            const float2 t = __ldg(reinterpret_cast<const float2*>(g + gx));
+            a.v[0] = t.x; a.v[1] = t.y;
         } else {
 #pragma unroll
             for (int q = 0; q < VW; q++) a.v[q] = __ldg(g + min(max(gx + q, 0), p.W - 1));
@@ -249,7 +250,7 @@ __device__ __forceinline__ V4 load_row(const Lane& L, int row, int hlo, int hhi,
     return a;
 }
 
-// Static, cost-balanced roles, one warp each (32 lanes x 4 columns = the 128-column strip).
+// Static, cost-balanced roles, two warps each (2 x 32 lanes x 2 columns = the 128-column strip).
 //   role 0..4: outflow of level role+1      role 5: velocity
 //   role 6: loader + water 1,2              role 7: water 3,4
 template <int I>
@@ -260,10 +261,10 @@ __global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) 
     const int zc0 = blockIdx.y * p.zc, zc1 = min(zc0 + p.zc, H);
     const int cmin = max(0, -xs0), cmax = min(FLW - 1, p.W - 1 - xs0);   // strip columns inside the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = warp;
+    const int role = warp >> 1;
     Lane L;
     L.sm = sm;
-    L.c = lane * VW;
+    L.c = (warp & 1) * 64 + lane * VW;
     L.dl = max(L.c - 1, cmin) - L.c;
     L.dr = min(L.c + VW, cmax) - L.c;
     L.H = H;
