@@ -110,3 +110,13 @@ def test_stage_mirror_keeps_reference_defaults(nz):
     assert (m.resolution, m.inputResolution, m.marginPix, m.tileSize, m.tileHeight) == (512, 512, 5, 512.0, 512.0)
     with pytest.raises(Exception, match="No stages"):
         nz.BasePipeline([])
+
+
+def test_cpp_host_mirror_is_built_and_fails_loudly_without_a_gpu(nz):
+    import subprocess
+    exe = os.path.join(os.path.dirname(nz.lib.LIB_PATH), "host_cpp", "example_chain")
+    assert os.path.exists(exe), "build() compiles host_cpp/example_chain from noize_stages.hpp"
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    out = subprocess.run([exe, "64"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 1 and "no CPU fallback" in out.stderr
