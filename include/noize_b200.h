@@ -202,6 +202,15 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
  * generator) and one D2H.  nz_pipeline_end flushes every dirty mirror to its host slice. */
 NZ_API int32_t nz_pipeline_begin(void);
 NZ_API int32_t nz_pipeline_end(void);
+/* The same residency as an explicit, process-wide scope, for hosts that run the stages of one chain on
+ * DIFFERENT threads (Unity executes every IJob on an arbitrary worker): create the scope when the chain is
+ * scheduled, bracket each stage's native call with enter/leave on whatever thread runs it, close it (flushes every
+ * dirty mirror to host memory, then frees) when the chain completes.  Streams of different threads are ordered
+ * through per-mirror events.  nz_pipeline_begin/end == create+enter / close on one thread. */
+NZ_API int64_t nz_scope_create(void);            /* > 0: scope id; < 0: NZ_E* */
+NZ_API int32_t nz_scope_enter(int64_t scope);
+NZ_API int32_t nz_scope_leave(void);
+NZ_API int32_t nz_scope_close(int64_t scope);
 /* Flush one mirror early (e.g. before a Burst stage reads the slice). */
 NZ_API int32_t nz_flush_to_host(const float* host_ptr);
 /* cudaHostRegister / Unregister a long-lived host allocation (PipelineStateManager buffers). */

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -158,7 +159,20 @@ struct Mirror {
     size_t n = 0;
     nz_slice_f32 host{};
     bool dirty = false;  // device newer than host
+    cudaEvent_t ready = nullptr;        // recorded after the last stage that touched the mirror (cross-thread ordering)
+    cudaStream_t last_stream = nullptr;
 };
+
+// A residency scope: the device mirrors of the host slices one chain of stages works on.  Scopes are process-wide
+// objects so that the stages of a chain may run on different threads (Unity runs every IJob on an arbitrary worker):
+// a thread ENTERS a scope, makes its stage call, and leaves; the mirror's `ready` event orders the streams.
+struct Scope {
+    std::mutex mu;
+    std::unordered_map<const void*, Mirror> mirrors;
+};
+static std::mutex g_scopes_mu;
+static std::unordered_map<long long, std::shared_ptr<Scope>> g_scopes;
+static std::atomic<long long> g_next_scope{1};
 
 struct ThreadState {
     cudaStream_t stream = nullptr;
@@ -166,11 +180,15 @@ struct ThreadState {
     bool timed = false;
     long long launches_at_start = 0;
     int launches = 0;
-    bool in_pipeline = false;
-    std::unordered_map<const void*, Mirror> mirrors;
+    std::shared_ptr<Scope> scope;   // scope this thread is inside of (nz_scope_enter / nz_pipeline_begin), if any
+    long long scope_id = 0;
+    bool owns_scope = false;        // entered through nz_pipeline_begin: nz_pipeline_end closes it
+    Scope local;                    // mirrors of a call made outside any scope (dropped when the call returns)
     ~ThreadState() {}
 };
 static thread_local ThreadState t_state;
+static inline bool in_scope() { return (bool)t_state.scope; }
+static inline Scope& cur_scope() { return t_state.scope ? *t_state.scope : t_state.local; }
 
 static int32_t thread_ready() {
     int32_t rc = ensure_init();
@@ -226,8 +244,13 @@ static int32_t download(Mirror& m) {
 // Obtain the device mirror of a host slice.  `need_contents`: the stage reads the slice (H2D unless a
 // resident mirror is already newer than the host).
 static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out) {
-    auto it = t_state.mirrors.find(s.ptr);
-    if (it != t_state.mirrors.end() && (it->second.n != (size_t)s.length || it->second.host.stride_bytes != s.stride_bytes)) {
+    Scope& sc = cur_scope();
+    std::lock_guard<std::mutex> lk(sc.mu);
+    auto& mirrors = sc.mirrors;
+    auto it = mirrors.find(s.ptr);
+    if (it != mirrors.end() && it->second.ready && it->second.last_stream != t_state.stream)
+        NZ_CUDA(cudaStreamWaitEvent(t_state.stream, it->second.ready, 0));   // previous stage ran on another thread's stream
+    if (it != mirrors.end() && (it->second.n != (size_t)s.length || it->second.host.stride_bytes != s.stride_bytes)) {
         // same base pointer, different shape: drop the stale mirror
         if (it->second.dirty) {
             int32_t rc = download(it->second);
@@ -236,16 +259,17 @@ static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out) 
         }
         pool_free(it->second.d);
         pool_free(it->second.d_tmp);
-        t_state.mirrors.erase(it);
-        it = t_state.mirrors.end();
+        if (it->second.ready) cudaEventDestroy(it->second.ready);
+        mirrors.erase(it);
+        it = mirrors.end();
     }
-    if (it == t_state.mirrors.end()) {
+    if (it == mirrors.end()) {
         Mirror m;
         m.n = (size_t)s.length;
         m.host = s;
         int32_t rc = pool_alloc((void**)&m.d, m.n * sizeof(float));
         if (rc != NZ_OK) return rc;
-        it = t_state.mirrors.emplace(s.ptr, m).first;
+        it = mirrors.emplace(s.ptr, m).first;
         if (need_contents) {
             rc = upload(it->second);
             if (rc != NZ_OK) return rc;
@@ -273,18 +297,22 @@ static void adopt_result(Mirror& m, float* result) {
 static int32_t finish(Mirror* m) {
     cudaStream_t s = t_state.stream;
     NZ_CUDA(cudaEventRecord(t_state.ev[2], s));
-    if (!t_state.in_pipeline) {
+    if (!in_scope()) {
         int32_t rc = NZ_OK;
         if (m->dirty) rc = download(*m);
         cudaError_t e = cudaEventRecord(t_state.ev[3], s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         pool_free(m->d);
         pool_free(m->d_tmp);
-        t_state.mirrors.erase(m->host.ptr);
+        t_state.local.mirrors.erase(m->host.ptr);
         if (rc != NZ_OK) return rc;
         if (e != cudaSuccess) return cuda_fail(e, "stage completion");
     } else {
         NZ_CUDA(cudaEventRecord(t_state.ev[3], s));
+        // publish: whoever touches this mirror next (possibly another thread, another stream) waits for this stage
+        if (!m->ready) NZ_CUDA(cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming));
+        NZ_CUDA(cudaEventRecord(m->ready, s));
+        m->last_stream = s;
     }
     t_state.timed = true;
     t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
@@ -511,22 +539,110 @@ NZ_API int32_t nz_dev_fma_peak(float* d_sink, int32_t grid, int32_t iters, doubl
 // =================================================================================================
 // host layer
 // =================================================================================================
+// ---- residency scopes ---------------------------------------------------------------------------------
+static int32_t scope_close(const std::shared_ptr<Scope>& sc) {
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(sc->mu);
+    cudaStream_t s = t_state.stream;
+    for (auto& kv : sc->mirrors) {
+        Mirror& m = kv.second;
+        if (m.ready && m.last_stream != s) cudaStreamWaitEvent(s, m.ready, 0);
+        if (m.dirty && rc == NZ_OK) rc = download(m);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    for (auto& kv : sc->mirrors) {
+        pool_free(kv.second.d);
+        pool_free(kv.second.d_tmp);
+        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+    }
+    sc->mirrors.clear();
+    if (rc != NZ_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "scope close");
+    return NZ_OK;
+}
+
+NZ_API int64_t nz_scope_create(void) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    const long long id = g_next_scope.fetch_add(1);
+    std::lock_guard<std::mutex> lk(g_scopes_mu);
+    g_scopes[id] = std::make_shared<Scope>();
+    return id;
+}
+
+NZ_API int32_t nz_scope_enter(int64_t id) {
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    if (in_scope()) {
+        set_error("nz_scope_enter: this thread is already inside scope %lld", t_state.scope_id);
+        return NZ_E_STATE;
+    }
+    std::lock_guard<std::mutex> lk(g_scopes_mu);
+    auto it = g_scopes.find(id);
+    if (it == g_scopes.end()) {
+        set_error("nz_scope_enter: unknown scope %lld", (long long)id);
+        return NZ_E_INVALID;
+    }
+    t_state.scope = it->second;
+    t_state.scope_id = id;
+    t_state.owns_scope = false;
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_scope_leave(void) {
+    if (!in_scope()) {
+        set_error("nz_scope_leave: this thread is in no scope");
+        return NZ_E_STATE;
+    }
+    t_state.scope.reset();
+    t_state.scope_id = 0;
+    t_state.owns_scope = false;
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_scope_close(int64_t id) {
+    std::shared_ptr<Scope> sc;
+    {
+        std::lock_guard<std::mutex> lk(g_scopes_mu);
+        auto it = g_scopes.find(id);
+        if (it == g_scopes.end()) {
+            set_error("nz_scope_close: unknown scope %lld", (long long)id);
+            return NZ_E_INVALID;
+        }
+        sc = it->second;
+        g_scopes.erase(it);
+    }
+    if (t_state.scope_id == id) {
+        t_state.scope.reset();
+        t_state.scope_id = 0;
+        t_state.owns_scope = false;
+    }
+    return scope_close(sc);
+}
+
 NZ_API int32_t nz_pipeline_begin(void) {
     int32_t rc = thread_ready();
     if (rc != NZ_OK) return rc;
-    if (t_state.in_pipeline) {
+    if (in_scope()) {
         set_error("nz_pipeline_begin: already inside a pipeline on this thread");
         return NZ_E_STATE;
     }
-    t_state.in_pipeline = true;
-    return NZ_OK;
+    const int64_t id = nz_scope_create();
+    if (id < 0) return (int32_t)id;
+    rc = nz_scope_enter(id);
+    if (rc == NZ_OK) t_state.owns_scope = true;
+    return rc;
 }
 
 NZ_API int32_t nz_flush_to_host(const float* host_ptr) {
     int32_t rc = thread_ready();
     if (rc != NZ_OK) return rc;
-    auto it = t_state.mirrors.find(host_ptr);
-    if (it == t_state.mirrors.end()) return NZ_OK;  // nothing resident: host is current
+    Scope& sc = cur_scope();
+    std::lock_guard<std::mutex> lk(sc.mu);
+    auto it = sc.mirrors.find(host_ptr);
+    if (it == sc.mirrors.end()) return NZ_OK;  // nothing resident: host is current
+    if (it->second.ready && it->second.last_stream != t_state.stream) NZ_CUDA(cudaStreamWaitEvent(t_state.stream, it->second.ready, 0));
     if (it->second.dirty) {
         rc = download(it->second);
         if (rc != NZ_OK) return rc;
@@ -536,23 +652,11 @@ NZ_API int32_t nz_flush_to_host(const float* host_ptr) {
 }
 
 NZ_API int32_t nz_pipeline_end(void) {
-    if (!t_state.in_pipeline) {
+    if (!in_scope() || !t_state.owns_scope) {
         set_error("nz_pipeline_end: no pipeline open on this thread");
         return NZ_E_STATE;
     }
-    int32_t rc = NZ_OK;
-    for (auto& kv : t_state.mirrors)
-        if (kv.second.dirty && rc == NZ_OK) rc = download(kv.second);
-    cudaError_t e = cudaStreamSynchronize(t_state.stream);
-    for (auto& kv : t_state.mirrors) {
-        pool_free(kv.second.d);
-        pool_free(kv.second.d_tmp);
-    }
-    t_state.mirrors.clear();
-    t_state.in_pipeline = false;
-    if (rc != NZ_OK) return rc;
-    if (e != cudaSuccess) return cuda_fail(e, "nz_pipeline_end");
-    return NZ_OK;
+    return nz_scope_close(t_state.scope_id);
 }
 
 NZ_API int32_t nz_pin(void* host_ptr, size_t bytes) {
@@ -667,7 +771,7 @@ NZ_API int32_t nz_flowmap(nz_slice_f32 height, int32_t resolution, int32_t itera
     });
     if (scratch) {
         // the stream may still be using it inside a pipeline: order the release after the work
-        if (t_state.in_pipeline) cudaStreamSynchronize(t_state.stream);
+        if (in_scope()) cudaStreamSynchronize(t_state.stream);
         pool_free(scratch);
     }
     return rc;
@@ -704,11 +808,11 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
     }
     pool_free(d_v);
     pool_free(d_i);
-    if (!t_state.in_pipeline) {
+    if (!in_scope()) {
         // heights were only read: nothing to bring home
         pool_free(m->d);
         pool_free(m->d_tmp);
-        t_state.mirrors.erase(heights.ptr);
+        t_state.local.mirrors.erase(heights.ptr);
     }
     if (rc != NZ_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "nz_heightmap_mesh");

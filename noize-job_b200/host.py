@@ -153,6 +153,36 @@ def pipeline():
         pipeline_end()
 
 
+def scope_create():
+    """Process-wide residency scope for chains whose stages run on different threads (see nz_scope_create)."""
+    sid = int(_l.load().nz_scope_create())
+    if sid < 0:
+        _l.check(sid)
+    return sid
+
+
+def scope_enter(scope):
+    _l.check(_l.load().nz_scope_enter(scope))
+
+
+def scope_leave():
+    _l.check(_l.load().nz_scope_leave())
+
+
+def scope_close(scope):
+    _l.check(_l.load().nz_scope_close(scope))
+
+
+@contextmanager
+def in_scope(scope):
+    """Bracket one stage call made on the current thread inside `scope`."""
+    scope_enter(scope)
+    try:
+        yield
+    finally:
+        scope_leave()
+
+
 def flush_to_host(arr):
     _l.check(_l.load().nz_flush_to_host(arr.ctypes.data))
 

@@ -60,6 +60,10 @@ SIGNATURES = {
     "nz_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, Slice]),
     "nz_pipeline_begin": (_i32, []),
     "nz_pipeline_end": (_i32, []),
+    "nz_scope_create": (C.c_int64, []),
+    "nz_scope_enter": (_i32, [C.c_int64]),
+    "nz_scope_leave": (_i32, []),
+    "nz_scope_close": (_i32, [C.c_int64]),
     "nz_flush_to_host": (_i32, [_vp]),
     "nz_pin": (_i32, [_vp, _sz]),
     "nz_unpin": (_i32, [_vp]),

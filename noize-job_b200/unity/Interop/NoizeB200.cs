@@ -61,6 +61,11 @@ namespace xshazwar.noize.interop.b200 {
         [DllImport(LIB)] public static extern int nz_heightmap_mesh(int meshType, void* vertices, uint* indices, int resolution,
             int inputResolution, int marginPix, float tileHeight, float tileSize, NzSlice heights);
 
+        // process-wide residency scope: the stages of one chain run on different worker threads
+        [DllImport(LIB)] public static extern long nz_scope_create();
+        [DllImport(LIB)] public static extern int nz_scope_enter(long scope);
+        [DllImport(LIB)] public static extern int nz_scope_leave();
+        [DllImport(LIB)] public static extern int nz_scope_close(long scope);
         [DllImport(LIB)] public static extern int nz_pipeline_begin();
         [DllImport(LIB)] public static extern int nz_pipeline_end();
         [DllImport(LIB)] public static extern int nz_flush_to_host(void* hostPtr);
@@ -83,10 +88,12 @@ namespace xshazwar.noize.interop.b200 {
         public int resolution, inputResolution, marginPix, i0, i1, i2, xpos, zpos;
         public float f0, f1, f2, f3;
         [NativeDisableContainerSafetyRestriction] public NativeReference<int> status;
+        public long scope;   // 0: stand-alone call (H2D + D2H around this stage); else a scope shared by the chain's jobs
 
         public void Execute() {
             NzSlice s = NzSlice.From(data);
             int rc = 0;
+            if (scope != 0) Native.nz_scope_enter(scope);
             switch (op) {
                 case Op.Fractal:      rc = Native.nz_fractal(s, resolution, i0, f0, f1, f2, f3, i1, xpos, zpos, i2); break;
                 case Op.KernelFilter: rc = Native.nz_kernel_filter(s, NzSlice.Null, i0, resolution, i1); break;
@@ -96,8 +103,17 @@ namespace xshazwar.noize.interop.b200 {
                 case Op.FlowMap:      rc = Native.nz_flowmap(s, resolution, i1, f0, f1); break;
                 case Op.Mesh:         rc = Native.nz_heightmap_mesh(i0, vertices, indices, resolution, inputResolution, marginPix, f0, f1, s); break;
             }
+            if (scope != 0) Native.nz_scope_leave();
             status.Value = rc;
         }
+    }
+
+    /// Closes a residency scope when the chain's last job has run: flushes the device mirrors to the host slices.
+    /// Schedule it with the last stage's JobHandle as dependency and hand ITS handle to the pipeline.
+    public struct CloseScopeJob : IJob {
+        public long scope;
+        [NativeDisableContainerSafetyRestriction] public NativeReference<int> status;
+        public void Execute() { status.Value = Native.nz_scope_close(scope); }
     }
 
     public abstract class GpuStage : PipelineStage {

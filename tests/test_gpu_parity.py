@@ -418,3 +418,45 @@ def test_cpp_host_mirror_gives_the_same_bits_as_the_python_mirror(nz):
     assert small["height"] == fnv(d2)
     assert small["vertices"] == fnv(m2.mesh.vertices)
     assert small["indices"] == fnv(m2.mesh.indices)
+
+
+def test_residency_scope_spans_threads(nz, oracle):
+    """The stages of one chain run on DIFFERENT threads (as Unity's job workers do) inside one process-wide scope:
+    the device mirror stays resident across threads/streams and the result equals the single-thread chain."""
+    import threading
+    res = 512
+    want = np.zeros(res * res, np.float32)
+    with nz.host.pipeline():
+        nz.host.fractal(want, res, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 0, 1700)
+        nz.host.kernel_filter(want, None, 2, res, 17)
+        nz.host.flowmap(want, res, 5, 0.0, 0.005)
+        nz.host.min_erosion(want, res, 5)
+
+    data = np.full(res * res, -1.0, np.float32)
+    scope = nz.host.scope_create()
+    errors = []
+
+    def stage(fn):
+        def run():
+            try:
+                with nz.host.in_scope(scope):
+                    fn()
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+        t = threading.Thread(target=run)
+        t.start()
+        t.join()
+
+    stage(lambda: nz.host.fractal(data, res, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 0, 1700))
+    assert (data == -1.0).all()          # nothing came back yet: the mirror is resident, the D2H deferred
+    stage(lambda: nz.host.kernel_filter(data, None, 2, res, 17))
+    stage(lambda: nz.host.flowmap(data, res, 5, 0.0, 0.005))
+    stage(lambda: nz.host.min_erosion(data, res, 5))
+    assert not errors, errors
+    assert (data == -1.0).all()
+    nz.host.scope_close(scope)           # any thread may close: flushes to host
+    assert np.array_equal(data, want)
+    with pytest.raises(nz.NzError):
+        nz.host.scope_enter(scope)       # closed scopes are gone
+    with pytest.raises(nz.NzError):
+        nz.host.scope_leave()
