@@ -54,25 +54,75 @@ __device__ __forceinline__ float permute_centered(float x) {
     return fmaf(-289.0f, q, u);
 }
 
-// Gradient fold of one hash value p in [0,288]: x = 2*frac(p/41) - 1, h = |x| - 0.5, a0 = x - floor(x + 0.5).
-// It is a pure function of p, so the simplex kernel evaluates it once per CTA for all 290 values into shared
-// memory (build_gradient_table) and the octave loop replaces 8 instructions (one of them an XU floor) per
-// corner by a conversion and one LDS.64.  Same operations, same bits.
-constexpr int NZ_GTAB = 290;
+// ---- per-CTA hash tables ------------------------------------------------------------------------------
+// What a basis function derives from a final hash value p in [0,288] is a pure function of p:
+//   simplex / perlin : gradient fold  x = 2*frac(p/41) - 1, h = |x| - 0.5, a0 = x - floor(x + 0.5)
+//   cellular         : feature-point jitter  ox = frac(p/7) - 3/7, oy = mod7(floor(p/7))/7 - 3/7
+//   psrnoise         : rotated gradient  (cos u, sin u), u = 2*pi*frac(p/41 + rot)
+// so the kernel evaluates it once per CTA for all 289 values into shared memory with exactly the operations the
+// straight-line code would use (same bits), and the octave loop replaces 8-10 instructions per corner (2-3 of them
+// XU floors, or a sin and a cos) by a conversion and one LDS.64.
+//
+// Indexing.  FAST (the host proved every lattice index of the launch is below 2^21, so all hash arithmetic is
+// exact integer arithmetic in float): every hash, the last one included, is kept as a CENTRED residue in
+// [-144,144] (round-to-nearest quotient, no XU floor) and the table is indexed by residue + 144, which names the
+// same canonical value.  Otherwise every hash keeps the canonical float-floor form, and the table is a CACHE of
+// the pure function: a final hash value that is not an exact integer in [0,288] (mod289 of a coordinate beyond
+// float's integer range returns 289, negatives or huge garbage) takes the straight-line code instead (a branch
+// that is never taken for sane coordinates), so the result is bit-for-bit the oracle's everywhere.
+constexpr int NZ_TAB = 289;
+template <bool FAST>
+__device__ __forceinline__ float hash_last(float x) { return FAST ? permute_centered(x) : permute(x); }
+template <bool FAST>
+__device__ __forceinline__ float hash_inner(float x) { return FAST ? permute_centered(x) : permute(x); }
+template <bool FAST>
+__device__ __forceinline__ float lattice_residue(float x) {
+    if (FAST) return fmaf(-289.0f, fmaf(x, 1.0f / 289.0f, NZ_MAGIC) - NZ_MAGIC, x);
+    return mod289(x);
+}
+
 __device__ __forceinline__ float2 gradient_fold(float p) {
     const float gx = fmaf(2.0f, fracf_(p * 0.024390243902439f), -1.0f);
     const float h = fabsf(gx) - 0.5f;
     const float a0 = gx - ((gx + NZ_MAGIC) - NZ_MAGIC);
     return make_float2(a0, h);
 }
-__device__ __forceinline__ void build_gradient_table(float2* gtab) {
-    for (int i = threadIdx.x; i < NZ_GTAB; i += blockDim.x) gtab[i] = gradient_fold((float)i);
+__device__ __forceinline__ float2 cellular_jitter(float p) {
+    const float K = 0.142857142857f, Ko = 0.428571428571f;
+    return make_float2(fracf_(p * K) - Ko, fmaf(mod7(floorf(p * K)), K, -Ko));
+}
+__device__ __forceinline__ float2 rotated_gradient(float p, float rot) {
+    float u = fmaf(p, 0.0243902439f, rot);
+    u = fracf_(u) * 6.28318530718f;
+    return make_float2(cosf(u), sinf(u));
+}
+template <int TYPE>
+__device__ __forceinline__ float2 table_function(float p) {
+    if (TYPE == NZ_NOISE_CELLULAR) return cellular_jitter(p);
+    if (TYPE == NZ_NOISE_PERIODIC_PERLIN) return rotated_gradient(p, 0.0f);
+    if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) return rotated_gradient(p, 0.62f);
+    return gradient_fold(p);
+}
+template <int TYPE>
+__device__ __forceinline__ void build_table(float2* tab) {
+    for (int i = threadIdx.x; i < NZ_TAB; i += blockDim.x) {
+        const int c = i - 144;
+        const float p = (float)(c < 0 ? c + 289 : c);
+        tab[i] = table_function<TYPE>(p);
+    }
     __syncthreads();
 }
-__device__ __forceinline__ float2 gradient_lookup(const float2* gtab, float p) {
-    // p is an exact integer in [0,288] wherever the hash is exact; saturate so that garbage coordinates
-    // (lattice index beyond 2^22) can never index outside the table
-    return gtab[min(__float2uint_rz(p), (unsigned)(NZ_GTAB - 1))];
+template <int TYPE, bool FAST>
+__device__ __forceinline__ float2 table_lookup(const float2* tab, float p) {
+    const int i = __float2int_rn(p);
+    if (FAST) return tab[i + 144];
+    if ((unsigned)i <= 288u && (float)i == p) return tab[i > 144 ? i - 145 : i + 144];
+    return table_function<TYPE>(p);
+}
+template <int TYPE>
+__host__ __device__ constexpr bool uses_table() {
+    return TYPE == NZ_NOISE_SIMPLEX || TYPE == NZ_NOISE_PERLIN || TYPE == NZ_NOISE_CELLULAR || TYPE == NZ_NOISE_PERIODIC_PERLIN ||
+           TYPE == NZ_NOISE_ROTATED_SIMPLEX;
 }
 
 // returns dot(m, g), i.e. snoise(float2) / 130 (the getter folds the factor, see basis_value)
@@ -88,27 +138,21 @@ __device__ __forceinline__ float snoise2_raw(float vx, float vy, const float2* g
     float i1x = xgty ? 1.0f : 0.0f, i1y = xgty ? 0.0f : 1.0f;
     float x1x = x0x + Cx - i1x, x1y = x0y + Cx - i1y;
     float x2x = x0x + Cz, x2y = x0y + Cz;
-    if (FAST) {
-        // lattice indices below 2^21 (the host checks the tile): the centred residue is congruent to the
-        // canonical one and saves two more XU floors; the outer hash canonicalises
-        ix = fmaf(-289.0f, fmaf(ix, 1.0f / 289.0f, NZ_MAGIC) - NZ_MAGIC, ix);
-        iy = fmaf(-289.0f, fmaf(iy, 1.0f / 289.0f, NZ_MAGIC) - NZ_MAGIC, iy);
-    } else {
-        ix = mod289(ix);
-        iy = mod289(iy);
-    }
+    ix = lattice_residue<FAST>(ix);
+    iy = lattice_residue<FAST>(iy);
     float py0 = permute_centered(iy), py1 = permute_centered(iy + 1.0f);
     const float hA = py0 + ix, hB = py1 + ix;     // (py + ix) + i1x with i1x in {0,1}: pick, do not recompute
-    float p0 = permute(hA);
-    float p1 = permute(xgty ? hA + 1.0f : hB);
-    float p2 = permute(hB + 1.0f);
+    float p0 = hash_last<FAST>(hA);
+    float p1 = hash_last<FAST>(xgty ? hA + 1.0f : hB);
+    float p2 = hash_last<FAST>(hB + 1.0f);
     float m0 = fmaxf(fmaf(-x0y, x0y, fmaf(-x0x, x0x, 0.5f)), 0.0f);
     float m1 = fmaxf(fmaf(-x1y, x1y, fmaf(-x1x, x1x, 0.5f)), 0.0f);
     float m2 = fmaxf(fmaf(-x2y, x2y, fmaf(-x2x, x2x, 0.5f)), 0.0f);
     m0 = m0 * m0; m0 = m0 * m0;
     m1 = m1 * m1; m1 = m1 * m1;
     m2 = m2 * m2; m2 = m2 * m2;
-    const float2 gr0 = gradient_lookup(gtab, p0), gr1 = gradient_lookup(gtab, p1), gr2 = gradient_lookup(gtab, p2);
+    const float2 gr0 = table_lookup<NZ_NOISE_SIMPLEX, FAST>(gtab, p0), gr1 = table_lookup<NZ_NOISE_SIMPLEX, FAST>(gtab, p1),
+                 gr2 = table_lookup<NZ_NOISE_SIMPLEX, FAST>(gtab, p2);
     const float a0 = gr0.x, h0 = gr0.y, a1 = gr1.x, h1 = gr1.y, a2 = gr2.x, h2 = gr2.y;
     m0 = m0 * taylorInvSqrt(fmaf(h0, h0, a0 * a0));
     m1 = m1 * taylorInvSqrt(fmaf(h1, h1, a1 * a1));
@@ -120,36 +164,38 @@ __device__ __forceinline__ float snoise2_raw(float vx, float vy, const float2* g
 }
 
 // ---- cnoise(float2) ---------------------------------------------------------------------------
-__device__ __forceinline__ float cnoise2(float Px, float Py) {
+template <bool FAST>
+__device__ __forceinline__ float cnoise2(float Px, float Py, const float2* gtab) {
     float flx = floorf(Px), fly = floorf(Py);
     float pfx0 = Px - flx, pfy0 = Py - fly;
     float pfx1 = pfx0 - 1.0f, pfy1 = pfy0 - 1.0f;
-    float pix0 = mod289(flx), pix1 = mod289(flx + 1.0f);
-    float piy0 = mod289(fly), piy1 = mod289(fly + 1.0f);
-    float hx0 = permute(pix0), hx1 = permute(pix1);
+    float pix0 = lattice_residue<FAST>(flx), pix1 = lattice_residue<FAST>(flx + 1.0f);
+    float piy0 = lattice_residue<FAST>(fly), piy1 = lattice_residue<FAST>(fly + 1.0f);
+    float hx0 = hash_inner<FAST>(pix0), hx1 = hash_inner<FAST>(pix1);   // inner hashes only feed the last hash
     float n[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         float fx = (k & 1) ? pfx1 : pfx0, fy = (k >> 1) ? pfy1 : pfy0;
-        float i = permute(((k & 1) ? hx1 : hx0) + ((k >> 1) ? piy1 : piy0));
-        float g = fmaf(fracf_(i * (1.0f / 41.0f)), 2.0f, -1.0f);
-        float gy = fabsf(g) - 0.5f;
-        float gx = g - floorf(g + 0.5f);
-        float norm = taylorInvSqrt(dot2(gx, gy, gx, gy));
-        n[k] = dot2(gx * norm, gy * norm, fx, fy);
+        float i = hash_last<FAST>(((k & 1) ? hx1 : hx0) + ((k >> 1) ? piy1 : piy0));
+        const float2 g = table_lookup<NZ_NOISE_PERLIN, FAST>(gtab, i);      // (gx, gy) = (g - floor(g + 0.5), |g| - 0.5), g = 2*frac(i/41) - 1
+        float norm = taylorInvSqrt(dot2(g.x, g.y, g.x, g.y));
+        n[k] = dot2(g.x * norm, g.y * norm, fx, fy);
     }
     float fdx = fade(pfx0), fdy = fade(pfy0);
     return 2.3f * lerpf_(lerpf_(n[0], n[1], fdx), lerpf_(n[2], n[3], fdx), fdy);
 }
 
 // ---- psrnoise(float2, float2 per, float rot) --------------------------------------------------
-__device__ __forceinline__ void rgrad2(float px, float py, float rot, float& gx, float& gy) {
-    float u = fmaf(permute(permute(px) + py), 0.0243902439f, rot);
-    u = fracf_(u) * 6.28318530718f;
-    gx = cosf(u);
-    gy = sinf(u);
+// The hash arguments are half-integers that can exceed float's exact-product range, so the hashes keep the
+// canonical float-floor form; only the (cos, sin) of the final hash value comes from the table.
+template <int TYPE>
+__device__ __forceinline__ void rgrad2(float px, float py, const float2* rtab, float& gx, float& gy) {
+    const float2 g = table_lookup<TYPE, false>(rtab, permute(permute(px) + py));
+    gx = g.x;
+    gy = g.y;
 }
-__device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, float pery, float rot) {
+template <int TYPE>
+__device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, float pery, const float2* rtab) {
     posy += 0.001f;
     float ux = fmaf(posy, 0.5f, posx), uy = posy;
     float i0x = floorf(ux), i0y = floorf(uy);
@@ -165,9 +211,9 @@ __device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, f
     float xw0 = fmodf(p0x, perx), xw1 = fmodf(p1x, perx), xw2 = fmodf(p2x, perx);
     float yw0 = fmodf(p0y, pery), yw1 = fmodf(p1y, pery), yw2 = fmodf(p2y, pery);
     float g0x, g0y, g1x, g1y, g2x, g2y;
-    rgrad2(fmaf(0.5f, yw0, xw0), yw0, rot, g0x, g0y);
-    rgrad2(fmaf(0.5f, yw1, xw1), yw1, rot, g1x, g1y);
-    rgrad2(fmaf(0.5f, yw2, xw2), yw2, rot, g2x, g2y);
+    rgrad2<TYPE>(fmaf(0.5f, yw0, xw0), yw0, rtab, g0x, g0y);
+    rgrad2<TYPE>(fmaf(0.5f, yw1, xw1), yw1, rtab, g1x, g1y);
+    rgrad2<TYPE>(fmaf(0.5f, yw2, xw2), yw2, rtab, g2x, g2y);
     float w0 = dot2(g0x, g0y, d0x, d0y), w1 = dot2(g1x, g1y, d1x, d1y), w2 = dot2(g2x, g2y, d2x, d2y);
     float t0 = fmaxf(0.8f - dot2(d0x, d0y, d0x, d0y), 0.0f);
     float t1 = fmaxf(0.8f - dot2(d1x, d1y, d1x, d1y), 0.0f);
@@ -179,25 +225,23 @@ __device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, f
 }
 
 // ---- cellular(float2) -> F1*F2 rectified ------------------------------------------------------
-__device__ __forceinline__ float cellular2_rectified(float Px, float Py) {
-    const float K = 0.142857142857f, Ko = 0.428571428571f;
+template <bool FAST>
+__device__ __forceinline__ float cellular2_rectified(float Px, float Py, const float2* jtab) {
     float flx = floorf(Px), fly = floorf(Py);
-    float Pix = mod289(flx), Piy = mod289(fly);
+    float Pix = lattice_residue<FAST>(flx), Piy = lattice_residue<FAST>(fly);
     float Pfx = Px - flx, Pfy = Py - fly;
     float d[3][3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const float oic = (float)(c - 1);
         const float xo = 0.5f - (float)c;
-        float pxc = permute(Pix + oic);
+        float pxc = hash_inner<FAST>(Pix + oic);   // inner hash: only feeds the last hash
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const float oij = (float)(j - 1), ofj = (float)j - 0.5f;
-            float p = permute(pxc + Piy + oij);
-            float ox = fracf_(p * K) - Ko;
-            float oy = fmaf(mod7(floorf(p * K)), K, -Ko);
-            float dx = Pfx + xo + ox;
-            float dy = Pfy - ofj + oy;
+            const float2 o = table_lookup<NZ_NOISE_CELLULAR, FAST>(jtab, hash_last<FAST>(pxc + Piy + oij));   // (ox, oy)
+            float dx = Pfx + xo + o.x;
+            float dy = Pfy - ofj + o.y;
             d[c][j] = fmaf(dy, dy, dx * dx);
         }
     }
@@ -309,15 +353,15 @@ __device__ __forceinline__ float basis_value(float x, float z, const float2* gta
         float vx = fmaf(0.5f, sinf(x), 0.5f), vz = fmaf(0.5f, sinf(z), 0.5f);
         return vx * vz;
     } else if (TYPE == NZ_NOISE_PERLIN) {
-        return rectify(cnoise2(x, z));
+        return rectify(cnoise2<FAST>(x, z, gtab));
     } else if (TYPE == NZ_NOISE_PERIODIC_PERLIN) {
-        return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.0f));
+        return rectify(psrnoise2<TYPE>(x, z, 1010.0f, 102.0f, gtab));
     } else if (TYPE == NZ_NOISE_SIMPLEX) {
         return fmaf(65.0f, snoise2_raw<FAST>(x, z, gtab), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
     } else if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) {
-        return rectify(psrnoise2(x, z, 1010.0f, 102.0f, 0.62f));
+        return rectify(psrnoise2<TYPE>(x, z, 1010.0f, 102.0f, gtab));
     } else if (TYPE == NZ_NOISE_CELLULAR) {
-        return cellular2_rectified(x, z);
+        return cellular2_rectified<FAST>(x, z, gtab);
     } else {
         float xz = x + z;
         float s2 = xz * -0.211324865405187f;
@@ -332,8 +376,8 @@ constexpr int NZ_FBM_THREADS = 128;
 
 template <int TYPE, int CELLS, bool FAST>
 __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__ dst, FractalParams p) {
-    __shared__ float2 gtab[TYPE == NZ_NOISE_SIMPLEX ? NZ_GTAB : 1];
-    if (TYPE == NZ_NOISE_SIMPLEX) build_gradient_table(gtab);
+    __shared__ float2 gtab[uses_table<TYPE>() ? NZ_TAB : 1];
+    if (uses_table<TYPE>()) build_table<TYPE>(gtab);
     const int r = blockIdx.y;
     const int xbase = blockIdx.x * (NZ_FBM_THREADS * CELLS) + threadIdx.x;
     const float zi = ((float)(p.z_first + r) + p.posz) / p.noise_size;
@@ -363,7 +407,7 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
 template <int TYPE, int CELLS>
 int32_t launch_typed(float* d_dst, const FractalParams& p, cudaStream_t s) {
     dim3 grid(cdiv(p.width, NZ_FBM_THREADS * CELLS), p.rows);
-    if (TYPE == NZ_NOISE_SIMPLEX && p.fast_hash)
+    if ((TYPE == NZ_NOISE_SIMPLEX || TYPE == NZ_NOISE_PERLIN || TYPE == NZ_NOISE_CELLULAR) && p.fast_hash)
         fbm_kernel<TYPE, CELLS, true><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
     else
         fbm_kernel<TYPE, CELLS, false><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
