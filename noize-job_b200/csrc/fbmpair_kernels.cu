@@ -1,0 +1,225 @@
+// fbmpair_kernels.cu — simplex fBm, second generation: packed FP32 pairs + bank-private hash tables.
+//
+// Same function as fbm_kernel<NZ_NOISE_SIMPLEX, *, FAST> in noise_kernels.cu (FractalGenerator<SimplexGetter>,
+// Noise/Fractal/Fractal.cs:114-138,196-205) and bit-for-bit the same results (tests compare the two kernels
+// bitwise); what changes is how the B200 executes it.  The first-generation kernel is issue-bound: 111
+// instructions per cell and octave, 90 of them scalar FP32, 92 % issue-slot utilisation.  Two changes:
+//
+//  1. Packed FP32 (FFMA2/FMUL2, sm_100).  A thread owns 4 cells of one column (4 consecutive rows) and carries
+//     them as two float2 pairs; every FP operation of the octave body is one f32x2 instruction per pair.  An
+//     f32x2 instruction occupies the FP32 pipe for two cycles but only ONE issue slot (tools/ubench2: FFMA2
+//     1.92 warp-inst/clk/SM, and ALU/LSU instructions fill the freed slots), so the FP work costs half the issue
+//     bandwidth.  Each half is an IEEE round-to-nearest fma/mul/add, identical to the scalar instruction.
+//
+//  2. The hash becomes three table walks.  With every lattice index below 2^21 (FAST, host-checked) the hash
+//     chain  p = permute(permute(iy + j) + ix + i)  is exact integer arithmetic, so
+//        T1[iy mod 289]            = permute(iy)                       (one LDS per lattice row)
+//        T2[(T1 + ix) mod 289]     = (a0, h, norm) of permute(T1 + ix) (three LDS per corner)
+//     replaces 5 float hashes (25 FP instructions), the gradient fold and the normalisation polynomial
+//     (9 more).  To make random lookups free of bank conflicts each table is BANK-PRIVATE: 32 copies, one per
+//     lane, interleaved so that lane l only ever touches bank l (row stride 128 B).  Four tables of 290 rows
+//     = 148,480 B of shared memory — one persistent 1024-thread CTA per SM, which a B200 SM (227 KB) holds.
+//     Indices never leave the float domain through a conversion: the residue r is turned into address bits by
+//     the magic add (r + 1.5*2^23 has r in its low mantissa bits) and one shift-add; the table entries carry
+//     the compensating constants.  The wrap of (T1 + ix) into [0,289) is an unsigned min.
+//
+// Result: ~57 issue slots and ~52 FP-pipe cycles per cell and octave instead of 111 / 90.
+#include "nz_common.cuh"
+
+namespace nz {
+namespace {
+
+constexpr float MAGIC = 12582912.0f;                                   // 1.5 * 2^23
+constexpr uint32_t MAGIC_SHL7 = (uint32_t)(0x4B400000ull << 7);        // bits(MAGIC) << 7, mod 2^32
+constexpr int PAIR_THREADS = 1024;
+constexpr int ROW_BYTES = 128;                                         // 32 lanes x 4 B
+constexpr int TAB_ROWS = 290;                                          // 289 residues + one wrapped row
+constexpr int TAB_BYTES = TAB_ROWS * ROW_BYTES;
+constexpr int OFF_T1 = 0, OFF_A = TAB_BYTES, OFF_H = 2 * TAB_BYTES, OFF_N = 3 * TAB_BYTES;
+constexpr int PAIR_SMEM = 4 * TAB_BYTES;
+constexpr uint32_t WRAP = 289u * ROW_BYTES;
+
+typedef float2 P;
+__device__ __forceinline__ P bc(float s) { return make_float2(s, s); }
+__device__ __forceinline__ P neg(P a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ P pfma(P a, P b, P c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ P pmul(P a, P b) { return __fmul2_rn(a, b); }
+// Additions are issued as fma(a, 1, b), which is the same IEEE sum: ptxas 12.9 contracts a mul.rn.f32x2 feeding
+// an add.rn.f32x2 into one FFMA2 even under --fmad=false, which would change the rounding the oracle fixes.
+__device__ __forceinline__ P padd(P a, P b) { return __ffma2_rn(a, bc(1.0f), b); }
+__device__ __forceinline__ P psub(P a, P b) { return __ffma2_rn(a, bc(1.0f), neg(b)); }
+__device__ __forceinline__ P pfloor(P a) { return make_float2(floorf(a.x), floorf(a.y)); }
+__device__ __forceinline__ P pmax0(P a) { return make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)); }
+
+// table reads: byte offsets relative to the start of the dynamic shared memory (the CTA's window base rides in a
+// uniform register of the LDS, so offsets can be wrapped with an unsigned min)
+extern __shared__ __align__(16) unsigned char sm[];
+__device__ __forceinline__ uint32_t lds_u32(uint32_t off) { return *reinterpret_cast<const uint32_t*>(sm + off); }
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t off) { return *reinterpret_cast<const float*>(sm + OFF + off); }
+
+// canonical hash of an integer residue class, exact (the float form is exact on this domain: tests/test_oracle.py)
+__device__ __forceinline__ int permute_int(int a) {
+    a %= 289;
+    if (a < 0) a += 289;
+    return ((34 * a + 1) * a) % 289;
+}
+
+// Every lane writes its own copy (its own bank) of every row.
+__device__ void build_tables() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < TAB_ROWS; r += nwarps) {
+        // T1 row r  <->  lattice residue iy = r - 144 in [-144, 145]:
+        //   byte offset of T2 row (permute(iy) + 144), this lane's column, minus the bits the magic-number form
+        //   of ix adds when it is shifted in (see the octave body)
+        const uint32_t t1 = (uint32_t)(permute_int(r - 144) + 144) * ROW_BYTES + lane * 4 - MAGIC_SHL7;
+        *reinterpret_cast<uint32_t*>(sm + OFF_T1 + r * ROW_BYTES + lane * 4) = t1;
+        // T2 row r  <->  hash argument (r - 144) mod 289 (row 289 repeats row 0): the gradient fold of its hash,
+        // with the operations of gradient_fold()/taylorInvSqrt in noise_kernels.cu
+        const float p = (float)permute_int(r - 144);
+        const float fr = p * 0.024390243902439f;
+        const float gx = fmaf(2.0f, fr - floorf(fr), -1.0f);
+        const float h = fabsf(gx) - 0.5f;
+        const float a0 = gx - ((gx + MAGIC) - MAGIC);
+        const float n = fmaf(-0.85373472095314f, fmaf(h, h, a0 * a0), 1.79284291400159f);
+        *reinterpret_cast<float*>(sm + OFF_A + r * ROW_BYTES + lane * 4) = a0;
+        *reinterpret_cast<float*>(sm + OFF_H + r * ROW_BYTES + lane * 4) = h;
+        *reinterpret_cast<float*>(sm + OFF_N + r * ROW_BYTES + lane * 4) = n;
+    }
+    __syncthreads();
+}
+
+struct Corner {
+    float a0, h, n;
+};
+__device__ __forceinline__ Corner fetch(uint32_t addr) {
+    Corner c;
+    c.a0 = lds_f32<OFF_A>(addr);
+    c.h = lds_f32<OFF_H>(addr);
+    c.n = lds_f32<OFF_N>(addr);
+    return c;
+}
+
+// one octave of two cells (a pair) that share vx; returns dot(m, g) = snoise/130 for both
+__device__ __forceinline__ P snoise_pair(float vx, float vxCy, P vy, uint32_t c1) {
+    const float Cx = 0.211324865405187f, Cy = 0.366025403784439f, Cz = -0.577350269189626f;
+    const P s = pfma(vy, bc(Cy), bc(vxCy));                       // dot2(vx, vy, Cy, Cy)
+    const P ix = pfloor(padd(bc(vx), s)), iy = pfloor(padd(vy, s));
+    const P t = pfma(iy, bc(Cx), pmul(ix, bc(Cx)));               // dot2(ix, iy, Cx, Cx)
+    const P x0x = padd(psub(bc(vx), ix), t), x0y = padd(psub(vy, iy), t);
+    const bool gA = x0x.x > x0y.x, gB = x0x.y > x0y.y;
+    const P i1x = make_float2(gA ? 1.0f : 0.0f, gB ? 1.0f : 0.0f);
+    const P i1y = make_float2(gA ? 0.0f : 1.0f, gB ? 0.0f : 1.0f);
+    const P x1x = psub(padd(x0x, bc(Cx)), i1x), x1y = psub(padd(x0y, bc(Cx)), i1y);
+    const P x2x = padd(x0x, bc(Cz)), x2y = padd(x0y, bc(Cz));
+    // lattice residues (centred, exact) and their address bits
+    const P rx = pfma(bc(-289.0f), psub(pfma(ix, bc(1.0f / 289.0f), bc(MAGIC)), bc(MAGIC)), ix);
+    const P ry = pfma(bc(-289.0f), psub(pfma(iy, bc(1.0f / 289.0f), bc(MAGIC)), bc(MAGIC)), iy);
+    const P bx = padd(rx, bc(MAGIC)), by = padd(ry, bc(MAGIC));
+    Corner c0[2], c1_[2], c2[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t ixb = __float_as_uint(e ? bx.y : bx.x) << 7, iyb = __float_as_uint(e ? by.y : by.x) << 7;
+        const bool g = e ? gB : gA;
+        const uint32_t a1 = iyb + c1;                              // T1 row of iy (this lane's column)
+        const uint32_t pv0 = lds_u32(a1), pv1 = lds_u32(a1 + ROW_BYTES);
+        uint32_t hA = ixb + pv0, hB = ixb + pv1;                   // T2 row (permute(iy+j) + ix + 144), unwrapped
+        hA = min(hA, hA - WRAP);                                   // row index into [0,289): unsigned min
+        hB = min(hB, hB - WRAP);
+        const uint32_t hM = g ? hA + ROW_BYTES : hB;               // middle corner: (i1x, i1y) = (1,0) or (0,1)
+        c0[e] = fetch(hA);
+        c1_[e] = fetch(hM);
+        c2[e] = fetch(hB + ROW_BYTES);
+    }
+    P m0 = pmax0(pfma(neg(x0y), x0y, pfma(neg(x0x), x0x, bc(0.5f))));
+    P m1 = pmax0(pfma(neg(x1y), x1y, pfma(neg(x1x), x1x, bc(0.5f))));
+    P m2 = pmax0(pfma(neg(x2y), x2y, pfma(neg(x2x), x2x, bc(0.5f))));
+    m0 = pmul(m0, m0); m0 = pmul(m0, m0);
+    m1 = pmul(m1, m1); m1 = pmul(m1, m1);
+    m2 = pmul(m2, m2); m2 = pmul(m2, m2);
+    m0 = pmul(m0, make_float2(c0[0].n, c0[1].n));
+    m1 = pmul(m1, make_float2(c1_[0].n, c1_[1].n));
+    m2 = pmul(m2, make_float2(c2[0].n, c2[1].n));
+    const P g0 = pfma(make_float2(c0[0].h, c0[1].h), x0y, pmul(make_float2(c0[0].a0, c0[1].a0), x0x));
+    const P g1 = pfma(make_float2(c1_[0].h, c1_[1].h), x1y, pmul(make_float2(c1_[0].a0, c1_[1].a0), x1x));
+    const P g2 = pfma(make_float2(c2[0].h, c2[1].h), x2y, pmul(make_float2(c2[0].a0, c2[1].a0), x2x));
+    return pfma(m2, g2, pfma(m1, g1, pmul(m0, g0)));              // dot3(m, g)
+}
+
+// Work item = 4*(PAIR_THREADS >> wshift) rows x (1 << wshift) columns; thread (ty, tx) owns rows 4*ty..4*ty+3 of
+// column tx.  Lanes are consecutive columns, so every row store is a coalesced 128 B line per warp.
+__global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_simplex_pair_kernel(float* __restrict__ dst, FractalParams p, int wshift,
+                                                                          int col_blocks, int n_items) {
+    build_tables();
+    const int lane = threadIdx.x & 31;
+    uint32_t c1 = OFF_T1 + 144 * ROW_BYTES + lane * 4 - MAGIC_SHL7;
+    asm volatile("" : "+r"(c1));   // keep the sum in one register (the constant does not fit an LDS immediate)
+    const int tx = threadIdx.x & ((1 << wshift) - 1), ty = threadIdx.x >> wshift;
+    const int rows_per_item = 4 * (PAIR_THREADS >> wshift);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cb = item % col_blocks, rg = item / col_blocks;
+        const int x = (cb << wshift) + tx;
+        const int r0 = rg * rows_per_item + 4 * ty;
+        const float xi = ((float)x + p.posx) / p.noise_size;
+        P zi[2], t[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            zi[q].x = ((float)(p.z_first + r0 + 2 * q) + p.posz) / p.noise_size;
+            zi[q].y = ((float)(p.z_first + r0 + 2 * q + 1) + p.posz) / p.noise_size;
+            t[q] = bc(0.0f);
+        }
+        float detune = 0.0f, f = 1.0f, a = p.start_amp;
+        for (int i = 0; i < p.octaves; i++) {
+            const float vx = f * xi;
+            const float vxCy = vx * 0.366025403784439f;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const P raw = snoise_pair(vx, vxCy, pmul(bc(f), zi[q]), c1);
+                t[q] = pfma(bc(a), pfma(bc(65.0f), raw, bc(0.5f)), t[q]);   // a * Rectify(130 * raw) + t
+            }
+            detune += p.detune_rate;
+            f *= (p.stepdown - detune);
+            a *= p.G;
+        }
+        if (x < p.width) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int r = r0 + 2 * q;
+                if (r < p.rows) dst[(size_t)r * p.width + x] = t[q].x / p.norm;
+                if (r + 1 < p.rows) dst[(size_t)(r + 1) * p.width + x] = t[q].y / p.norm;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+bool fractal_pair_supported(int noise_type, const FractalParams& p) {
+    return noise_type == NZ_NOISE_SIMPLEX && p.fast_hash && p.width >= 32 && (long long)p.width * p.rows >= (1 << 19);
+}
+
+int32_t launch_fractal_pair(float* d_dst, const FractalParams& p, cudaStream_t s) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        NZ_CUDA(cudaGetDevice(&dev));
+        NZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static bool configured = false;   // per-process; the attribute is per-function and sticky
+    if (!configured) {
+        NZ_CUDA(cudaFuncSetAttribute(fbm_simplex_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+        configured = true;
+    }
+    int wshift = 5;
+    while ((1 << wshift) < p.width && wshift < 10) wshift++;
+    const int col_blocks = cdiv(p.width, 1 << wshift);
+    const int rows_per_item = 4 * (PAIR_THREADS >> wshift);
+    const long long n_items = (long long)col_blocks * cdiv(p.rows, rows_per_item);
+    NZ_REQUIRE(n_items < (1ll << 31), "nz_fractal: window too large");
+    const int grid = n_items < sms ? (int)n_items : sms;
+    fbm_simplex_pair_kernel<<<grid, PAIR_THREADS, PAIR_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
+    NZ_LAUNCHED();
+    return NZ_OK;
+}
+
+}  // namespace nz

@@ -55,6 +55,43 @@ def test_c1_simplex_fbm(nz, oracle, pos):
     assert np.abs(got - ref).max() <= TOL_NOISE
 
 
+@pytest.fixture
+def fbm_path(monkeypatch):
+    """Force one of the two simplex kernels (NZ_FBM_PATH is read by the library at every launch)."""
+    def force(which):
+        if which is None:
+            monkeypatch.delenv("NZ_FBM_PATH", raising=False)
+        else:
+            monkeypatch.setenv("NZ_FBM_PATH", which)
+    return force
+
+
+@pytest.mark.parametrize("res,pos", [(96, (0, 0)), (256, (0, 424)), (600, (-5000, 7777)), (1031, (100000, 3)),
+                                      (2048, (14336, 14336))])
+def test_packed_pair_simplex_kernel_is_bit_identical_to_the_scalar_kernel(nz, oracle, fbm_path, res, pos):
+    # fbmpair_kernels.cu (f32x2 pairs + bank-private hash tables) vs fbm_kernel<SIMPLEX> in noise_kernels.cu
+    fbm_path("scalar")
+    a = gpu_fractal(nz, res, 3, *pos)
+    fbm_path("pair")
+    b = gpu_fractal(nz, res, 3, *pos)
+    fbm_path(None)
+    assert np.isfinite(a).all()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if res <= 600:
+        ref = ref_fractal(oracle, res, 3, *pos)
+        assert np.abs(b - ref).max() <= TOL_NOISE
+
+
+def test_packed_pair_simplex_kernel_detune_and_odd_parameters(nz, fbm_path):
+    kw = dict(hurst=0.9001, octaves=6, noise_size=7475, stepdown=2.17, detune_rate=0.013, starting_amplitude=0.7)
+    fbm_path("scalar")
+    a = gpu_fractal(nz, 777, 3, 12345, -999, **kw)
+    fbm_path("pair")
+    b = gpu_fractal(nz, 777, 3, 12345, -999, **kw)
+    fbm_path(None)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 @pytest.mark.parametrize("noise_type", range(8))
 def test_every_basis_matches_oracle(nz, oracle, noise_type):
     got = gpu_fractal(nz, 192, noise_type, 1000, 3000)
