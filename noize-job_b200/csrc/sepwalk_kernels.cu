@@ -21,6 +21,7 @@
 // take the edge lane's value (one shuffle, border warps only), and at the top/bottom of the grid a stage's
 // window is filled with / keeps repeating the X pass of its first / last row.  That is exactly "an
 // out-of-range neighbour reads the edge cell's current-iteration value".
+#include <stdlib.h>
 #include "nz_common.cuh"
 
 namespace nz {
@@ -29,14 +30,14 @@ namespace {
 constexpr int VW = 4;
 constexpr int STRIP = 32 * VW;       // 128 columns per warp
 constexpr int WALK_WARPS = 4;        // warps (strips) per CTA
-constexpr int WALK_ZC = 256;         // rows per chunk
+constexpr int WALK_ZC = 256;         // rows per chunk (default; NZ_WALK_ZC overrides while profiling)
 
 template <int R>
 struct TapsW {
     float k[2 * R + 1];
 };
 
-constexpr int PFR = 16;              // rows of the per-warp cp.async landing ring (PFR-1 in flight)
+// PFR = rows of the per-warp cp.async landing ring (PFR-1 in flight); template parameter, power of two
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -51,7 +52,7 @@ __device__ __forceinline__ float4 ld_shared_f4(unsigned smem_addr) {
 }
 
 // BORDER = false is the steady-state body for warps whose strip and chunk touch no grid border: no clamp logic.
-template <int R, int T, bool SCALE, bool BORDER>
+template <int R, int T, bool SCALE, bool BORDER, int PFR>
 __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor,
                                           const TapsW<R>& kx, const TapsW<R>& kz, int wx0, int zc0, int zc1, unsigned ring_base) {
     constexpr int KS = 2 * R + 1;
@@ -184,23 +185,24 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     }
 }
 
-template <int R, int T, bool SCALE>
+template <int R, int T, bool SCALE, int PFR>
 __global__ void __launch_bounds__(WALK_WARPS * 32)
-sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz) {
+sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz,
+                int zc) {
     constexpr int HALO = (R * T + 3) & ~3;
     constexpr int USE = STRIP - 2 * HALO;
     const int strip = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
     const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
     if (wx0 + HALO >= W) return;                 // whole warp: nothing to produce
-    const int zc0 = blockIdx.y * WALK_ZC, zc1 = min(zc0 + WALK_ZC, H);
+    const int zc0 = blockIdx.y * zc, zc1 = min(zc0 + zc, H);
     // steady state: the strip lies inside the grid and so does the chunk with its warm-up and drain rows
     const bool plain = wx0 >= 0 && wx0 + STRIP <= W && zc0 - R * T - (2 * R + 1) > 0 && zc1 - 1 + R * T <= H - 1;
-    __shared__ __align__(16) float ring[WALK_WARPS][PFR][STRIP];
-    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&ring[threadIdx.x >> 5][0][0]);
+    extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP]
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (PFR * STRIP));
     if (plain)
-        walk_body<R, T, SCALE, false>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+        walk_body<R, T, SCALE, false, PFR>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
     else
-        walk_body<R, T, SCALE, true>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+        walk_body<R, T, SCALE, true, PFR>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
 }
 
 template <int R, int T>
@@ -213,11 +215,26 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     }
     constexpr int HALO = (R * T + 3) & ~3;
     constexpr int USE = STRIP - 2 * HALO;
-    dim3 grid(cdiv(cdiv(width, USE), WALK_WARPS), cdiv(rows, WALK_ZC));
-    if (factor == 1.0f)
-        sep_walk_kernel<R, T, false><<<grid, WALK_WARPS * 32, 0, s>>>(in, out, width, rows, factor, tx, tz);
-    else
-        sep_walk_kernel<R, T, true><<<grid, WALK_WARPS * 32, 0, s>>>(in, out, width, rows, factor, tx, tz);
+    const char* ez = getenv("NZ_WALK_ZC");
+    const char* ep = getenv("NZ_WALK_PFR");
+    const int zc = ez ? atoi(ez) : WALK_ZC;
+    const int pfr = ep ? atoi(ep) : 16;
+    dim3 grid(cdiv(cdiv(width, USE), WALK_WARPS), cdiv(rows, zc));
+#define NZ_WALK_LAUNCH(SC, PF)                                                                                          \
+    do {                                                                                                               \
+        const size_t sm = (size_t)WALK_WARPS * PF * STRIP * sizeof(float);                                             \
+        if (sm > 48 * 1024)                                                                                            \
+            NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, SC, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        sep_walk_kernel<R, T, SC, PF><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc);     \
+    } while (0)
+    if (factor == 1.0f) {
+        if (pfr == 8) NZ_WALK_LAUNCH(false, 8);
+        else if (pfr == 32) NZ_WALK_LAUNCH(false, 32);
+        else NZ_WALK_LAUNCH(false, 16);
+    } else {
+        NZ_WALK_LAUNCH(true, 16);
+    }
+#undef NZ_WALK_LAUNCH
     NZ_LAUNCHED();
     return NZ_OK;
 }
