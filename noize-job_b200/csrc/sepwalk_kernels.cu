@@ -30,7 +30,7 @@ namespace {
 constexpr int VW = 4;
 constexpr int STRIP = 32 * VW;       // 128 columns per warp
 constexpr int WALK_WARPS = 4;        // warps (strips) per CTA
-constexpr int WALK_ZC = 256;         // rows per chunk (default; NZ_WALK_ZC overrides while profiling)
+constexpr int WALK_ZC = 128;         // rows per chunk (default; NZ_WALK_ZC overrides while profiling): 128 beat 64/96/192/256/512
 
 template <int R>
 struct TapsW {
@@ -153,13 +153,20 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
 #pragma unroll
                             for (int q = 0; q < VW; q++) win[t][P][q] = xp[q];
                         }
-                        // Z pass of row rt-R: taps j = 0..2R pair K[j] with row rt-j (descending k of the reference)
+                        // Z pass of row rt-R: taps j = 0..2R pair K[j] with row rt-j (descending k of the reference).
+                        // Packed FP32: columns (0,1) and (2,3) of the lane are one f32x2 chain each -- FFMA2 with a
+                        // broadcast tap costs one issue slot for two IEEE fmas (same bits as the scalar chain).
 #pragma unroll
-                        for (int q = 0; q < VW; q++) {
-                            float tot = 0.0f;
+                        for (int q = 0; q < VW; q += 2) {
+                            float2 tot = make_float2(0.0f, 0.0f);
 #pragma unroll
-                            for (int j = 0; j < KS; j++) tot = fmaf(win[t][(P - j + 2 * KS) % KS][q], kz.k[j], tot);
-                            v[q] = SCALE ? tot * factor : tot;
+                            for (int j = 0; j < KS; j++) {
+                                const int row = (P - j + 2 * KS) % KS;
+                                tot = __ffma2_rn(make_float2(win[t][row][q], win[t][row][q + 1]), make_float2(kz.k[j], kz.k[j]), tot);
+                            }
+                            if (SCALE) tot = __fmul2_rn(tot, make_float2(factor, factor));
+                            v[q] = tot.x;
+                            v[q + 1] = tot.y;
                         }
                         if (has_left) {
                             const float e = __shfl_sync(0xffffffffu, v[0], L0);
