@@ -94,6 +94,23 @@ typedef enum {
     NZ_MESH__COUNT = 2
 } nz_mesh_type;
 
+/* ConstantStage.ConstantOperationType, Filter/ConstantStage.cs:15-18 (index into the delegate table :20-23) */
+typedef enum {
+    NZ_CONSTANT_MULTIPLY = 0,
+    NZ_CONSTANT_BINARIZE = 1,
+    NZ_CONSTANT__COUNT = 2
+} nz_constant_op;
+
+/* ReductionType, Filter/Reduce/ReduceStage.cs:12-18 (index into the delegate table :22-28) */
+typedef enum {
+    NZ_REDUCE_SUBTRACT = 0,
+    NZ_REDUCE_MULTIPLY = 1,
+    NZ_REDUCE_ROOTSUMSQUARES = 2,
+    NZ_REDUCE_MAX = 3,
+    NZ_REDUCE_MIN = 4,
+    NZ_REDUCE__COUNT = 5
+} nz_reduce_op;
+
 #define NZ_MAX_KERNEL_WIDTH 25          /* BlurHelper.max_width, BlurKernels.cs:29 */
 #define NZ_MESH_VERTEX_BYTES 48         /* PositionStream32.Stream0, Mesh/Streams/PositionStream.cs:77-82 */
 
@@ -195,6 +212,42 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
                                  int32_t resolution, int32_t input_resolution, int32_t margin_pix,
                                  float tile_height, float tile_size, nz_slice_f32 heights);
 
+/* ---- host layer: the "next" rows of SURVEY.md section 8f ------------------------------- */
+
+/* ThermalErosionFilterDelegate, Filter/Kernel/Blur/ThermalErosionFilter.cs:138-146 (Schedule :111-133; stage
+ * StageThermalErosion.cs:13-29): `iterations` x 4 phases of in-place 2x2 talus relaxation.
+ * talus in degrees; maxDiff = tan(talus/90 * 3.14159/2) * mesh_height_width_ratio / resolution. */
+NZ_API int32_t nz_thermal_erosion(nz_slice_f32 src, float talus, float increment_ratio,
+                                  float mesh_height_width_ratio, int32_t iterations, int32_t resolution);
+
+/* ConstantJobScheduleDelegate, Filter/ConstantJob.cs:49-55 (operators Operators/SimpleMutation.cs:16-54):
+ * MULTIPLY: v * value;  BINARIZE: v >= value ? 1 : 0.  `tmp` is accepted for signature parity, never touched. */
+NZ_API int32_t nz_constant(nz_slice_f32 src, nz_slice_f32 tmp, int32_t operation, float constant_value,
+                           int32_t resolution);
+
+/* ReductionJobScheduleDelegate, Filter/ReductionJob.cs:55-61 (operators SimpleMutation.cs:56-171):
+ * left = op(left, right); ROOTSUMSQUARES = sqrt(a*a + b*b). */
+NZ_API int32_t nz_reduce(nz_slice_f32 left, nz_slice_f32 right, nz_slice_f32 tmp, int32_t operation,
+                         int32_t resolution);
+
+/* CurveJobScheduleDelegate, Filter/Curve/CurveJob.cs:91-97 (CurveOperator.Apply :69-80): piecewise-linear
+ * LUT over [0,1]; `curve` holds the samples CurveStage.ExtractCurve takes at i/samples (CurveStage.cs:27-35). */
+NZ_API int32_t nz_curve(nz_slice_f32 src, nz_slice_f32 tmp, nz_slice_f32 curve, int32_t resolution);
+
+/* CropJobDelegate, Filter/Sample/CropJob.cs:63-69: output(x,z) = input(x+offset, z+offset), clamped reads.
+ * The reference never assigns CropJob.Offset (:25,43-59), i.e. offset == 0; pass (input_resolution -
+ * output_resolution)/2 for the centre crop the stage's menu name promises. */
+NZ_API int32_t nz_crop(nz_slice_f32 input, int32_t input_resolution, nz_slice_f32 output,
+                       int32_t output_resolution, int32_t offset);
+
+/* GetMapRangeJob, Filter/NormalizeJob.cs:18-53: res3 = {min, max, max - min} of the map, folded from
+ * lim_min / lim_max (the reference's defaults are +inf / -inf). */
+NZ_API int32_t nz_map_range(nz_slice_f32 map, float* res3, float lim_min, float lim_max);
+
+/* MapNormalizeValuesDelegate, Filter/NormalizeJob.cs:94-100 with NormalizeMap (FlowMapComponents.cs:150-166):
+ * args3 = {min, max, range}; v = range < 1e-12 ? 0 : v;  out = (v - min) / range. */
+NZ_API int32_t nz_normalize(nz_slice_f32 src, nz_slice_f32 tmp, const float* args3, int32_t resolution);
+
 /* ---- host layer: residency ---------------------------------------------------------- */
 
 /* Between begin/end (per calling thread) the device mirror of every host slice a stage touches
@@ -258,6 +311,20 @@ NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32
                                      float tile_height, float tile_size, const float* d_heights,
                                      int32_t h_row_first, int32_t h_rows,
                                      int32_t vz_begin, int32_t vz_end, void* stream);
+
+/* Device-layer forms of the section-8f rows (n = number of cells; all in place). */
+NZ_API int32_t nz_dev_thermal_erosion(float* d_data, int32_t resolution, float talus, float increment_ratio,
+                                      float mesh_height_width_ratio, int32_t iterations, void* stream);
+NZ_API int32_t nz_dev_constant(float* d_data, size_t n, int32_t operation, float constant_value, void* stream);
+NZ_API int32_t nz_dev_reduce(float* d_left, const float* d_right, size_t n, int32_t operation, void* stream);
+NZ_API int32_t nz_dev_curve(float* d_data, size_t n, const float* d_curve, int32_t curve_size, void* stream);
+NZ_API int32_t nz_dev_crop(const float* d_input, int32_t input_resolution, float* d_output,
+                           int32_t output_resolution, int32_t offset, void* stream);
+/* d_res3: 3 floats {min, max, range}; d_scratch: nz_dev_map_range_scratch_bytes() bytes */
+NZ_API size_t  nz_dev_map_range_scratch_bytes(void);
+NZ_API int32_t nz_dev_map_range(const float* d_map, size_t n, float lim_min, float lim_max, float* d_res3,
+                                void* d_scratch, void* stream);
+NZ_API int32_t nz_dev_normalize(float* d_data, size_t n, float vmin, float range, void* stream);
 
 /* FP32 FMA-pipe peak micro-benchmark: launches `grid` CTAs of 256 threads each running `iters`
  * x 16 independent dependent-chain FFMAs per thread; returns FLOP count in *flops.  Used by

@@ -12,4 +12,6 @@ from . import lib, host, device, stages  # noqa: F401
 from .lib import NzError, load, build  # noqa: F401
 from .stages import (FractalNoise, KernelFilterType, GaussSigma, MeshType, JobHandle, StageIO, GeneratorData,  # noqa: F401
                      MeshStageData, Mesh, PipelineWorkItem, PipelineStage, NoiseStage, KernelFilterStage,
-                     StageGaussianBlur, StageSmoothBlur, ErosionFilterStage, FlowMapStage, MeshTileStage, BasePipeline)
+                     StageGaussianBlur, StageSmoothBlur, ErosionFilterStage, FlowMapStage, MeshTileStage, BasePipeline,
+                     ConstantOperationType, ReductionType, ReduceData, DownsampleData, StageThermalErosion,
+                     ConstantStage, ReduceStage, CurveStage, CropStage)

@@ -530,6 +530,42 @@ NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32
                        h_row_first, h_rows, vz_begin, vz_end, (cudaStream_t)stream);
 }
 
+NZ_API int32_t nz_dev_thermal_erosion(float* d_data, int32_t resolution, float talus, float increment_ratio,
+                                      float mesh_height_width_ratio, int32_t iterations, void* stream) {
+    NZ_REQUIRE(d_data && resolution > 0, "nz_dev_thermal_erosion: bad arguments");
+    NZ_REQUIRE(iterations >= 0, "nz_dev_thermal_erosion: iterations %d < 0", iterations);
+    return launch_thermal_erosion(d_data, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, (cudaStream_t)stream);
+}
+NZ_API int32_t nz_dev_constant(float* d_data, size_t n, int32_t operation, float constant_value, void* stream) {
+    NZ_REQUIRE(d_data || n == 0, "nz_dev_constant: null grid");
+    return launch_constant(d_data, n, operation, constant_value, (cudaStream_t)stream);
+}
+NZ_API int32_t nz_dev_reduce(float* d_left, const float* d_right, size_t n, int32_t operation, void* stream) {
+    NZ_REQUIRE((d_left && d_right) || n == 0, "nz_dev_reduce: null grid");
+    return launch_reduce(d_left, d_right, n, operation, (cudaStream_t)stream);
+}
+NZ_API int32_t nz_dev_curve(float* d_data, size_t n, const float* d_curve, int32_t curve_size, void* stream) {
+    NZ_REQUIRE(d_data || n == 0, "nz_dev_curve: null grid");
+    NZ_REQUIRE(d_curve && curve_size >= 2, "nz_dev_curve: the curve needs at least 2 samples (got %d)", curve_size);
+    return launch_curve(d_data, n, d_curve, curve_size, (cudaStream_t)stream);
+}
+NZ_API int32_t nz_dev_crop(const float* d_input, int32_t input_resolution, float* d_output, int32_t output_resolution,
+                           int32_t offset, void* stream) {
+    NZ_REQUIRE(d_input && d_output && input_resolution > 0 && output_resolution > 0 && output_resolution <= 65535,
+               "nz_dev_crop: bad arguments");
+    return launch_crop(d_input, input_resolution, d_output, output_resolution, offset, (cudaStream_t)stream);
+}
+NZ_API size_t nz_dev_map_range_scratch_bytes(void) { return map_range_scratch_bytes(); }
+NZ_API int32_t nz_dev_map_range(const float* d_map, size_t n, float lim_min, float lim_max, float* d_res3, void* d_scratch,
+                                void* stream) {
+    NZ_REQUIRE(d_map && d_res3 && d_scratch && n > 0, "nz_dev_map_range: bad arguments");
+    return launch_map_range(d_map, n, lim_min, lim_max, d_res3, d_scratch, (cudaStream_t)stream);
+}
+NZ_API int32_t nz_dev_normalize(float* d_data, size_t n, float vmin, float range, void* stream) {
+    NZ_REQUIRE(d_data || n == 0, "nz_dev_normalize: null grid");
+    return launch_normalize(d_data, n, vmin, range, (cudaStream_t)stream);
+}
+
 NZ_API int32_t nz_dev_fma_peak(float* d_sink, int32_t grid, int32_t iters, double* flops, void* stream) {
     int32_t rc = ensure_init();
     if (rc != NZ_OK) return rc;
@@ -816,6 +852,127 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
     }
     if (rc != NZ_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "nz_heightmap_mesh");
+    t_state.timed = true;
+    t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
+    return NZ_OK;
+}
+
+}  // extern "C"
+
+// ---- the section-8f rows ----------------------------------------------------------------------------------
+// a slice that a stage only reads: outside a pipeline nothing keeps its mirror alive after the call
+static void drop_if_unscoped(Mirror* m) {
+    if (in_scope() || !m) return;
+    const void* key = m->host.ptr;
+    pool_free(m->d);
+    pool_free(m->d_tmp);
+    t_state.local.mirrors.erase(key);
+}
+
+extern "C" {
+
+NZ_API int32_t nz_thermal_erosion(nz_slice_f32 src, float talus, float increment_ratio, float mesh_height_width_ratio,
+                                  int32_t iterations, int32_t resolution) {
+    NZ_REQUIRE(iterations >= 0, "nz_thermal_erosion: iterations %d < 0", iterations);
+    return run_inplace_stage(src, resolution, "nz_thermal_erosion", false, [&](Mirror& m, float**) {
+        return launch_thermal_erosion(m.d, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, t_state.stream);
+    });
+}
+
+NZ_API int32_t nz_constant(nz_slice_f32 src, nz_slice_f32 tmp, int32_t operation, float constant_value, int32_t resolution) {
+    (void)tmp;
+    NZ_REQUIRE(operation >= 0 && operation < NZ_CONSTANT__COUNT, "nz_constant: operation %d out of range", operation);
+    return run_inplace_stage(src, resolution, "nz_constant", false, [&](Mirror& m, float**) {
+        return launch_constant(m.d, m.n, operation, constant_value, t_state.stream);
+    });
+}
+
+NZ_API int32_t nz_normalize(nz_slice_f32 src, nz_slice_f32 tmp, const float* args3, int32_t resolution) {
+    (void)tmp;
+    NZ_REQUIRE(args3 != nullptr, "nz_normalize: args is null");
+    const float vmin = args3[0], range = args3[2];
+    return run_inplace_stage(src, resolution, "nz_normalize", false, [&](Mirror& m, float**) {
+        return launch_normalize(m.d, m.n, vmin, range, t_state.stream);
+    });
+}
+
+NZ_API int32_t nz_reduce(nz_slice_f32 left, nz_slice_f32 right, nz_slice_f32 tmp, int32_t operation, int32_t resolution) {
+    (void)tmp;
+    NZ_REQUIRE(operation >= 0 && operation < NZ_REDUCE__COUNT, "nz_reduce: operation %d out of range", operation);
+    NZ_REQUIRE(resolution > 0 && resolution <= 46340, "nz_reduce: resolution %d out of range", resolution);
+    int32_t rc = check_slice(right, (long long)resolution * resolution, "nz_reduce(right)");
+    if (rc != NZ_OK) return rc;
+    NZ_REQUIRE(left.ptr != right.ptr, "nz_reduce: left and right are the same slice");
+    Mirror* r = nullptr;
+    rc = run_inplace_stage(left, resolution, "nz_reduce", false, [&](Mirror& m, float**) {
+        int32_t rr = acquire(right, /*need_contents=*/true, &r);
+        if (rr != NZ_OK) return rr;
+        return launch_reduce(m.d, r->d, m.n, operation, t_state.stream);
+    });
+    drop_if_unscoped(r);    // run_inplace_stage synchronised the stream when no scope is open
+    return rc;
+}
+
+NZ_API int32_t nz_curve(nz_slice_f32 src, nz_slice_f32 tmp, nz_slice_f32 curve, int32_t resolution) {
+    (void)tmp;
+    NZ_REQUIRE(curve.ptr && curve.length >= 2 && curve.stride_bytes >= 4, "nz_curve: the curve needs at least 2 samples");
+    NZ_REQUIRE(curve.ptr != src.ptr, "nz_curve: curve and data are the same slice");
+    Mirror* c = nullptr;
+    int32_t rc = run_inplace_stage(src, resolution, "nz_curve", false, [&](Mirror& m, float**) {
+        int32_t rr = acquire(curve, /*need_contents=*/true, &c);
+        if (rr != NZ_OK) return rr;
+        return launch_curve(m.d, m.n, c->d, curve.length, t_state.stream);
+    });
+    drop_if_unscoped(c);
+    return rc;
+}
+
+NZ_API int32_t nz_crop(nz_slice_f32 input, int32_t input_resolution, nz_slice_f32 output, int32_t output_resolution,
+                       int32_t offset) {
+    NZ_REQUIRE(input_resolution > 0 && input_resolution <= 46340 && output_resolution > 0 && output_resolution <= 46340,
+               "nz_crop: resolution out of range");
+    int32_t rc = check_slice(input, (long long)input_resolution * input_resolution, "nz_crop(input)");
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_slice(output, (long long)output_resolution * output_resolution, "nz_crop(output)")) != NZ_OK) return rc;
+    NZ_REQUIRE(input.ptr != output.ptr, "nz_crop: input and output are the same slice");
+    if ((rc = begin_stage()) != NZ_OK) return rc;
+    Mirror *in = nullptr, *out = nullptr;
+    if ((rc = acquire(input, /*need_contents=*/true, &in)) != NZ_OK) return rc;
+    if ((rc = acquire(output, /*need_contents=*/false, &out)) != NZ_OK) return rc;
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    rc = launch_crop(in->d, input_resolution, out->d, output_resolution, offset, t_state.stream);
+    if (rc == NZ_OK) out->dirty = true;
+    int32_t rc2 = finish(out);
+    drop_if_unscoped(in);
+    return rc != NZ_OK ? rc : rc2;
+}
+
+NZ_API int32_t nz_map_range(nz_slice_f32 map, float* res3, float lim_min, float lim_max) {
+    NZ_REQUIRE(res3 != nullptr, "nz_map_range: result pointer is null");
+    NZ_REQUIRE(map.ptr && map.length > 0 && map.stride_bytes >= 4, "nz_map_range: empty map");
+    int32_t rc = begin_stage();
+    if (rc != NZ_OK) return rc;
+    Mirror* m = nullptr;
+    if ((rc = acquire(map, /*need_contents=*/true, &m)) != NZ_OK) return rc;
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    void* scratch = nullptr;
+    rc = pool_alloc(&scratch, map_range_scratch_bytes() + 3 * sizeof(float));
+    cudaError_t e = cudaSuccess;
+    if (rc == NZ_OK) {
+        float* d_res = (float*)((char*)scratch + map_range_scratch_bytes());
+        cudaStream_t s = t_state.stream;
+        rc = launch_map_range(m->d, m->n, lim_min, lim_max, d_res, scratch, s);
+        if (rc == NZ_OK) {
+            e = cudaEventRecord(t_state.ev[2], s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(res3, d_res, 3 * sizeof(float), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaEventRecord(t_state.ev[3], s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // the caller reads res3 on return
+        }
+    }
+    pool_free(scratch);
+    drop_if_unscoped(m);
+    if (rc != NZ_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "nz_map_range");
     t_state.timed = true;
     t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
     return NZ_OK;

@@ -78,6 +78,16 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
 int32_t launch_mesh(int mesh_type, void* d_vtx, uint32_t* d_idx, int R, int inRes, float tile_height,
                     float tile_size, const float* d_heights, int h_row_first, int h_rows, int vz_begin, int vz_end,
                     cudaStream_t s);
+float thermal_max_diff(float talus_deg, float height_ratio, int resolution);
+int32_t launch_thermal_erosion(float* d_data, int res, float talus_deg, float increment, float height_ratio, int iterations,
+                               cudaStream_t s);
+int32_t launch_constant(float* d, size_t n, int op, float value, cudaStream_t s);
+int32_t launch_reduce(float* d_left, const float* d_right, size_t n, int op, cudaStream_t s);
+int32_t launch_curve(float* d, size_t n, const float* d_curve, int curve_size, cudaStream_t s);
+int32_t launch_normalize(float* d, size_t n, float vmin, float range, cudaStream_t s);
+int32_t launch_crop(const float* d_in, int in_res, float* d_out, int out_res, int offset, cudaStream_t s);
+size_t map_range_scratch_bytes();
+int32_t launch_map_range(const float* d, size_t n, float lim_min, float lim_max, float* d_res3, void* d_scratch, cudaStream_t s);
 int32_t launch_fma_peak(float* d_sink, int grid, int iters, double* flops, cudaStream_t s);
 int32_t launch_gather_strided(float* d_dst, const unsigned char* d_src, int stride_bytes, size_t n, cudaStream_t s);
 

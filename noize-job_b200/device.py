@@ -91,6 +91,61 @@ def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, m
                                              h_row_first, heights.shape[0], vz_begin, vz_end, _l.stream_ptr(stream)))
 
 
+# ---- SURVEY.md section 8f rows (all in place on a square or rectangular device grid) -----------------------
+def thermal_erosion(data, talus=45.0, increment_ratio=0.5, mesh_height_width_ratio=0.75, iterations=1, stream=None):
+    _grid(data, "data")
+    assert data.shape[0] == data.shape[1], "thermal erosion works on a square tile"
+    _l.check(_l.load().nz_dev_thermal_erosion(data.data_ptr(), data.shape[0], talus, increment_ratio, mesh_height_width_ratio,
+                                              iterations, _l.stream_ptr(stream)))
+    return data
+
+
+def constant(data, operation, value, stream=None):
+    _grid(data, "data")
+    _l.check(_l.load().nz_dev_constant(data.data_ptr(), data.numel(), int(operation), value, _l.stream_ptr(stream)))
+    return data
+
+
+def reduce(left, right, operation, stream=None):
+    _grid(left, "left"); _grid(right, "right")
+    assert left.shape == right.shape
+    _l.check(_l.load().nz_dev_reduce(left.data_ptr(), right.data_ptr(), left.numel(), int(operation), _l.stream_ptr(stream)))
+    return left
+
+
+def curve(data, curve_samples, stream=None):
+    _grid(data, "data")
+    assert curve_samples.is_cuda and curve_samples.is_contiguous() and curve_samples.dim() == 1
+    _l.check(_l.load().nz_dev_curve(data.data_ptr(), data.numel(), curve_samples.data_ptr(), curve_samples.numel(),
+                                    _l.stream_ptr(stream)))
+    return data
+
+
+def crop(input, output, offset=0, stream=None):
+    _grid(input, "input"); _grid(output, "output")
+    assert input.shape[0] == input.shape[1] and output.shape[0] == output.shape[1]
+    _l.check(_l.load().nz_dev_crop(input.data_ptr(), input.shape[0], output.data_ptr(), output.shape[0], offset,
+                                   _l.stream_ptr(stream)))
+    return output
+
+
+def map_range(data, lim_min=float("inf"), lim_max=float("-inf"), stream=None):
+    """Returns a 3-element CUDA tensor [min, max, range] (no synchronisation)."""
+    import torch
+    _grid(data, "data")
+    res = torch.empty(3, dtype=torch.float32, device=data.device)
+    scratch = torch.empty(int(_l.load().nz_dev_map_range_scratch_bytes()), dtype=torch.uint8, device=data.device)
+    _l.check(_l.load().nz_dev_map_range(data.data_ptr(), data.numel(), lim_min, lim_max, res.data_ptr(), scratch.data_ptr(),
+                                        _l.stream_ptr(stream)))
+    return res
+
+
+def normalize(data, vmin, vrange, stream=None):
+    _grid(data, "data")
+    _l.check(_l.load().nz_dev_normalize(data.data_ptr(), data.numel(), vmin, vrange, _l.stream_ptr(stream)))
+    return data
+
+
 def fma_peak(sink, grid, iters, stream=None):
     flops = C.c_double()
     _l.check(_l.load().nz_dev_fma_peak(sink.data_ptr(), grid, iters, C.byref(flops), _l.stream_ptr(stream)))

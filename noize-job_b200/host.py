@@ -121,6 +121,48 @@ def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, m
                                          margin_pix, tile_height, tile_size, _l.as_slice(heights)))
 
 
+# ---- SURVEY.md section 8f rows ---------------------------------------------------------------------
+def thermal_erosion(src, talus, increment_ratio, mesh_height_width_ratio, iterations, resolution):
+    """ThermalErosionFilterDelegate, Filter/Kernel/Blur/ThermalErosionFilter.cs:138-146."""
+    _l.check(_l.load().nz_thermal_erosion(_l.as_slice(src), talus, increment_ratio, mesh_height_width_ratio, iterations,
+                                          resolution))
+
+
+def constant(src, tmp, operation, constant_value, resolution):
+    """ConstantJobScheduleDelegate, Filter/ConstantJob.cs:49-55."""
+    _l.check(_l.load().nz_constant(_l.as_slice(src), _l.as_slice(tmp), int(operation), constant_value, resolution))
+
+
+def reduce(left, right, tmp, operation, resolution):
+    """ReductionJobScheduleDelegate, Filter/ReductionJob.cs:55-61: left = op(left, right)."""
+    _l.check(_l.load().nz_reduce(_l.as_slice(left), _l.as_slice(right), _l.as_slice(tmp), int(operation), resolution))
+
+
+def curve(src, tmp, curve_samples, resolution):
+    """CurveJobScheduleDelegate, Filter/Curve/CurveJob.cs:91-97."""
+    _l.check(_l.load().nz_curve(_l.as_slice(src), _l.as_slice(tmp), _l.as_slice(curve_samples), resolution))
+
+
+def crop(input, input_resolution, output, output_resolution, offset=0):
+    """CropJobDelegate, Filter/Sample/CropJob.cs:63-69 (offset 0 == the reference, which never assigns it)."""
+    _l.check(_l.load().nz_crop(_l.as_slice(input), input_resolution, _l.as_slice(output), output_resolution, offset))
+
+
+def map_range(map_, lim_min=float("inf"), lim_max=float("-inf")):
+    """GetMapRangeJob, Filter/NormalizeJob.cs:18-53: returns [min, max, range]."""
+    res = np.zeros(3, np.float32)
+    _l.check(_l.load().nz_map_range(_l.as_slice(map_), res.ctypes.data_as(_l._pf32), lim_min, lim_max))
+    return res
+
+
+def normalize(src, tmp, args3, resolution):
+    """MapNormalizeValuesDelegate (NormalizeJob.cs:94-100) with NormalizeMap (FlowMapComponents.cs:150-166)."""
+    a, pa = _l.fptr(args3)
+    if a.size != 3:
+        raise ValueError("args must be [min, max, range]")
+    _l.check(_l.load().nz_normalize(_l.as_slice(src), _l.as_slice(tmp), pa, resolution))
+
+
 # ---- residency -----------------------------------------------------------------------------------
 _scope = threading.local()
 

@@ -58,6 +58,13 @@ SIGNATURES = {
     "nz_min_erosion": (_i32, [Slice, _i32, _i32]),
     "nz_flowmap": (_i32, [Slice, _i32, _i32, _f32, _f32]),
     "nz_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, Slice]),
+    "nz_thermal_erosion": (_i32, [Slice, _f32, _f32, _f32, _i32, _i32]),
+    "nz_constant": (_i32, [Slice, Slice, _i32, _f32, _i32]),
+    "nz_reduce": (_i32, [Slice, Slice, Slice, _i32, _i32]),
+    "nz_curve": (_i32, [Slice, Slice, Slice, _i32]),
+    "nz_crop": (_i32, [Slice, _i32, Slice, _i32, _i32]),
+    "nz_map_range": (_i32, [Slice, _pf32, _f32, _f32]),
+    "nz_normalize": (_i32, [Slice, Slice, _pf32, _i32]),
     "nz_pipeline_begin": (_i32, []),
     "nz_pipeline_end": (_i32, []),
     "nz_scope_create": (C.c_int64, []),
@@ -74,6 +81,14 @@ SIGNATURES = {
     "nz_dev_flowmap_scratch_bytes": (_sz, [_i32, _i32, _i32]),
     "nz_dev_flowmap": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, C.POINTER(_vp), _vp]),
     "nz_dev_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "nz_dev_thermal_erosion": (_i32, [_vp, _i32, _f32, _f32, _f32, _i32, _vp]),
+    "nz_dev_constant": (_i32, [_vp, _sz, _i32, _f32, _vp]),
+    "nz_dev_reduce": (_i32, [_vp, _vp, _sz, _i32, _vp]),
+    "nz_dev_curve": (_i32, [_vp, _sz, _vp, _i32, _vp]),
+    "nz_dev_crop": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp]),
+    "nz_dev_map_range_scratch_bytes": (_sz, []),
+    "nz_dev_map_range": (_i32, [_vp, _sz, _f32, _f32, _vp, _vp, _vp]),
+    "nz_dev_normalize": (_i32, [_vp, _sz, _f32, _f32, _vp]),
     "nz_dev_fma_peak": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_double), _vp]),
 }
 

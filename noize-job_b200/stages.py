@@ -12,6 +12,11 @@ file side by side with the originals (paths relative to xshazwar/noize-job):
   FlowMapStage                      Geologic/Stage/FlowMapStage.cs:16-221
   MeshTileStage                     Mesh/Stage/MeshTileStage.cs:28-62
   BasePipeline (scheduling chain)   Pipeline/Executable/Pipeline.cs:104-181
+  StageThermalErosion               Filter/Kernel/Blur/StageThermalErosion.cs:13-29
+  ConstantStage                     Filter/ConstantStage.cs:13-60
+  ReduceStage, ReduceData           Filter/Reduce/ReduceStage.cs:12-68, Pipeline/Stage/StageIOTypes/ReduceData.cs
+  CurveStage                        Filter/Curve/CurveStage.cs:13-73
+  CropStage, DownsampleData         Filter/Sample/CropStage.cs:13-19, Pipeline/Stage/StageIOTypes/DownsampleData.cs
   ErosionFilterStage                NEW: wraps ErosionKernelJob (Filter/Kernel/KernelJob.cs:317-350), which no
                                     stage binds in the current reference tree ("Value Erosion", README.md:18)
 
@@ -66,6 +71,19 @@ class MeshType(IntEnum):               # Mesh/Stage/MeshTileStage.cs:22-25
     OvershootSquareGridHeightMap = 1
 
 
+class ConstantOperationType(IntEnum):  # Filter/ConstantStage.cs:15-18
+    MULTIPLY = 0
+    BINARIZE = 1
+
+
+class ReductionType(IntEnum):          # Filter/Reduce/ReduceStage.cs:12-18
+    SUBTRACT = 0
+    MULTIPLY = 1
+    ROOTSUMSQUARES = 2
+    MAX = 3
+    MIN = 4
+
+
 # ---- job handle -------------------------------------------------------------------------------------
 class JobHandle:
     """Completion token of scheduled GPU work.  Complete() brings every deferred result back to host."""
@@ -104,6 +122,18 @@ class GeneratorData(StageIO):
     def __init__(self, uuid="", data=None, resolution=512, xpos=0, zpos=0):
         super().__init__(uuid, data)
         self.resolution, self.xpos, self.zpos = resolution, xpos, zpos
+
+
+class ReduceData(StageIO):             # Pipeline/Stage/StageIOTypes/ReduceData.cs
+    def __init__(self, uuid="", data=None, rightData=None, resolution=512, xpos=0, zpos=0):
+        super().__init__(uuid, data)
+        self.rightData, self.resolution, self.xpos, self.zpos = rightData, resolution, xpos, zpos
+
+
+class DownsampleData(StageIO):         # Pipeline/Stage/StageIOTypes/DownsampleData.cs
+    def __init__(self, uuid="", data=None, resolution=512, inputResolution=512, inputData=None):
+        super().__init__(uuid, data)
+        self.resolution, self.inputResolution, self.inputData = resolution, inputResolution, inputData
 
 
 class Mesh:
@@ -247,6 +277,86 @@ class ErosionFilterStage(PipelineStage):
         d = requirements.data
         self.jobHandle = _chain(dependency)
         _h.min_erosion(d.data, d.resolution, self.iterations)
+
+
+class StageThermalErosion(PipelineStage):
+    def __init__(self, iterations=1, talus=45, increment=0.5, meshHeightWidthRatio=0.75):
+        super().__init__()
+        self.iterations, self.talus, self.increment, self.meshHeightWidthRatio = iterations, talus, increment, meshHeightWidthRatio
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.thermal_erosion(d.data, float(self.talus), self.increment, self.meshHeightWidthRatio, self.iterations, d.resolution)
+
+
+class ConstantStage(PipelineStage):
+    def __init__(self, operation=ConstantOperationType.MULTIPLY, value=0.5):
+        super().__init__()
+        self.operation, self.value = operation, value
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.constant(d.data, None, self.operation, self.value, d.resolution)
+
+
+class ReduceStage(PipelineStage):
+    def __init__(self, operation=ReductionType.SUBTRACT):
+        super().__init__()
+        self.operation = operation
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(ReduceData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.reduce(d.data, d.rightData, None, self.operation, d.resolution)
+
+    def TransformData(self, inputData):    # ReduceStage.cs:52-61: downstream stages see a GeneratorData
+        d = inputData.data
+        inputData.data = GeneratorData(d.uuid, d.data, d.resolution, d.xpos, d.zpos)
+
+
+class CurveStage(PipelineStage):
+    """`unityCurve` is any callable t -> value on [0,1] (AnimationCurve.Evaluate); it is discretised exactly as
+    CurveStage.ExtractCurve does: curve[i] = Evaluate((float) i / samples), Filter/Curve/CurveStage.cs:27-35."""
+
+    def __init__(self, unityCurve=None, samples=256):
+        super().__init__()
+        self.unityCurve, self.samples = unityCurve if unityCurve is not None else (lambda t: t), samples
+        self.curve = None
+
+    def ExtractCurve(self):
+        s = np.float32(self.samples)
+        self.curve = np.array([self.unityCurve(float(np.float32(i) / s)) for i in range(self.samples)], np.float32)
+
+    def ResizeNativeContainers(self, size):
+        self.ExtractCurve()
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.curve(d.data, None, self.curve, d.resolution)
+
+
+class CropStage(PipelineStage):
+    """The reference never assigns CropJob.Offset, so its "CenterCropResolution" stage copies the top-left corner
+    (Filter/Sample/CropJob.cs:25,36-43).  offset=None reproduces that; offset='center' is the evident intent."""
+
+    def __init__(self, offset=None):
+        super().__init__()
+        self.offset = offset
+
+    def Schedule(self, requirements, dependency):
+        d = requirements.data
+        if not isinstance(d, DownsampleData):
+            raise Exception(f"Unhandled stageio {type(d).__name__}")
+        off = 0 if self.offset is None else ((d.inputResolution - d.resolution) // 2 if self.offset == "center" else int(self.offset))
+        self.jobHandle = _chain(dependency)
+        _h.crop(d.inputData, d.inputResolution, d.data, d.resolution, off)
 
 
 class FlowMapStage(PipelineStage):

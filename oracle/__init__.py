@@ -62,6 +62,23 @@ def _bind(lib):
     lib.nzref_heightmap_mesh.argtypes = [i32, _f32p, _u32p, i32, i32, i32, f32, f32, _f32p]
     lib.nzref_tile_geometry.restype = i32
     lib.nzref_tile_geometry.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]
+    i64 = C.c_int64
+    lib.nzref_thermal_max_diff.restype = f32
+    lib.nzref_thermal_max_diff.argtypes = [f32, f32, i32]
+    lib.nzref_thermal_erosion.restype = i32
+    lib.nzref_thermal_erosion.argtypes = [_f32p, i32, f32, f32, f32, i32]
+    lib.nzref_constant.restype = i32
+    lib.nzref_constant.argtypes = [_f32p, i64, i32, f32]
+    lib.nzref_reduce.restype = i32
+    lib.nzref_reduce.argtypes = [_f32p, _f32p, i64, i32]
+    lib.nzref_curve.restype = i32
+    lib.nzref_curve.argtypes = [_f32p, i64, _f32p, i32]
+    lib.nzref_crop.restype = i32
+    lib.nzref_crop.argtypes = [_f32p, i32, _f32p, i32, i32]
+    lib.nzref_map_range.restype = i32
+    lib.nzref_map_range.argtypes = [_f32p, i64, f32, f32, _f32p]
+    lib.nzref_normalize.restype = i32
+    lib.nzref_normalize.argtypes = [_f32p, i64, _f32p]
     lib.nzref_num_threads.restype = i32
     lib.nzref_mod289_mismatches.restype = C.c_int64
     lib.nzref_mod289_mismatches.argtypes = [i32, i32, C.POINTER(i32)]
@@ -152,6 +169,59 @@ class Oracle:
     def flowmap(self, grid, iterations=5, norm_min=-0.1, norm_max=0.1):
         d = self._grid(grid)
         rc = self.lib.nzref_flowmap(d, d.shape[1], d.shape[0], iterations, norm_min, norm_max)
+        assert rc == 0, rc
+        return d
+
+    # -- section 8f rows: thermal erosion and the element-wise stages ---------------------------
+    def thermal_max_diff(self, talus, height_ratio, resolution):
+        return float(self.lib.nzref_thermal_max_diff(talus, height_ratio, resolution))
+
+    def thermal_erosion(self, grid, talus=45.0, increment=0.5, mesh_height_width_ratio=0.75, iterations=1):
+        d = self._grid(grid)
+        assert d.shape[0] == d.shape[1]
+        rc = self.lib.nzref_thermal_erosion(d, d.shape[0], talus, increment, mesh_height_width_ratio, iterations)
+        assert rc == 0, rc
+        return d
+
+    def constant(self, grid, op, value):
+        d = self._grid(grid)
+        rc = self.lib.nzref_constant(d, d.size, int(op), value)
+        assert rc == 0, rc
+        return d
+
+    def reduce(self, left, right, op):
+        d = self._grid(left)
+        r = np.ascontiguousarray(right, np.float32)
+        assert r.shape == d.shape
+        rc = self.lib.nzref_reduce(d, r, d.size, int(op))
+        assert rc == 0, rc
+        return d
+
+    def curve(self, grid, curve):
+        d = self._grid(grid)
+        c = np.ascontiguousarray(curve, np.float32)
+        rc = self.lib.nzref_curve(d, d.size, c, c.size)
+        assert rc == 0, rc
+        return d
+
+    def crop(self, grid, out_res, offset=0):
+        g = np.ascontiguousarray(grid, np.float32)
+        assert g.shape[0] == g.shape[1]
+        out = np.empty((out_res, out_res), np.float32)
+        rc = self.lib.nzref_crop(g, g.shape[0], out, out_res, offset)
+        assert rc == 0, rc
+        return out
+
+    def map_range(self, grid, lim_min=np.inf, lim_max=-np.inf):
+        g = np.ascontiguousarray(grid, np.float32)
+        res = np.zeros(3, np.float32)
+        rc = self.lib.nzref_map_range(g.reshape(-1), g.size, lim_min, lim_max, res)
+        assert rc == 0, rc
+        return res
+
+    def normalize(self, grid, args3):
+        d = self._grid(grid)
+        rc = self.lib.nzref_normalize(d, d.size, np.ascontiguousarray(args3, np.float32))
         assert rc == 0, rc
         return d
 

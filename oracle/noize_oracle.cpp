@@ -732,6 +732,144 @@ NZREF_API int32_t nzref_tile_geometry(int32_t tileResolution, int32_t tileSize, 
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * thermal erosion and the element-wise stage set
+ * ------------------------------------------------------------------------------------------ */
+
+/* ThermalErosionFilter.rectify(float2), Filter/Kernel/Blur/ThermalErosionFilter.cs:84-98.
+ * `v += increment * excess` is an a*b+c form: fmaf (canonical order, see the header). */
+static inline void thermal_rectify(float* a, float* b, float maxDiff, float increment) {
+    float diff = fabsf(*a - *b);
+    if (diff > maxDiff) {
+        float excess = diff - maxDiff;
+        if (*a > *b) {
+            *b = fmaf(increment, excess, *b);
+            *a = fmaf(-increment, excess, *a);
+        } else {
+            *a = fmaf(increment, excess, *a);
+            *b = fmaf(-increment, excess, *b);
+        }
+    }
+}
+
+/* ThermalErosionFilter.Schedule (:111-133) and Execute (:101-119): iterations x flip 0..3, one IJobFor of
+ * resolution/2 - 1 row jobs per flip; idxNeighborhood / getIdx clamp (:37-50); the six pair updates of
+ * rectifyNeighborhood in order xy, xz, xw, yz, yw, zw (:73-80). */
+NZREF_API float nzref_thermal_max_diff(float talus_deg, float heightRatio, int32_t resolution) {
+    float talus = (talus_deg / 90.0f) * 3.14159f / 2.0f;
+    return (tanf(talus) * heightRatio) / (float)resolution;
+}
+NZREF_API int32_t nzref_thermal_erosion(float* data, int32_t resolution, float talus_deg, float incrementRatio,
+                                        float meshHeightWidthRatio, int32_t iterations) {
+    if (!data || resolution <= 0 || iterations < 0) return -1;
+    const int res = resolution;
+    const float maxDiff = nzref_thermal_max_diff(talus_deg, meshHeightWidthRatio, resolution);
+    const int jobs = res / 2 - 1;
+    for (int it = 0; it < iterations; it++)
+        for (int flip = 0; flip < 4; flip++) {
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int job = 0; job < jobs; job++) {
+                int offset = 1;
+                int z = job + 1;
+                if (flip % 2 != 0) offset += 1;
+                z *= 2;
+                if (flip > 1) z -= 1;
+                for (int x = offset; x < res - 1; x += 2) {
+                    const int x1 = clampi(x + 1, 0, res - 1), z1 = clampi(z + 1, 0, res - 1);
+                    float* px = &data[(size_t)z * res + x];
+                    float* py = &data[(size_t)z * res + x1];
+                    float* pz = &data[(size_t)z1 * res + x];
+                    float* pw = &data[(size_t)z1 * res + x1];
+                    float vx = *px, vy = *py, vz = *pz, vw = *pw;
+                    thermal_rectify(&vx, &vy, maxDiff, incrementRatio);
+                    thermal_rectify(&vx, &vz, maxDiff, incrementRatio);
+                    thermal_rectify(&vx, &vw, maxDiff, incrementRatio);
+                    thermal_rectify(&vy, &vz, maxDiff, incrementRatio);
+                    thermal_rectify(&vy, &vw, maxDiff, incrementRatio);
+                    thermal_rectify(&vz, &vw, maxDiff, incrementRatio);
+                    *px = vx; *py = vy; *pz = vz; *pw = vw;
+                }
+            }
+        }
+    return 0;
+}
+
+/* ConstantJob<ConstantMultiply|ConstantBinarize>, Filter/ConstantJob.cs:16-47, SimpleMutation.cs:16-54
+ * (write to tmp + SWAP_RWTILE copy-back == in place for an element-wise map) */
+NZREF_API int32_t nzref_constant(float* data, int64_t n, int32_t op, float value) {
+    if (!data || n < 0 || op < 0 || op > 1) return -1;
+    for (int64_t i = 0; i < n; i++) data[i] = op == 0 ? data[i] * value : (data[i] >= value ? 1.0f : 0.0f);
+    return 0;
+}
+
+/* ReductionJob<...>, Filter/ReductionJob.cs:16-53; operators SimpleMutation.cs:56-171; enum order
+ * ReductionType, Filter/Reduce/ReduceStage.cs:12-18 */
+NZREF_API int32_t nzref_reduce(float* left, const float* right, int64_t n, int32_t op) {
+    if (!left || !right || n < 0 || op < 0 || op > 4) return -1;
+    for (int64_t i = 0; i < n; i++) {
+        const float a = left[i], b = right[i];
+        float v;
+        switch (op) {
+            case 0: v = a - b; break;
+            case 1: v = a * b; break;
+            case 2: v = sqrtf(fmaf(b, b, a * a)); break;   /* sqrt((a*a) + (b*b)) */
+            case 3: v = fmaxf(a, b); break;
+            default: v = fminf(a, b); break;
+        }
+        left[i] = v;
+    }
+    return 0;
+}
+
+/* CurveOperator.Apply, Filter/Curve/CurveJob.cs:69-80 */
+NZREF_API int32_t nzref_curve(float* data, int64_t n, const float* curve, int32_t curveSize) {
+    if (!data || !curve || n < 0 || curveSize < 2) return -1;
+    const float size = (float)curveSize;
+    for (int64_t i = 0; i < n; i++) {
+        float rect = fminf(fmaxf(data[i], 0.0f), 1.0f) * size;
+        float lowerIdx = fminf(floorf(rect), size - 2.0f);
+        float left = curve[(int)lowerIdx], right = curve[(int)lowerIdx + 1];
+        float value = lerpf_(left, right, rect - lowerIdx);
+        value = fmaxf(0.0f, value);
+        value = fminf(1.0f, value);
+        data[i] = value;
+    }
+    return 0;
+}
+
+/* CropJob.Execute, Filter/Sample/CropJob.cs:36-43 (Offset is never assigned by the reference: 0) */
+NZREF_API int32_t nzref_crop(const float* input, int32_t inputResolution, float* output, int32_t outputResolution, int32_t offset) {
+    if (!input || !output || inputResolution <= 0 || outputResolution <= 0) return -1;
+    Tile in = {input, inputResolution, inputResolution};
+    for (int z = 0; z < outputResolution; z++)
+        for (int x = 0; x < outputResolution; x++) output[(size_t)z * outputResolution + x] = in.get(x + offset, z + offset);
+    return 0;
+}
+
+/* GetMapRangeJob.Execute, Filter/NormalizeJob.cs:33-43 */
+NZREF_API int32_t nzref_map_range(const float* map, int64_t n, float lim_min, float lim_max, float* res3) {
+    if (!map || !res3 || n < 0) return -1;
+    float min_ = lim_min, max_ = lim_max;
+    for (int64_t i = 0; i < n; i++) {
+        min_ = fminf(min_, map[i]);
+        max_ = fmaxf(max_, map[i]);
+    }
+    res3[0] = min_; res3[1] = max_; res3[2] = max_ - min_;
+    return 0;
+}
+
+/* NormalizeMap.CalculateCell, Geologic/FlowMap/FlowMapComponents.cs:157-165 via MapNormalizeValues (NormalizeJob.cs:58-92) */
+NZREF_API int32_t nzref_normalize(float* data, int64_t n, const float* args3) {
+    if (!data || !args3 || n < 0) return -1;
+    const float a0 = args3[0], a2 = args3[2];
+    for (int64_t i = 0; i < n; i++) {
+        float v = data[i];
+        if (a2 < 1e-12f) v = 0.0f;
+        data[i] = (v - a0) / a2;
+    }
+    return 0;
+}
+
 NZREF_API int32_t nzref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -1,0 +1,123 @@
+"""Known-answer tests of the oracle's SURVEY section-8f rows (thermal erosion, element-wise stages), independent of
+the C++ restatement: each is re-derived here in plain numpy / Python from the reference source.
+
+  ThermalErosionFilter   Filter/Kernel/Blur/ThermalErosionFilter.cs:21-147
+  Constant / Reduce ops  Filter/Operators/SimpleMutation.cs:16-171
+  CurveOperator          Filter/Curve/CurveJob.cs:56-89
+  CropJob                Filter/Sample/CropJob.cs:18-61
+  GetMapRangeJob / NormalizeMap   Filter/NormalizeJob.cs:18-53, Geologic/FlowMap/FlowMapComponents.cs:150-166
+"""
+import math
+
+import numpy as np
+import pytest
+
+f32 = np.float32
+
+
+def py_thermal(grid, talus, inc, ratio, iterations):
+    """Straight transcription of ThermalErosionFilter.Execute/Schedule in Python floats rounded to binary32 after every
+    operation (fma emulated in float64: exact product + one rounding)."""
+    d = grid.astype(np.float32).copy()
+    res = d.shape[0]
+    talus_r = f32(f32(f32(talus) / f32(90.0)) * f32(3.14159)) / f32(2.0)
+    max_diff = f32(f32(f32(math.tan(float(talus_r))) * f32(ratio)) / f32(res))   # tanf == rounded tan for these inputs (checked below)
+    inc = f32(inc)
+
+    def fma(a, b, c):
+        return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+    def rectify(a, b):
+        diff = f32(abs(f32(a - b)))
+        if diff > max_diff:
+            excess = f32(diff - max_diff)
+            if a > b:
+                return fma(-inc, excess, a), fma(inc, excess, b)
+            return fma(inc, excess, a), fma(-inc, excess, b)
+        return a, b
+
+    for _ in range(iterations):
+        for flip in range(4):
+            for job in range(res // 2 - 1):
+                offset = 1 + (1 if flip % 2 else 0)
+                z = (job + 1) * 2 - (1 if flip > 1 else 0)
+                x = offset
+                while x < res - 1:
+                    x1, z1 = min(x + 1, res - 1), min(z + 1, res - 1)
+                    v = [d[z, x], d[z, x1], d[z1, x], d[z1, x1]]
+                    for i, j in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)):
+                        v[i], v[j] = rectify(v[i], v[j])
+                    d[z, x], d[z, x1], d[z1, x], d[z1, x1] = v
+                    x += 2
+    return d, float(max_diff)
+
+
+@pytest.mark.parametrize("res,iters,talus", [(16, 1, 45), (33, 2, 30), (48, 3, 60)])
+def test_thermal_erosion_matches_python_transcription(oracle, res, iters, talus):
+    g = np.random.default_rng(res).random((res, res), dtype=np.float32)
+    want, md = py_thermal(g, talus, 0.5, 0.75, iters)
+    assert oracle.thermal_max_diff(talus, 0.75, res) == pytest.approx(md, rel=2e-7)
+    got = oracle.thermal_erosion(g, talus, 0.5, 0.75, iters)
+    if oracle.thermal_max_diff(talus, 0.75, res) == md:
+        assert np.array_equal(got, want)
+    else:   # tanf differs from the rounded double tan by an ulp on this libm: values agree to rounding
+        assert np.abs(got - want).max() < 1e-6
+
+
+def test_thermal_erosion_properties(oracle):
+    g = np.random.default_rng(7).random((64, 64), dtype=np.float32)
+    out = oracle.thermal_erosion(g, 45, 0.5, 0.75, 4)
+    assert np.array_equal(out[0], g[0]) and np.array_equal(out[:, 0], g[:, 0])          # row 0 / column 0 untouched
+    assert abs(float(out.sum(dtype=np.float64) - g.sum(dtype=np.float64))) < 1e-3       # material is moved, not created
+    # roughness (sum of |neighbour differences|) decreases
+    rough = lambda a: float(np.abs(np.diff(a, axis=0)).sum() + np.abs(np.diff(a, axis=1)).sum())
+    assert rough(out) < rough(g)
+    # a surface already below the talus everywhere is a fixed point
+    flat = (np.arange(64, dtype=np.float32)[None, :] * f32(1e-4)).repeat(64, 0)
+    assert np.array_equal(oracle.thermal_erosion(flat, 45, 0.5, 0.75, 3), flat)
+    assert np.array_equal(oracle.thermal_erosion(g, 45, 0.5, 0.75, 0), g)
+
+
+def test_constant_and_reduce_ops(oracle):
+    rng = np.random.default_rng(3)
+    a, b = rng.random((37, 53), dtype=np.float32), rng.random((37, 53), dtype=np.float32) - f32(0.5)
+    assert np.array_equal(oracle.constant(a, 0, 0.37), a * f32(0.37))
+    assert np.array_equal(oracle.constant(a, 1, 0.5), (a >= f32(0.5)).astype(np.float32))
+    assert np.array_equal(oracle.reduce(a, b, 0), a - b)
+    assert np.array_equal(oracle.reduce(a, b, 1), a * b)
+    rss = np.sqrt((a.astype(np.float64) ** 2 + b.astype(np.float64) ** 2)).astype(np.float32)
+    assert np.abs(oracle.reduce(a, b, 2) - rss).max() <= 6e-8 * 2
+    assert np.array_equal(oracle.reduce(a, b, 3), np.maximum(a, b))
+    assert np.array_equal(oracle.reduce(a, b, 4), np.minimum(a, b))
+
+
+def test_curve_lut(oracle):
+    rng = np.random.default_rng(5)
+    v = (rng.random((40, 40), dtype=np.float32) * f32(1.4) - f32(0.2))       # also outside [0,1]: clamped
+    samples = 256
+    curve = np.array([(i / samples) ** 2 for i in range(samples)], np.float32)
+    got = oracle.curve(v, curve)
+    rect = np.clip(v, 0, 1) * f32(samples)
+    lo = np.minimum(np.floor(rect), f32(samples - 2))
+    li = lo.astype(np.int64)
+    want = curve[li].astype(np.float64) + (rect - lo).astype(np.float64) * (curve[li + 1].astype(np.float64) - curve[li])
+    assert np.abs(got - np.clip(want, 0, 1)).max() < 2e-7
+    assert got.min() >= 0.0 and got.max() <= 1.0
+    # identity curve sampled at i/samples reproduces the input up to rounding; the last segment extrapolates
+    ident = np.arange(samples, dtype=np.float32) / f32(samples)
+    assert np.abs(oracle.curve(np.clip(v, 0, 1), ident) - np.clip(v, 0, 1)).max() < 1e-6
+
+
+def test_crop_and_range_and_normalize(oracle):
+    g = np.random.default_rng(11).random((20, 20), dtype=np.float32)
+    assert np.array_equal(oracle.crop(g, 12, 0), g[:12, :12])               # the reference's Offset == 0
+    assert np.array_equal(oracle.crop(g, 12, 4), g[4:16, 4:16])
+    c = oracle.crop(g, 12, 12)                                              # reads past the edge clamp
+    assert np.array_equal(c[:8, :8], g[12:, 12:]) and np.all(c[8:, :8] == g[19, 12:]) and c[11, 11] == g[19, 19]
+    r = oracle.map_range(g)
+    assert r[0] == g.min() and r[1] == g.max() and r[2] == f32(g.max() - g.min())
+    assert np.array_equal(oracle.map_range(g, lim_min=-1.0), np.array([-1.0, g.max(), g.max() + f32(1.0)], np.float32))
+    n = oracle.normalize(g, r)
+    assert np.array_equal(n, (g - r[0]) / r[2]) and n.min() == 0.0 and n.max() == 1.0
+    z = oracle.normalize(g, np.array([0.25, 0.25, 0.0], np.float32))        # degenerate range: value forced to 0
+    assert np.all(np.isinf(z)) and np.all(z < 0)
