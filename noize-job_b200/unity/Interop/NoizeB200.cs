@@ -61,6 +61,21 @@ namespace xshazwar.noize.interop.b200 {
         [DllImport(LIB)] public static extern int nz_heightmap_mesh(int meshType, void* vertices, uint* indices, int resolution,
             int inputResolution, int marginPix, float tileHeight, float tileSize, NzSlice heights);
 
+        // ThermalErosionFilterDelegate, Filter/Kernel/Blur/ThermalErosionFilter.cs:138-146
+        [DllImport(LIB)] public static extern int nz_thermal_erosion(NzSlice src, float talus, float incrementRatio,
+            float meshHeightWidthRatio, int iterations, int resolution);
+        // ConstantJobScheduleDelegate, Filter/ConstantJob.cs:49-55
+        [DllImport(LIB)] public static extern int nz_constant(NzSlice src, NzSlice tmp, int operation, float constantValue, int resolution);
+        // ReductionJobScheduleDelegate, Filter/ReductionJob.cs:55-61
+        [DllImport(LIB)] public static extern int nz_reduce(NzSlice left, NzSlice right, NzSlice tmp, int operation, int resolution);
+        // CurveJobScheduleDelegate, Filter/Curve/CurveJob.cs:91-97
+        [DllImport(LIB)] public static extern int nz_curve(NzSlice src, NzSlice tmp, NzSlice curve, int resolution);
+        // CropJobDelegate, Filter/Sample/CropJob.cs:63-69 (offset 0 == the reference)
+        [DllImport(LIB)] public static extern int nz_crop(NzSlice input, int inputResolution, NzSlice output, int outputResolution, int offset);
+        // GetMapRangeJob / MapNormalizeValuesDelegate, Filter/NormalizeJob.cs:18-53,94-100
+        [DllImport(LIB)] public static extern int nz_map_range(NzSlice map, float* res3, float limMin, float limMax);
+        [DllImport(LIB)] public static extern int nz_normalize(NzSlice src, NzSlice tmp, float* args3, int resolution);
+
         // process-wide residency scope: the stages of one chain run on different worker threads
         [DllImport(LIB)] public static extern long nz_scope_create();
         [DllImport(LIB)] public static extern int nz_scope_enter(long scope);
@@ -80,9 +95,10 @@ namespace xshazwar.noize.interop.b200 {
     /// One blocking native call, run where the Burst job body used to run.  Not [BurstCompile]: P/Invoke from a
     /// managed IJob is legal; the status code comes back through a NativeReference checked in OnStageComplete.
     public unsafe struct NativeCallJob : IJob {
-        public enum Op { Fractal, KernelFilter, GaussFilter, SmoothFilter, MinErosion, FlowMap, Mesh }
+        public enum Op { Fractal, KernelFilter, GaussFilter, SmoothFilter, MinErosion, FlowMap, Mesh, ThermalErosion, Constant, Reduce, Curve, Crop }
         public Op op;
         [NativeDisableContainerSafetyRestriction] public NativeSlice<float> data;
+        [NativeDisableContainerSafetyRestriction] public NativeSlice<float> data2;   // right operand / curve samples / crop input
         [NativeDisableUnsafePtrRestriction] public void* vertices;
         [NativeDisableUnsafePtrRestriction] public uint* indices;
         public int resolution, inputResolution, marginPix, i0, i1, i2, xpos, zpos;
@@ -102,6 +118,11 @@ namespace xshazwar.noize.interop.b200 {
                 case Op.MinErosion:   rc = Native.nz_min_erosion(s, resolution, i1); break;
                 case Op.FlowMap:      rc = Native.nz_flowmap(s, resolution, i1, f0, f1); break;
                 case Op.Mesh:         rc = Native.nz_heightmap_mesh(i0, vertices, indices, resolution, inputResolution, marginPix, f0, f1, s); break;
+                case Op.ThermalErosion: rc = Native.nz_thermal_erosion(s, f0, f1, f2, i1, resolution); break;
+                case Op.Constant:     rc = Native.nz_constant(s, NzSlice.Null, i0, f0, resolution); break;
+                case Op.Reduce:       rc = Native.nz_reduce(s, NzSlice.From(data2), NzSlice.Null, i0, resolution); break;
+                case Op.Curve:        rc = Native.nz_curve(s, NzSlice.Null, NzSlice.From(data2), resolution); break;
+                case Op.Crop:         rc = Native.nz_crop(NzSlice.From(data2), inputResolution, s, resolution, i0); break;
             }
             if (scope != 0) Native.nz_scope_leave();
             status.Value = rc;
@@ -174,6 +195,93 @@ namespace xshazwar.noize.interop.b200 {
             EnsureStatus();
             jobHandle = new NativeCallJob {
                 op = NativeCallJob.Op.MinErosion, data = d.data, resolution = d.resolution, i1 = iterations, status = status
+            }.Schedule(dependency);
+        }
+    }
+
+    // StageThermalErosion, Filter/Kernel/Blur/StageThermalErosion.cs:13-29 (same serialized fields)
+    [CreateAssetMenu(fileName = "GpuStageThermalErosion", menuName = "Noize/B200/ThermalErosion", order = 2)]
+    public class GpuStageThermalErosion : GpuStage {
+        [Range(1, 32)] public int iterations = 1;
+        [Range(1, 90)] public int talus = 45;
+        public float increment = 0.5f;
+        public float meshHeightWidthRatio = 0.75f;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            EnsureStatus();
+            jobHandle = new NativeCallJob {
+                op = NativeCallJob.Op.ThermalErosion, data = d.data, resolution = d.resolution, i1 = iterations,
+                f0 = (float) talus, f1 = increment, f2 = meshHeightWidthRatio, status = status
+            }.Schedule(dependency);
+        }
+    }
+
+    // ConstantStage, Filter/ConstantStage.cs:13-60
+    [CreateAssetMenu(fileName = "GpuConstant", menuName = "Noize/B200/Constant", order = 2)]
+    public class GpuConstantStage : GpuStage {
+        public ConstantStage.ConstantOperationType operation;
+        [Range(0, 1)] public float value = 0.5f;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            EnsureStatus();
+            jobHandle = new NativeCallJob {
+                op = NativeCallJob.Op.Constant, data = d.data, resolution = d.resolution, i0 = (int) operation, f0 = value, status = status
+            }.Schedule(dependency);
+        }
+    }
+
+    // ReduceStage, Filter/Reduce/ReduceStage.cs:21-68 (TransformData hands a GeneratorData downstream, :52-61)
+    [CreateAssetMenu(fileName = "GpuReduceStage", menuName = "Noize/B200/ReduceFilter", order = 2)]
+    public class GpuReduceStage : GpuStage {
+        public ReductionType operation;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<ReduceData>(requirements);
+            ReduceData d = (ReduceData) requirements.data;
+            EnsureStatus();
+            jobHandle = new NativeCallJob {
+                op = NativeCallJob.Op.Reduce, data = d.data, data2 = d.rightData, resolution = d.resolution, i0 = (int) operation, status = status
+            }.Schedule(dependency);
+        }
+        public override void TransformData(PipelineWorkItem inputData) {
+            ReduceData d = (ReduceData) inputData.data;
+            inputData.data = new GeneratorData { uuid = d.uuid, resolution = d.resolution, data = d.data, xpos = d.xpos, zpos = d.zpos };
+        }
+    }
+
+    // CurveStage, Filter/Curve/CurveStage.cs:13-73: the AnimationCurve is discretised exactly as ExtractCurve does (:27-35)
+    [CreateAssetMenu(fileName = "GpuCurveStage", menuName = "Noize/B200/CurveFilter", order = 2)]
+    public class GpuCurveStage : GpuStage {
+        public AnimationCurve unityCurve;
+        public int samples = 256;
+        NativeArray<float> curve;
+        public override void ResizeNativeContainers(int size) {
+            if (curve.IsCreated) curve.Dispose();
+            curve = new NativeArray<float>(samples, Allocator.Persistent, NativeArrayOptions.UninitializedMemory);
+            for (int i = 0; i < samples; i++) curve[i] = unityCurve.Evaluate((float) i / samples);
+        }
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            EnsureStatus();
+            jobHandle = new NativeCallJob {
+                op = NativeCallJob.Op.Curve, data = d.data, data2 = new NativeSlice<float>(curve), resolution = d.resolution, status = status
+            }.Schedule(dependency);
+        }
+        public override void OnDestroy() { if (curve.IsCreated) curve.Dispose(); base.OnDestroy(); }
+    }
+
+    // CropStage, Filter/Sample/CropStage.cs:13-19 (offset 0 reproduces the reference, whose CropJob.Offset is never set)
+    [CreateAssetMenu(fileName = "GpuCropStage", menuName = "Noize/B200/CenterCropResolution", order = 2)]
+    public class GpuCropStage : GpuStage {
+        public bool center = false;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            DownsampleData d = (DownsampleData) requirements.data;
+            EnsureStatus();
+            jobHandle = new NativeCallJob {
+                op = NativeCallJob.Op.Crop, data = d.data, data2 = d.inputData, resolution = d.resolution,
+                inputResolution = d.inputResolution, i0 = center ? (d.inputResolution - d.resolution) / 2 : 0, status = status
             }.Schedule(dependency);
         }
     }
