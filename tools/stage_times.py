@@ -47,6 +47,24 @@ def main():
     rows.append(("flowmap x5", ms, 8 * cells))
     ms = timeit(lambda: d.min_erosion(a, b, 5), reps)
     rows.append(("min erosion x5", ms, 8 * cells))
+    # SURVEY section 8f rows (compulsory bytes: 8 B/cell per unary map, 12 B/cell per binary map,
+    # 8 B/cell per thermal phase = 32 B/cell per thermal iteration)
+    d.fractal(a, 3, 0.4, octaves=13, noise_size=1700)
+    d.fractal(b, 1, 0.4, octaves=2, noise_size=1700)
+    ms = timeit(lambda: d.thermal_erosion(a, 45.0, 0.5, 0.75, 1), reps)
+    rows.append(("thermal x1", ms, 32 * cells))
+    ms = timeit(lambda: d.constant(a, 0, 0.999), reps)
+    rows.append(("constant mul", ms, 8 * cells))
+    ms = timeit(lambda: d.reduce(a, b, 3), reps)
+    rows.append(("reduce max", ms, 12 * cells))
+    cv = torch.linspace(0, 1, 256, device="cuda") ** 2
+    ms = timeit(lambda: d.curve(a, cv), reps)
+    rows.append(("curve 256", ms, 8 * cells))
+    ms = timeit(lambda: d.map_range(a), reps)
+    rows.append(("map range", ms, 4 * cells))
+    ms = timeit(lambda: d.normalize(a, 0.1, 0.7), reps)
+    rows.append(("normalize", ms, 8 * cells))
+    d.fractal(a, 3, 0.4, octaves=13, noise_size=1700)
     R = N - 8
     vtx = torch.empty((R + 1) * (R + 1), 12, device="cuda")
     idx = torch.empty(6 * R * R, dtype=torch.int32, device="cuda")
