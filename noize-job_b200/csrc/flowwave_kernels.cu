@@ -56,14 +56,24 @@ struct WaveParams {
 struct V4 {
     float v[VW];
 };
-__device__ __forceinline__ V4 ld4(const float* base, int off) {
-    const float2 t = *reinterpret_cast<const float2*>(base + off);
+// Shared-memory accessors: `slot` is an ABSOLUTE shared-window byte address (ring slot row + this lane's first
+// column), FIELD a compile-time float offset of the ring (an LDS/STS immediate), `d` a per-lane float offset
+// (outer neighbours).  Nothing but the access itself is executed per load: no base materialisation, no index scaling.
+template <int FIELD>
+__device__ __forceinline__ V4 ld4(uint32_t slot) {
     V4 r;
-    r.v[0] = t.x; r.v[1] = t.y;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(r.v[0]), "=f"(r.v[1]) : "r"(slot), "n"(FIELD * 4));
     return r;
 }
-__device__ __forceinline__ void st4(float* base, int off, const V4& a) {
-    *reinterpret_cast<float2*>(base + off) = make_float2(a.v[0], a.v[1]);
+template <int FIELD>
+__device__ __forceinline__ float ld1(uint32_t slot, int dbytes) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(slot + dbytes), "n"(FIELD * 4));
+    return r;
+}
+template <int FIELD>
+__device__ __forceinline__ void st4(uint32_t slot, const V4& a) {
+    asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(slot), "n"(FIELD * 4), "f"(a.v[0]), "f"(a.v[1]) : "memory");
 }
 __device__ __forceinline__ V4 splat(float x) {
     V4 r;
@@ -113,15 +123,14 @@ template <int I> struct Rings {
 };
 
 struct Lane {
-    float* sm;
-    int R[RING];   // R[j] = float offset (ring-relative) of the slot of row s-j, plus this lane's first column
-    int dl, dr;    // offsets (from this lane's first column) of the clamped west / east outer neighbours
-    int c;         // first of this lane's VW strip columns
-    int H;         // grid rows
+    uint32_t R[RING];   // R[j] = shared-window byte address of the slot of row s-j, at this lane's first column
+    int dl, dr;         // BYTE offsets (from this lane's first column) of the clamped west / east outer neighbours
+    int c;              // first of this lane's VW strip columns
+    int H;              // grid rows
 };
 
 // slot of row (s - lag + d), d in {-1,0,+1}; rows outside the grid clamp onto the border row
-__device__ __forceinline__ int slot_of(const Lane& L, int lag, int d, int r) {
+__device__ __forceinline__ uint32_t slot_of(const Lane& L, int lag, int d, int r) {
     const int j0 = lag % RING, jm = (lag + 1) % RING, jp = (lag + RING - 1) % RING;
     if (d == 0) return L.R[j0];
     if (d < 0) return r == 0 ? L.R[j0] : L.R[jm];
@@ -135,40 +144,39 @@ __device__ __forceinline__ void stage_outflow(const Lane& L, int s, int zc0, int
     const int r = s - lag;
     const int lo = max(0, zc0 - (2 * I - 2 * T + 1)), hi = min(L.H, zc1 + (2 * I - 2 * T + 1));
     if (r < lo || r >= hi) return;
-    const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
-    float* sm = L.sm;
+    const uint32_t o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
     V4 H0, HS, HN, w0, fW, fE, fS, fN;
     float HWl, HEr;
     if (T == 1) {
         // level 0: water == 1e-4 everywhere, flows == 0: H_0 = 1e-4 + h computed on the fly
-        const V4 a = ld4(sm + RG::HC(0), o0), b = ld4(sm + RG::HC(0), os), d = ld4(sm + RG::HC(0), on);
+        const V4 a = ld4<RG::HC(0)>(o0), b = ld4<RG::HC(0)>(os), d = ld4<RG::HC(0)>(on);
 #pragma unroll
         for (int q = 0; q < VW; q++) {
             H0.v[q] = WATER0 + a.v[q];
             HS.v[q] = WATER0 + b.v[q];
             HN.v[q] = WATER0 + d.v[q];
         }
-        HWl = WATER0 + sm[RG::HC(0) + o0 + L.dl];
-        HEr = WATER0 + sm[RG::HC(0) + o0 + L.dr];
+        HWl = WATER0 + ld1<RG::HC(0)>(o0, L.dl);
+        HEr = WATER0 + ld1<RG::HC(0)>(o0, L.dr);
         w0 = splat(WATER0);
         fW = fE = fS = fN = splat(0.0f);
     } else {
         constexpr int P = T > 1 ? T - 1 : 1;
-        H0 = ld4(sm + RG::Ht(P), o0); HS = ld4(sm + RG::Ht(P), os); HN = ld4(sm + RG::Ht(P), on);
-        HWl = sm[RG::Ht(P) + o0 + L.dl]; HEr = sm[RG::Ht(P) + o0 + L.dr];
-        w0 = ld4(sm + RG::Wt(P), o0);
-        fW = ld4(sm + RG::F(P, 0), o0); fE = ld4(sm + RG::F(P, 1), o0);
-        fS = ld4(sm + RG::F(P, 2), o0); fN = ld4(sm + RG::F(P, 3), o0);
+        H0 = ld4<RG::Ht(P)>(o0); HS = ld4<RG::Ht(P)>(os); HN = ld4<RG::Ht(P)>(on);
+        HWl = ld1<RG::Ht(P)>(o0, L.dl); HEr = ld1<RG::Ht(P)>(o0, L.dr);
+        w0 = ld4<RG::Wt(P)>(o0);
+        fW = ld4<RG::F(P, 0)>(o0); fE = ld4<RG::F(P, 1)>(o0);
+        fS = ld4<RG::F(P, 2)>(o0); fN = ld4<RG::F(P, 3)>(o0);
     }
     V4 oW, oE, oS, oN;
 #pragma unroll
     for (int q = 0; q < VW; q++)
         flow_cell(H0.v[q], q == 0 ? HWl : H0.v[q > 0 ? q - 1 : 0], q == VW - 1 ? HEr : H0.v[q < VW - 1 ? q + 1 : 0], HS.v[q],
                   HN.v[q], w0.v[q], fW.v[q], fE.v[q], fS.v[q], fN.v[q], oW.v[q], oE.v[q], oS.v[q], oN.v[q]);
-    st4(sm + RG::F(T, 0), o0, oW);
-    st4(sm + RG::F(T, 1), o0, oE);
-    st4(sm + RG::F(T, 2), o0, oS);
-    st4(sm + RG::F(T, 3), o0, oN);
+    st4<RG::F(T, 0)>(o0, oW);
+    st4<RG::F(T, 1)>(o0, oE);
+    st4<RG::F(T, 2)>(o0, oS);
+    st4<RG::F(T, 3)>(o0, oN);
 }
 
 template <int I, int T>
@@ -178,15 +186,14 @@ __device__ __forceinline__ void stage_water(const Lane& L, int s, int zc0, int z
     const int r = s - lag;
     const int lo = max(0, zc0 - (2 * I - 2 * T)), hi = min(L.H, zc1 + (2 * I - 2 * T));
     if (r < lo || r >= hi) return;
-    const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
-    float* sm = L.sm;
-    const V4 fW = ld4(sm + RG::F(T, 0), o0), fE = ld4(sm + RG::F(T, 1), o0);
-    const V4 fS = ld4(sm + RG::F(T, 2), o0), fN = ld4(sm + RG::F(T, 3), o0);
-    const float fE_l = sm[RG::F(T, 1) + o0 + L.dl], fW_r = sm[RG::F(T, 0) + o0 + L.dr];
-    const V4 fN_s = ld4(sm + RG::F(T, 3), os), fS_n = ld4(sm + RG::F(T, 2), on);
+    const uint32_t o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
+    const V4 fW = ld4<RG::F(T, 0)>(o0), fE = ld4<RG::F(T, 1)>(o0);
+    const V4 fS = ld4<RG::F(T, 2)>(o0), fN = ld4<RG::F(T, 3)>(o0);
+    const float fE_l = ld1<RG::F(T, 1)>(o0, L.dl), fW_r = ld1<RG::F(T, 0)>(o0, L.dr);
+    const V4 fN_s = ld4<RG::F(T, 3)>(os), fS_n = ld4<RG::F(T, 2)>(on);
     constexpr int P = T > 1 ? T - 1 : 1;
-    const V4 w = (T == 1) ? splat(WATER0) : ld4(sm + RG::Wt(P), o0);
-    const V4 hh = ld4(sm + RG::HC(T - 1), o0);
+    const V4 w = (T == 1) ? splat(WATER0) : ld4<RG::Wt(P)>(o0);
+    const V4 hh = ld4<RG::HC(T - 1)>(o0);
     V4 nw, nH;
 #pragma unroll
     for (int q = 0; q < VW; q++) {
@@ -195,9 +202,9 @@ __device__ __forceinline__ void stage_water(const Lane& L, int s, int zc0, int z
         nw.v[q] = fmaxf(0.0f, fmaf(in - out, TIMESTEP, w.v[q]));
         nH.v[q] = nw.v[q] + hh.v[q];
     }
-    st4(sm + RG::Wt(T), o0, nw);
-    st4(sm + RG::Ht(T), o0, nH);
-    if (T + 1 < I) st4(sm + RG::HC(T < I - 1 ? T : 0), o0, hh);   // hand the height row to the next water stage
+    st4<RG::Wt(T)>(o0, nw);
+    st4<RG::Ht(T)>(o0, nH);
+    if (T + 1 < I) st4<RG::HC(T < I - 1 ? T : 0)>(o0, hh);   // hand the height row to the next water stage
 }
 
 template <int I>
@@ -206,12 +213,11 @@ __device__ __forceinline__ void stage_velocity(const Lane& L, int s, int zc0, in
     constexpr int lag = 4 * I;
     const int r = s - lag;
     if (r < zc0 || r >= zc1) return;
-    const int o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
-    float* sm = L.sm;
-    const V4 fW = ld4(sm + RG::F(I, 0), o0), fE = ld4(sm + RG::F(I, 1), o0);
-    const float fE_l = sm[RG::F(I, 1) + o0 + L.dl], fW_r = sm[RG::F(I, 0) + o0 + L.dr];
-    const V4 fS = ld4(sm + RG::F(I, 2), o0), fN = ld4(sm + RG::F(I, 3), o0);
-    const V4 fS_n = ld4(sm + RG::F(I, 2), on), fN_s = ld4(sm + RG::F(I, 3), os);
+    const uint32_t o0 = slot_of(L, lag, 0, r), os = slot_of(L, lag, -1, r), on = slot_of(L, lag, +1, r);
+    const V4 fW = ld4<RG::F(I, 0)>(o0), fE = ld4<RG::F(I, 1)>(o0);
+    const float fE_l = ld1<RG::F(I, 1)>(o0, L.dl), fW_r = ld1<RG::F(I, 0)>(o0, L.dr);
+    const V4 fS = ld4<RG::F(I, 2)>(o0), fN = ld4<RG::F(I, 3)>(o0);
+    const V4 fS_n = ld4<RG::F(I, 2)>(on), fN_s = ld4<RG::F(I, 3)>(os);
     V4 res;
 #pragma unroll
     for (int q = 0; q < VW; q++) {
@@ -262,18 +268,18 @@ __global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) 
     const int cmin = max(0, -xs0), cmax = min(FLW - 1, p.W - 1 - xs0);   // strip columns inside the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int role = warp >> 1;
+    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm);
     Lane L;
-    L.sm = sm;
     L.c = (warp & 1) * 64 + lane * VW;
-    L.dl = max(L.c - 1, cmin) - L.c;
-    L.dr = min(L.c + VW, cmax) - L.c;
+    L.dl = (max(L.c - 1, cmin) - L.c) * 4;
+    L.dr = (min(L.c + VW, cmax) - L.c) * 4;
     L.H = H;
     const int hlo = max(0, zc0 - 2 * I), hhi = min(H, zc1 + 2 * I);
     // first step, rounded down to a multiple of RING so that slot(s) = s mod RING starts at 0
     const int s_first = zc0 - 2 * I;
     const int s_begin = s_first - (((s_first % RING) + RING) % RING);
 #pragma unroll
-    for (int j = 0; j < RING; j++) L.R[j] = ((RING - j) % RING) * FLW + L.c;   // rows s_begin - j
+    for (int j = 0; j < RING; j++) L.R[j] = sm_base + (((RING - j) % RING) * FLW + L.c) * 4;   // rows s_begin - j
 
     V4 pf[PF];
     if (role == 6) {
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) 
             case 4: if (I >= 5) stage_outflow<I, (I >= 5 ? 5 : 1)>(L, s, zc0, zc1); break;
             case 5: stage_velocity<I>(L, s, zc0, zc1, p, xs0); break;
             case 6:
-                st4(sm + Rings<I>::HC(0), L.R[0], pf[0]);          // row s, requested PF steps ago
+                st4<Rings<I>::HC(0)>(L.R[0], pf[0]);          // row s, requested PF steps ago
 #pragma unroll
                 for (int j = 0; j + 1 < PF; j++) pf[j] = pf[j + 1];
                 pf[PF - 1] = load_row(L, s + PF, hlo, hhi, p, xs0);
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) 
         }
         __syncthreads();
         // advance the slot registers: row s+1 takes the slot row s-4 vacates
-        const int r4 = L.R[RING - 1];
+        const uint32_t r4 = L.R[RING - 1];
 #pragma unroll
         for (int j = RING - 1; j > 0; j--) L.R[j] = L.R[j - 1];
         L.R[0] = r4;
