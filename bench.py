@@ -272,6 +272,8 @@ def run_ours(args):
     stage_bytes = {"filter": 8 * cells, "flow": 8 * cells, "erosion": 8 * cells,
                    "mesh": 4 * cells + 48 * (R + 1) ** 2 + 24 * R * R}
     stages = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    stage_traffic = json.load(open(tpath)).get("stage_dram_bytes_per_step", {}) if os.path.exists(tpath) else {}
     for name, ms in zip(names[:-1], stage_ms):
         s = {"ms": round(ms, 4), "mcells_s": round(cells / ms / 1e3, 1)}
         if name == "noise":
@@ -280,6 +282,8 @@ def run_ours(args):
         else:
             ach = stage_bytes[name] / ms / 1e6
             s.update(bound="hbm", compulsory_gbs=round(ach, 1), peak_gbs=hbm_peak, frac=round(ach / hbm_peak, 4))
+        # DRAM bytes the stage's kernels moved per step at N = 16384 on one GPU (ncu --set full, profiles/traffic.json)
+        s["traffic"] = stage_traffic.get(name) if (N == N_GRID and world == 1) else None
         stages[name] = s
     # dominant kernel: the fBm evaluator (one launch per step on this rank's band)
     own_cells = chain.own * N
