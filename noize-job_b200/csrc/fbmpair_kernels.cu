@@ -24,6 +24,7 @@
 //     the compensating constants.  The wrap of (T1 + ix) into [0,289) is an unsigned min.
 //
 // Result: ~57 issue slots and ~52 FP-pipe cycles per cell and octave instead of 111 / 90.
+#include <stdlib.h>
 #include "nz_common.cuh"
 
 namespace nz {
@@ -192,13 +193,157 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_simplex_pair_kernel(float
     }
 }
 
+// =====================================================================================================================
+// cellular (Worley F1*F2) fBm, same two techniques.  cellular2D hashes the 3x3 neighbourhood of the lattice cell:
+//   p(c, j) = permute(permute(Pix + c-1) + Piy + j-1)  ->  jitter (ox, oy) of the feature point   (cellular2D.cs)
+// With the thread's 4 cells in one COLUMN, Pix and everything derived from x alone (floor, residue, the three inner
+// hashes, Pfx + xo) is computed once per thread and octave.  Tables: T1[Pix + c-1] = permute row offset (4 B, 128-B rows),
+// T2[(T1 + Piy + j-1) mod 289] = (ox, oy) as one bank-private LDS.64 (lane l owns bytes 8l..8l+7 of a 256-B row; rows
+// 289 and 290 repeat rows 0 and 1 so that j = 0..2 are immediate offsets after ONE wrap).  112 KB of shared memory.
+constexpr int CT_ROWS = 291;
+constexpr int C_OFF_T1 = 0, C_OFF_T2 = CT_ROWS * 128;
+constexpr int CELL_SMEM = CT_ROWS * 128 + CT_ROWS * 256;
+constexpr uint32_t MAGIC_SHL8 = (uint32_t)(0x4B400000ull << 8);
+constexpr uint32_t WRAP8 = 289u * 256;
+
+__device__ void build_cellular_tables() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < CT_ROWS; r += nwarps) {
+        // T1 row r <-> inner hash argument Pix + oi = r - 145: byte offset of T2 row (permute + 144) [+ Piy comes in the kernel]
+        *reinterpret_cast<uint32_t*>(sm + C_OFF_T1 + r * 128 + lane * 4) =
+            (uint32_t)(permute_int(r - 145) + 144) * 256 + lane * 8 - MAGIC_SHL8;
+        // T2 row r <-> outer hash argument r - 145: jitter of its hash, with the operations of cellular_jitter() in noise_kernels.cu
+        const float p = (float)permute_int(r - 145);
+        const float K = 0.142857142857f, Ko = 0.428571428571f;
+        const float pk = p * K;
+        const float fl = floorf(pk);
+        const float ox = (pk - fl) - Ko;
+        const float m7 = fmaf(-floorf(fl * (1.0f / 7.0f)), 7.0f, fl);
+        const float oy = fmaf(m7, K, -Ko);
+        *reinterpret_cast<float2*>(sm + C_OFF_T2 + r * 256 + lane * 8) = make_float2(ox, oy);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t off) { return *reinterpret_cast<const float2*>(sm + C_OFF_T2 + off); }
+__device__ __forceinline__ float rectify1(float v) { return (1.0f + v) * 0.5f; }
+
+// F1*F2 of one cell from its nine squared distances d[c][j] (min network of cellular2D.cs, as noise_kernels.cu)
+struct Mins {
+    float d1[3], d2[3];
+};
+__device__ __forceinline__ void fold_column(Mins& m, int j, float d0, float d1_, float d2_) {
+    const float d1a = fminf(d0, d1_);
+    float t = fmaxf(d0, d1_);
+    t = fminf(t, d2_);
+    m.d1[j] = fminf(d1a, t);
+    m.d2[j] = fmaxf(d1a, t);
+}
+__device__ __forceinline__ float finish_cell(Mins& m) {
+    if (!(m.d1[0] < m.d1[1])) { const float t = m.d1[0]; m.d1[0] = m.d1[1]; m.d1[1] = t; }
+    if (!(m.d1[0] < m.d1[2])) { const float t = m.d1[0]; m.d1[0] = m.d1[2]; m.d1[2] = t; }
+    m.d1[1] = fminf(m.d1[1], m.d2[1]);
+    m.d1[2] = fminf(m.d1[2], m.d2[2]);
+    m.d1[1] = fminf(m.d1[1], m.d1[2]);
+    m.d1[1] = fminf(m.d1[1], m.d2[0]);
+    return rectify1(sqrtf(m.d1[0])) * rectify1(sqrtf(m.d1[1]));
+}
+
+template <int PAIRS>
+__global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_cellular_pair_kernel(float* __restrict__ dst, FractalParams p, int wshift,
+                                                                           int col_blocks, int n_items) {
+    build_cellular_tables();
+    const int lane = threadIdx.x & 31;
+    uint32_t c1 = C_OFF_T1 + 144 * 128 + lane * 4 - MAGIC_SHL7;
+    asm volatile("" : "+r"(c1));
+    const int tx = threadIdx.x & ((1 << wshift) - 1), ty = threadIdx.x >> wshift;
+    constexpr int CELLS = 2 * PAIRS;
+    const int rows_per_item = CELLS * (PAIR_THREADS >> wshift);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cb = item % col_blocks, rg = item / col_blocks;
+        const int x = (cb << wshift) + tx;
+        const int r0 = rg * rows_per_item + CELLS * ty;
+        const float xi = ((float)x + p.posx) / p.noise_size;
+        P zi[PAIRS], t[PAIRS];
+#pragma unroll
+        for (int q = 0; q < PAIRS; q++) {
+            zi[q].x = ((float)(p.z_first + r0 + 2 * q) + p.posz) / p.noise_size;
+            zi[q].y = ((float)(p.z_first + r0 + 2 * q + 1) + p.posz) / p.noise_size;
+            t[q] = bc(0.0f);
+        }
+        float detune = 0.0f, f = 1.0f, a = p.start_amp;
+        for (int i = 0; i < p.octaves; i++) {
+            // ---- everything that depends on x alone: once per thread ----
+            const float Px = f * xi;
+            const float flx = floorf(Px);
+            const float Pfx = Px - flx;
+            const float rx = fmaf(-289.0f, fmaf(flx, 1.0f / 289.0f, MAGIC) - MAGIC, flx);
+            const uint32_t a1 = (__float_as_uint(rx + MAGIC) << 7) + c1;        // T1 row of Pix - 1
+            uint32_t t1[3];
+            float xs[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                t1[c] = lds_u32(a1 + c * 128);
+                xs[c] = Pfx + (0.5f - (float)c);                                  // Pfx + xo
+            }
+#pragma unroll
+            for (int q = 0; q < PAIRS; q++) {
+                const P Py = pmul(bc(f), zi[q]);
+                const P fly = pfloor(Py);
+                const P Pfy = psub(Py, fly);
+                const P ry = pfma(bc(-289.0f), psub(pfma(fly, bc(1.0f / 289.0f), bc(MAGIC)), bc(MAGIC)), fly);
+                const P by = padd(ry, bc(MAGIC));
+                uint32_t h[2][3];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t yb = __float_as_uint(e ? by.y : by.x) << 8;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const uint32_t u = yb + t1[c];                            // T2 row permute(Pix+c-1) + Piy - 1 + 145, unwrapped
+                        h[e][c] = min(u, u - WRAP8);
+                    }
+                }
+                Mins mA, mB;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const P ys = psub(Pfy, bc((float)j - 0.5f));                  // Pfy - ofj
+                    float dA[3], dB[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float2 oA = lds_f2(h[0][c] + j * 256), oB = lds_f2(h[1][c] + j * 256);
+                        const P dx = padd(bc(xs[c]), make_float2(oA.x, oB.x));
+                        const P dy = padd(ys, make_float2(oA.y, oB.y));
+                        const P d = pfma(dy, dy, pmul(dx, dx));
+                        dA[c] = d.x;
+                        dB[c] = d.y;
+                    }
+                    fold_column(mA, j, dA[0], dA[1], dA[2]);
+                    fold_column(mB, j, dB[0], dB[1], dB[2]);
+                }
+                t[q] = pfma(bc(a), make_float2(finish_cell(mA), finish_cell(mB)), t[q]);
+            }
+            detune += p.detune_rate;
+            f *= (p.stepdown - detune);
+            a *= p.G;
+        }
+        if (x < p.width) {
+#pragma unroll
+            for (int q = 0; q < PAIRS; q++) {
+                const int r = r0 + 2 * q;
+                if (r < p.rows) dst[(size_t)r * p.width + x] = t[q].x / p.norm;
+                if (r + 1 < p.rows) dst[(size_t)(r + 1) * p.width + x] = t[q].y / p.norm;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 bool fractal_pair_supported(int noise_type, const FractalParams& p) {
-    return noise_type == NZ_NOISE_SIMPLEX && p.fast_hash && p.width >= 32 && (long long)p.width * p.rows >= (1 << 19);
+    return (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR) && p.fast_hash && p.width >= 32 &&
+           (long long)p.width * p.rows >= (1 << 19);
 }
 
-int32_t launch_fractal_pair(float* d_dst, const FractalParams& p, cudaStream_t s) {
+int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s) {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -208,16 +353,31 @@ int32_t launch_fractal_pair(float* d_dst, const FractalParams& p, cudaStream_t s
     static bool configured = false;   // per-process; the attribute is per-function and sticky
     if (!configured) {
         NZ_CUDA(cudaFuncSetAttribute(fbm_simplex_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
         configured = true;
     }
     int wshift = 5;
     while ((1 << wshift) < p.width && wshift < 10) wshift++;
     const int col_blocks = cdiv(p.width, 1 << wshift);
-    const int rows_per_item = 4 * (PAIR_THREADS >> wshift);
+    // cells per thread: 4 (two pairs) for simplex; cellular carries nine distances per cell, NZ_CELL_PAIRS picks 1 or 2 pairs
+    static const int cell_pairs = [] {
+        const char* e = getenv("NZ_CELL_PAIRS");
+        return e ? atoi(e) : 2;
+    }();
+    const int cells = noise_type == NZ_NOISE_CELLULAR ? 2 * (cell_pairs == 1 ? 1 : 2) : 4;
+    const int rows_per_item = cells * (PAIR_THREADS >> wshift);
     const long long n_items = (long long)col_blocks * cdiv(p.rows, rows_per_item);
     NZ_REQUIRE(n_items < (1ll << 31), "nz_fractal: window too large");
     const int grid = n_items < sms ? (int)n_items : sms;
-    fbm_simplex_pair_kernel<<<grid, PAIR_THREADS, PAIR_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
+    if (noise_type == NZ_NOISE_CELLULAR) {
+        if (cells == 2)
+            fbm_cellular_pair_kernel<1><<<grid, PAIR_THREADS, CELL_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
+        else
+            fbm_cellular_pair_kernel<2><<<grid, PAIR_THREADS, CELL_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
+    } else {
+        fbm_simplex_pair_kernel<<<grid, PAIR_THREADS, PAIR_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
+    }
     NZ_LAUNCHED();
     return NZ_OK;
 }

@@ -418,14 +418,14 @@ int32_t launch_typed(float* d_dst, const FractalParams& p, cudaStream_t s) {
 }  // namespace
 
 int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s) {
-    // simplex on a window large enough to fill the GPU: packed-pair kernel (fbmpair_kernels.cu), bit-identical
+    // simplex / cellular on a window large enough to fill the GPU: packed-pair kernels (fbmpair_kernels.cu), bit-identical
     // to the scalar kernel below; NZ_FBM_PATH=scalar|pair forces one (tests compare the two bitwise)
     {
         const char* force = getenv("NZ_FBM_PATH");
         const bool scalar = force && force[0] == 's', pair = force && force[0] == 'p';
-        if (!scalar && noise_type == NZ_NOISE_SIMPLEX && p.fast_hash && p.width >= 32 &&
+        if (!scalar && (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR) && p.fast_hash && p.width >= 32 &&
             (pair || fractal_pair_supported(noise_type, p)))
-            return launch_fractal_pair(d_dst, p, s);
+            return launch_fractal_pair(d_dst, noise_type, p, s);
     }
     if (p.rows > 65535) {
         // gridDim.y limit: split into row chunks

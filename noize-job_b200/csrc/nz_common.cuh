@@ -55,7 +55,7 @@ struct FractalParams {
 };
 int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
 bool fractal_pair_supported(int noise_type, const FractalParams& p);
-int32_t launch_fractal_pair(float* d_dst, const FractalParams& p, cudaStream_t s);
+int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
 
 int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,
                          const float* kz, float factor, int iterations, float** d_result, cudaStream_t s);
