@@ -194,7 +194,22 @@ __device__ __forceinline__ void rgrad2(float px, float py, const float2* rtab, f
     gx = g.x;
     gy = g.y;
 }
-template <int TYPE>
+// fmodf(p, per) for |p| < 2^22 (FAST: the host proved it): fmod is exact, so p - per*trunc(p/per) with a one-step
+// correction of the estimated quotient gives the same value as the library routine (whose generic bit-serial loop
+// costs ~80 instructions at C5 coordinates).  The sign of a zero result may differ from fmodf's; it cannot reach the
+// output: permute() maps +-0 to +0 and every other use adds the value to a non-zero or to another hash input.
+template <bool FAST>
+__device__ __forceinline__ float fmod_period(float p, float per, float inv_per) {
+    if (!FAST) return fmodf(p, per);
+    const float a = fabsf(p);
+    const float q = truncf(a * inv_per);
+    float r = fmaf(-per, q, a);             // exact: |r| < 2*per, a and per*q below 2^23
+    r = r < 0.0f ? r + per : r;
+    r = r >= per ? r - per : r;
+    return copysignf(r, p);
+}
+
+template <int TYPE, bool FAST>
 __device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, float pery, const float2* rtab) {
     posy += 0.001f;
     float ux = fmaf(posy, 0.5f, posx), uy = posy;
@@ -208,8 +223,9 @@ __device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, f
     float d0x = posx - p0x, d0y = posy - p0y;
     float d1x = posx - p1x, d1y = posy - p1y;
     float d2x = posx - p2x, d2y = posy - p2y;
-    float xw0 = fmodf(p0x, perx), xw1 = fmodf(p1x, perx), xw2 = fmodf(p2x, perx);
-    float yw0 = fmodf(p0y, pery), yw1 = fmodf(p1y, pery), yw2 = fmodf(p2y, pery);
+    const float ipx = 1.0f / perx, ipy = 1.0f / pery;      // compile-time constants at both call sites
+    float xw0 = fmod_period<FAST>(p0x, perx, ipx), xw1 = fmod_period<FAST>(p1x, perx, ipx), xw2 = fmod_period<FAST>(p2x, perx, ipx);
+    float yw0 = fmod_period<FAST>(p0y, pery, ipy), yw1 = fmod_period<FAST>(p1y, pery, ipy), yw2 = fmod_period<FAST>(p2y, pery, ipy);
     float g0x, g0y, g1x, g1y, g2x, g2y;
     rgrad2<TYPE>(fmaf(0.5f, yw0, xw0), yw0, rtab, g0x, g0y);
     rgrad2<TYPE>(fmaf(0.5f, yw1, xw1), yw1, rtab, g1x, g1y);
@@ -355,11 +371,11 @@ __device__ __forceinline__ float basis_value(float x, float z, const float2* gta
     } else if (TYPE == NZ_NOISE_PERLIN) {
         return rectify(cnoise2<FAST>(x, z, gtab));
     } else if (TYPE == NZ_NOISE_PERIODIC_PERLIN) {
-        return rectify(psrnoise2<TYPE>(x, z, 1010.0f, 102.0f, gtab));
+        return rectify(psrnoise2<TYPE, FAST>(x, z, 1010.0f, 102.0f, gtab));
     } else if (TYPE == NZ_NOISE_SIMPLEX) {
         return fmaf(65.0f, snoise2_raw<FAST>(x, z, gtab), 0.5f);  // Rectify(130*d) = (1 + 130*d)/2 = 0.5 + 65*d
     } else if (TYPE == NZ_NOISE_ROTATED_SIMPLEX) {
-        return rectify(psrnoise2<TYPE>(x, z, 1010.0f, 102.0f, gtab));
+        return rectify(psrnoise2<TYPE, FAST>(x, z, 1010.0f, 102.0f, gtab));
     } else if (TYPE == NZ_NOISE_CELLULAR) {
         return cellular2_rectified<FAST>(x, z, gtab);
     } else {
@@ -407,7 +423,8 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
 template <int TYPE, int CELLS>
 int32_t launch_typed(float* d_dst, const FractalParams& p, cudaStream_t s) {
     dim3 grid(cdiv(p.width, NZ_FBM_THREADS * CELLS), p.rows);
-    if ((TYPE == NZ_NOISE_SIMPLEX || TYPE == NZ_NOISE_PERLIN || TYPE == NZ_NOISE_CELLULAR) && p.fast_hash)
+    if ((TYPE == NZ_NOISE_SIMPLEX || TYPE == NZ_NOISE_PERLIN || TYPE == NZ_NOISE_CELLULAR || TYPE == NZ_NOISE_PERIODIC_PERLIN ||
+         TYPE == NZ_NOISE_ROTATED_SIMPLEX) && p.fast_hash)
         fbm_kernel<TYPE, CELLS, true><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
     else
         fbm_kernel<TYPE, CELLS, false><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
