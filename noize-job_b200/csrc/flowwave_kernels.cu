@@ -47,7 +47,7 @@ struct WaveParams {
     int W, H;
     int zc;        // rows per chunk
     int swi;       // interior columns per strip = FLW - 2*hx
-    int hx;        // halo columns each side (2I rounded up to a multiple of 4)
+    int hx;        // halo columns each side: 2I (even, so strips start on a float2 boundary)
     float nmin, nrange;
     float nsign;   // copysign(1, nrange)
     int zero_ok;   // nrange is finite and non-zero: 0/nrange == 0*nsign
@@ -263,7 +263,7 @@ template <int I>
 __global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) {
     extern __shared__ __align__(16) float sm[];
     const int H = p.H;
-    const int xs0 = blockIdx.x * p.swi - p.hx;           // grid x of strip column 0 (multiple of 4)
+    const int xs0 = blockIdx.x * p.swi - p.hx;           // grid x of strip column 0 (even)
     const int zc0 = blockIdx.y * p.zc, zc1 = min(zc0 + p.zc, H);
     const int cmin = max(0, -xs0), cmax = min(FLW - 1, p.W - 1 - xs0);   // strip columns inside the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -345,7 +345,7 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
     const int I = iterations;
     WaveParams p;
     p.h = d_height; p.out = d_out; p.W = width; p.H = rows;
-    p.hx = (2 * I + 3) & ~3;
+    p.hx = 2 * I;
     p.swi = FLW - 2 * p.hx;
     p.nmin = norm_min;
     p.nrange = norm_max - norm_min;
