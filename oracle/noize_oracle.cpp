@@ -7,7 +7,11 @@
  * and bench.py's cpu_baseline / --impl reference legs may load the library built from it.  The
  * product (libnoize_b200.so) never links, loads or calls anything in oracle/.
  *
- * PARITY STATUS: **parity unpinned** at the noise-basis boundary.  The reference has no tests, no
+ * PARITY STATUS: pinned at IMAGE precision, **parity unpinned** at bit level.  The reference's README screenshots
+ * (docs~/0.jpg, 3.jpg, 4.jpg, 5.jpg) show rendered outputs next to the inspector panel with every parameter of the
+ * run; tests/test_screenshot_pins.py runs this oracle with those parameters and rank-correlates it with the renders
+ * (simplex fBm 0.93, cellular fBm 0.99, Gauss -> value erosion terrain 0.87, flow map 0.88, with controls: other
+ * basis / position / size / orientation / stage order fit clearly worse).  Beyond that the reference has no tests, no
  * golden arrays and cannot be built here (Unity 2020.3 + Burst 1.5.4; no dotnet/mono/Unity in the
  * image).  The basis functions live in the un-vendored dependency com.unity.mathematics@1.2.1
  * (package.json:18), class Unity.Mathematics.noise — a C# port of the MIT-licensed Ashima Arts /

@@ -106,6 +106,35 @@ def test_packed_pair_simplex_kernel_detune_and_odd_parameters(nz, fbm_path):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), noise_type
 
 
+def test_gpu_chain_matches_readme_screenshots(nz):
+    """The CUDA path against the reference's own rendered output (tests/test_screenshot_pins.py explains the fixture):
+    README example #1 at the inspector panel's parameters, through the stage API."""
+    import os
+    from scipy.stats import spearmanr
+    shots = np.load(os.path.join(os.path.dirname(__file__), "golden", "readme_screenshots.npz"))
+    res = 1000
+    data = np.zeros(res * res, np.float32)
+
+    def view(a):
+        return np.fliplr(a.reshape(250, 4, 250, 4).mean(axis=(1, 3)))
+
+    def rho(a, img):
+        return float(spearmanr(a.ravel(), np.asarray(img, np.float32).ravel()).correlation)
+
+    nz.BasePipeline([nz.NoiseStage(nz.FractalNoise.Simplex, hurst=0.422, octaves=13, noiseSize=1757)]).Run(
+        nz.GeneratorData("shot3", data, res, 0, 424))
+    assert rho(view(data.reshape(res, res)), shots["shot3"].mean(axis=2)) > 0.92
+    nz.BasePipeline([nz.KernelFilterStage(nz.KernelFilterType.Gauss5_S1, iterations=17), nz.ErosionFilterStage(iterations=5)]).Run(
+        nz.GeneratorData("shot5", data, res, 0, 424))
+    assert rho(view(data.reshape(res, res)), shots["shot5"][:, :, 1]) > 0.85
+    nz.BasePipeline([nz.FlowMapStage(iterations=5, normMin=0.0, normMax=0.005)]).Run(nz.GeneratorData("shot5", data, res, 0, 424))
+    assert rho(view(data.reshape(res, res)), shots["shot5"][:, :, 2]) > 0.85
+    cell = np.zeros(res * res, np.float32)
+    nz.BasePipeline([nz.NoiseStage(nz.FractalNoise.Cellular, hurst=1.0, octaves=13, noiseSize=1757)]).Run(
+        nz.GeneratorData("shot0", cell, res, 0, 0))
+    assert rho(view(cell.reshape(res, res)), shots["shot0"].mean(axis=2)) > 0.98
+
+
 @pytest.mark.parametrize("noise_type", range(8))
 def test_every_basis_matches_oracle(nz, oracle, noise_type):
     got = gpu_fractal(nz, 192, noise_type, 1000, 3000)
