@@ -224,9 +224,25 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     constexpr int USE = STRIP - 2 * HALO;
     const char* ez = getenv("NZ_WALK_ZC");
     const char* ep = getenv("NZ_WALK_PFR");
-    const int zc = ez ? atoi(ez) : WALK_ZC;
     const int pfr = ep ? atoi(ep) : 16;
-    dim3 grid(cdiv(cdiv(width, USE), WALK_WARPS), cdiv(rows, zc));
+    const int ctas_x = cdiv(cdiv(width, USE), WALK_WARPS);
+    // Rows per chunk.  A CTA walks its chunk serially (~0.7 us per row), so the launch ends with a tail unless there are
+    // several waves of CTAs: aim for ~8 waves of the resident slots, within [48, 128] rows (shorter chunks pay more
+    // warm-up rows, R*T + 2R + 1 each).  Measured at width 16384: 16384 rows -> 128 (3.28 ms), 4164 -> 48 (1.05 ms vs
+    // 1.13 at 128), 2116 -> 48 (0.64 vs 0.69), 1024 -> 64 (0.40 vs 0.57).
+    int zc = WALK_ZC;
+    if (ez) {
+        zc = atoi(ez);
+    } else {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int slots = sms * 4;                       // 4 CTAs of 128 threads x 128 registers per SM
+        const int chunks = cdiv(8LL * slots, ctas_x);
+        zc = cdiv(rows, chunks < 1 ? 1 : chunks);
+        zc = zc < 48 ? 48 : (zc > WALK_ZC ? WALK_ZC : zc);
+        if (rows <= 1536 && zc < 64) zc = 64;
+    }
+    dim3 grid(ctas_x, cdiv(rows, zc));
 #define NZ_WALK_LAUNCH(SC, PF)                                                                                          \
     do {                                                                                                               \
         const size_t sm = (size_t)WALK_WARPS * PF * STRIP * sizeof(float);                                             \
