@@ -75,6 +75,9 @@ int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width
 bool flow_wave_supported(int width, int rows, int iterations, const void* a, const void* b);
 int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
                          float norm_max, cudaStream_t s);
+bool flow_tile_supported(int width, int rows, int iterations, const void* a, const void* b);
+int32_t launch_flow_tile(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
+                         float norm_max, cudaStream_t s);
 int32_t launch_mesh(int mesh_type, void* d_vtx, uint32_t* d_idx, int R, int inRes, float tile_height,
                     float tile_size, const float* d_heights, int h_row_first, int h_rows, int vz_begin, int vz_end,
                     cudaStream_t s);

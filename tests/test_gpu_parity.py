@@ -285,6 +285,21 @@ def test_flow_wavefront_kernel_equals_per_iteration_kernels_bitwise(nz, oracle, 
     assert np.abs(fused.cpu().numpy() - ref).max() <= TOL_FLOW * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("rows,width,iters", [(700, 600, 5), (300, 1000, 4), (97, 236, 3), (40, 20, 2), (513, 472, 1), (33, 4, 5),
+                                              (1100, 1304, 5)])
+def test_flow_tile_kernel_equals_wavefront_kernel_bitwise(nz, oracle, torch_cuda, monkeypatch, rows, width, iters):
+    """The tile-resident formulation (flowtile_kernels.cu) against the wavefront one, over tile seams, grid borders
+    and partial tiles."""
+    torch = torch_cuda
+    h = torch.from_numpy(oracle.kernel_filter(rand_grid(rows, width), 3, 2) * np.float32(0.05)).cuda()
+    monkeypatch.setenv("NZ_FLOW_PATH", "wave")
+    wave = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    monkeypatch.setenv("NZ_FLOW_PATH", "tile")
+    tile = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(tile, wave)
+
+
 def test_flow_row_band_with_ghost_rows_equals_full_grid_bitwise(nz, oracle, torch_cuda):
     torch = torch_cuda
     n, iters = 640, 5
