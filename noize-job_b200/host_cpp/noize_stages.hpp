@@ -46,6 +46,8 @@ enum class KernelFilterType {
     Sobel3Horizontal, Sobel3Vertical, Sobel3_2D, Prewitt3Horizontal, Prewitt3Vertical
 };
 enum class MeshType { SquareGridHeightMap, OvershootSquareGridHeightMap };
+enum class ConstantOperationType { MULTIPLY, BINARIZE };                          // Filter/ConstantStage.cs:15-18
+enum class ReductionType { SUBTRACT, MULTIPLY, ROOTSUMSQUARES, MAX, MIN };        // Filter/Reduce/ReduceStage.cs:12-18
 
 // ---- job handle: one residency scope shared by the stages of a scheduled chain ----------------------
 class JobHandle {
@@ -86,6 +88,14 @@ struct StageIO {
 };
 struct GeneratorData : StageIO {
     int resolution = 512, xpos = 0, zpos = 0;
+};
+struct ReduceData : StageIO {                   // Pipeline/Stage/StageIOTypes/ReduceData.cs
+    int resolution = 512, xpos = 0, zpos = 0;
+    nz_slice_f32 rightData{nullptr, 4, 0};
+};
+struct DownsampleData : StageIO {               // Pipeline/Stage/StageIOTypes/DownsampleData.cs
+    int resolution = 512, inputResolution = 512;
+    nz_slice_f32 inputData{nullptr, 4, 0};
 };
 struct Mesh {                                   // Mesh.MeshData as PositionStream32.Setup declares it
     std::vector<nz_mesh_vertex> vertices;       // (R+1)^2 x 48 B
@@ -192,6 +202,75 @@ public:
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
         jobHandle = JobHandle::Chain(dependency);
         check(nz_min_erosion(d->data, d->resolution, iterations), "nz_min_erosion");
+    }
+};
+
+// ---- SURVEY section 8f rows ---------------------------------------------------------------------------------
+class StageThermalErosion : public PipelineStage {      // Filter/Kernel/Blur/StageThermalErosion.cs:13-29
+public:
+    int iterations = 1, talus = 45;
+    float increment = 0.5f, meshHeightWidthRatio = 0.75f;
+    void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
+        GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
+        jobHandle = JobHandle::Chain(dependency);
+        check(nz_thermal_erosion(d->data, (float)talus, increment, meshHeightWidthRatio, iterations, d->resolution), "nz_thermal_erosion");
+    }
+};
+
+class ConstantStage : public PipelineStage {            // Filter/ConstantStage.cs:13-60
+public:
+    ConstantOperationType operation = ConstantOperationType::MULTIPLY;
+    float value = 0.5f;
+    void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
+        GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
+        jobHandle = JobHandle::Chain(dependency);
+        check(nz_constant(d->data, nz_slice_f32{nullptr, 0, 0}, (int)operation, value, d->resolution), "nz_constant");
+    }
+};
+
+class ReduceStage : public PipelineStage {              // Filter/Reduce/ReduceStage.cs:21-68
+    GeneratorData transformed;
+
+public:
+    ReductionType operation = ReductionType::SUBTRACT;
+    void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
+        ReduceData* d = CheckRequirements<ReduceData>(requirements);
+        jobHandle = JobHandle::Chain(dependency);
+        check(nz_reduce(d->data, d->rightData, nz_slice_f32{nullptr, 0, 0}, (int)operation, d->resolution), "nz_reduce");
+    }
+    void TransformData(PipelineWorkItem& inputData) override {   // downstream stages see a GeneratorData (:52-61)
+        ReduceData* d = static_cast<ReduceData*>(inputData.data);
+        transformed.uuid = d->uuid; transformed.data = d->data; transformed.resolution = d->resolution;
+        transformed.xpos = d->xpos; transformed.zpos = d->zpos;
+        inputData.data = &transformed;
+    }
+};
+
+class CurveStage : public PipelineStage {               // Filter/Curve/CurveStage.cs:13-73
+    std::vector<float> curve;
+
+public:
+    std::function<float(float)> unityCurve = [](float t) { return t; };   // AnimationCurve.Evaluate
+    int samples = 256;
+    void ResizeNativeContainers(int) override {                           // ExtractCurve, :27-35
+        curve.resize(samples);
+        for (int i = 0; i < samples; i++) curve[i] = unityCurve((float)i / samples);
+    }
+    void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
+        GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
+        jobHandle = JobHandle::Chain(dependency);
+        check(nz_curve(d->data, nz_slice_f32{nullptr, 0, 0}, nz_slice_f32{curve.data(), 4, (int32_t)curve.size()}, d->resolution), "nz_curve");
+    }
+};
+
+class CropStage : public PipelineStage {                // Filter/Sample/CropStage.cs:13-19
+public:
+    bool center = false;   // false: the reference's behaviour (CropJob.Offset is never assigned: top-left corner)
+    void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
+        DownsampleData* d = dynamic_cast<DownsampleData*>(requirements.data);
+        if (!d) throw std::runtime_error("Unhandled stageio");
+        jobHandle = JobHandle::Chain(dependency);
+        check(nz_crop(d->inputData, d->inputResolution, d->data, d->resolution, center ? (d->inputResolution - d->resolution) / 2 : 0), "nz_crop");
     }
 };
 
