@@ -60,12 +60,12 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
     const float flN = fmaxf(0.0f, fN + (H0 - HN));
     const float sum_ = (flW + flE) + (flS + flN);
     const float d = sum_ * TIMESTEP;
-    float K = 0.0f;
-    if (sum_ > 0.0f) {
-        if (w0 >= d) K = 1.0f;
-        else if (w0 > 0.0f) K = fminf(w0 / d, 1.0f);
-    }
+    // one divergent region (the quotient) instead of three nested branches; same values
     const bool pos = sum_ > 0.0f;
+    const bool full = w0 >= d;
+    float K = 0.0f;
+    if (pos && !full && w0 > 0.0f) K = fminf(w0 / d, 1.0f);
+    K = (pos && full) ? 1.0f : K;
     oW = pos ? flW * K : 0.0f;
     oE = pos ? flE * K : 0.0f;
     oS = pos ? flS * K : 0.0f;

@@ -94,12 +94,12 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
     // instructions, and drained cells (w0 == 0) are common, so the two clamped outcomes are decided without
     // dividing: w0 >= d  =>  fl(w0/d) >= 1  => 1 ;  w0 <= 0  =>  quotient <= 0  => 0.  Same bits as the plain form.
     const float d = sum_ * TIMESTEP;
-    float K = 0.0f;
-    if (sum_ > 0.0f) {
-        if (w0 >= d) K = 1.0f;
-        else if (w0 > 0.0f) K = fminf(w0 / d, 1.0f);
-    }
+    // one divergent region (the quotient) instead of three nested branches; same values
     const bool pos = sum_ > 0.0f;
+    const bool full = w0 >= d;
+    float K = 0.0f;
+    if (pos && !full && w0 > 0.0f) K = fminf(w0 / d, 1.0f);
+    K = (pos && full) ? 1.0f : K;
     oW = pos ? flW * K : 0.0f;
     oE = pos ? flE * K : 0.0f;
     oS = pos ? flS * K : 0.0f;
