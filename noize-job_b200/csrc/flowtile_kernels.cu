@@ -72,30 +72,20 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
     oN = pos ? flN * K : 0.0f;
 }
 
-template <int I>
-__global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) {
-    extern __shared__ __align__(16) float sm[];
-    float* const pW = sm;
-    float* const pE = sm + PLANE;
-    float* const pS = sm + 2 * PLANE;
-    float* const pN = sm + 3 * PLANE;
-    float* const pH = sm + 4 * PLANE;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = 4 * lane;
-    const int int_w = TW - 2 * p.hx, int_h = TH - 2 * p.hz;
-
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int bx = tile % p.tiles_x, bz = tile / p.tiles_x;
-        const int x0 = bx * int_w - p.hx, z0 = bz * int_h - p.hz;      // grid coordinates of tile cell (0,0); x0 % 4 == 0
+// One tile.  BORDER = false is the body for tiles that contain no grid border (the great majority): no clamp selects,
+// no load guards.
+template <int I, bool BORDER>
+__device__ __forceinline__ void flow_tile_body(const TileParams& p, float* const pW, float* const pE, float* const pS,
+                                               float* const pN, float* const pH, int warp, int col, int x0, int z0) {
         const int gx = x0 + col;
-        const bool edgeL = gx == 0, edgeR = gx + 3 == p.W - 1;         // my cell 0 / cell 3 lies on the grid's west / east border
+        const bool edgeL = BORDER && gx == 0, edgeR = BORDER && gx + 3 == p.W - 1;   // my cell 0 / cell 3 lies on the grid's west / east border
         float h[FT_G][4], w[FT_G][4];
         __syncthreads();                                               // the previous tile's velocity phase has read the planes
 #pragma unroll
         for (int g = 0; g < FT_G; g++) {
             const int r = warp + FT_WARPS * g, gz = z0 + r;
             float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (gz >= 0 && gz < p.H && gx >= 0 && gx + 3 < p.W) t = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)gz * p.W + gx));
+            if (!BORDER || (gz >= 0 && gz < p.H && gx >= 0 && gx + 3 < p.W)) t = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)gz * p.W + gx));
             h[g][0] = t.x; h[g][1] = t.y; h[g][2] = t.z; h[g][3] = t.w;
             F4 H0;
 #pragma unroll
@@ -119,8 +109,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) 
                 for (int q = 0; q < 4; q++) H0.v[q] = w[g][q] + h[g][q];
                 HS = lds4(pH + max(r - 1, 0) * TW + col);
                 HN = lds4(pH + min(r + 1, TH - 1) * TW + col);
-                if (gz == 0) HS = H0;
-                if (gz == p.H - 1) HN = H0;
+                if (BORDER && gz == 0) HS = H0;
+                if (BORDER && gz == p.H - 1) HN = H0;
                 if (t == 0) {
 #pragma unroll
                     for (int q = 0; q < 4; q++) fW.v[q] = fE.v[q] = fS.v[q] = fN.v[q] = 0.0f;
@@ -145,8 +135,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) 
                 const int o = r * TW + col;
                 const F4 fW = lds4(pW + o), fE = lds4(pE + o), fS = lds4(pS + o), fN = lds4(pN + o);
                 F4 fN_s = lds4(pN + max(r - 1, 0) * TW + col), fS_n = lds4(pS + min(r + 1, TH - 1) * TW + col);
-                if (gz == 0) fN_s = fN;
-                if (gz == p.H - 1) fS_n = fS;
+                if (BORDER && gz == 0) fN_s = fN;
+                if (BORDER && gz == p.H - 1) fS_n = fS;
                 float fE_l = __shfl_up_sync(0xffffffffu, fE.v[3], 1), fW_r = __shfl_down_sync(0xffffffffu, fW.v[0], 1);
                 if (edgeL) fE_l = fE.v[0];
                 if (edgeR) fW_r = fW.v[3];
@@ -167,12 +157,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) 
 #pragma unroll
         for (int g = 0; g < FT_G; g++) {
             const int r = warp + FT_WARPS * g, gz = z0 + r;
-            if (r < p.hz || r >= TH - p.hz || gz >= p.H) continue;          // warp-uniform
+            if (r < p.hz || r >= TH - p.hz || (BORDER && gz >= p.H)) continue;          // warp-uniform
             const int o = r * TW + col;
             const F4 fW = lds4(pW + o), fE = lds4(pE + o), fS = lds4(pS + o), fN = lds4(pN + o);
             F4 fN_s = lds4(pN + (r - 1) * TW + col), fS_n = lds4(pS + (r + 1) * TW + col);
-            if (gz == 0) fN_s = fN;
-            if (gz == p.H - 1) fS_n = fS;
+            if (BORDER && gz == 0) fN_s = fN;
+            if (BORDER && gz == p.H - 1) fS_n = fS;
             float fE_l = __shfl_up_sync(0xffffffffu, fE.v[3], 1), fW_r = __shfl_down_sync(0xffffffffu, fW.v[0], 1);
             if (edgeL) fE_l = fE.v[0];
             if (edgeR) fW_r = fW.v[3];
@@ -189,9 +179,32 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) 
                 const float tt = v - p.nmin;
                 res.v[q] = (tt == 0.0f && p.zero_ok) ? tt * p.nsign : tt / p.nrange;
             }
-            if (col >= p.hx && col < TW - p.hx && gx >= 0 && gx + 3 < p.W)
+            if (col >= p.hx && col < TW - p.hx && (!BORDER || (gx >= 0 && gx + 3 < p.W)))
                 *reinterpret_cast<float4*>(p.out + (size_t)gz * p.W + gx) = make_float4(res.v[0], res.v[1], res.v[2], res.v[3]);
         }
+}
+
+template <int I>
+__global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* const pW = sm;
+    float* const pE = sm + PLANE;
+    float* const pS = sm + 2 * PLANE;
+    float* const pN = sm + 3 * PLANE;
+    float* const pH = sm + 4 * PLANE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = 4 * lane;
+    const int int_w = TW - 2 * p.hx, int_h = TH - 2 * p.hz;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int bx = tile % p.tiles_x, bz = tile / p.tiles_x;
+        const int x0 = bx * int_w - p.hx, z0 = bz * int_h - p.hz;      // grid coordinates of tile cell (0,0); x0 % 4 == 0
+        // the tile's cells lie strictly inside the grid: no cell has a missing neighbour
+        const bool inside = x0 > 0 && z0 > 0 && x0 + TW < p.W && z0 + TH < p.H;
+        if (inside)
+            flow_tile_body<I, false>(p, pW, pE, pS, pN, pH, warp, col, x0, z0);
+        else
+            flow_tile_body<I, true>(p, pW, pE, pS, pN, pH, warp, col, x0, z0);
     }
 }
 
