@@ -205,10 +205,14 @@ int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int k
     NZ_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= NZ_MAX_KERNEL_WIDTH, "separable: ksize %d must be odd and <= %d",
                ksize, NZ_MAX_KERNEL_WIDTH);
     NZ_REQUIRE(iterations >= 0 && kx && kz, "separable: bad iterations/taps");
-    // NZ_SEP_PATH=fused|generic forces the older paths (the tests compare all three bit for bit)
+    // NZ_SEP_PATH=walk|fused|generic forces one path (the tests compare all three bit for bit)
     const char* force = getenv("NZ_SEP_PATH");
     const bool want_generic = force && force[0] == 'g', want_fused = force && force[0] == 'f';
-    if (!want_generic && !want_fused && iterations > 0 && separable_walk_supported(width, ksize, d_data, d_tmp))
+    // The register walk streams long columns per warp and needs ~10^7 cells to fill the GPU; below that the
+    // shared-memory tile kernel (one CTA per 128 x 96 tile) has the shorter critical path.  Measured Gauss5 x17,
+    // walk / fused ms: 1024^2 0.290 / 0.102, 2048^2 0.264 / 0.166, 4096^2 0.432 / 0.485.  All paths give the same bits.
+    const bool small = (long long)width * rows < (8ll << 20) && separable_fused_supported(ksize) && !(force && force[0] == 'w');
+    if (!want_generic && !want_fused && !small && iterations > 0 && separable_walk_supported(width, ksize, d_data, d_tmp))
         return launch_separable_walk(d_data, d_tmp, width, rows, ksize, kx, kz, factor, iterations, d_result, s);
     if (!want_generic && separable_fused_supported(ksize) && iterations > 0)
         return launch_separable_fused(d_data, d_tmp, width, rows, ksize, kx, kz, factor, iterations, d_result, s);

@@ -465,6 +465,7 @@ def test_separable_paths_agree_bitwise(nz, torch_cuda, monkeypatch, rows, width,
     chunk and grid borders."""
     torch = torch_cuda
     a = torch.from_numpy(rand_grid(rows, width)).cuda()
+    monkeypatch.setenv("NZ_SEP_PATH", "walk")      # small grids default to the tile kernel: force the walk
     walk = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
     monkeypatch.setenv("NZ_SEP_PATH", "fused")
     fused = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()

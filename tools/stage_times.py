@@ -33,7 +33,7 @@ def main():
     scratch = torch.empty(max(16, d.flowmap_scratch_bytes(N, N, 5)), dtype=torch.uint8, device="cuda")
     cells = N * N
     rows = []
-    for nt in (3, 5, 4, 1, 0):
+    for nt in (3, 5, 4, 1, 0, 2, 6, 7):
         ms = timeit(lambda: d.fractal(a, nt, 0.4, octaves=13, noise_size=1700), reps)
         rows.append((f"fbm type {nt} x13", ms, None))
     d.fractal(a, 3, 0.4, octaves=13, noise_size=1700)
