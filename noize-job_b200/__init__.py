@@ -5,6 +5,7 @@
     device   device layer (nz_dev_*): device buffers on a stream, rectangular row bands
     stages   mirror of the reference's PipelineStage classes bound to the host layer
     bands    row-band partition of one large heightmap across the GPUs of a box
+    tiles    tile sharding of a tiled world across the GPUs of a box (independent tiles, several in flight per GPU)
 
 The directory name carries a hyphen; import it as `noize_job_b200` (see /noize_job_b200.py).
 """

@@ -89,3 +89,24 @@ def test_nccl_halo_exchange_bands_equal_single_grid_bitwise(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_nccl_worker, args=(world, port, 512, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok_{r}").exists() for r in range(world))
+
+
+def test_tile_world_on_gpu_matches_oracle_tile_by_tile(nz, oracle):
+    """BASELINE config C4 (reduced): tiles sharded over 2 virtual ranks, 3 tiles in flight per rank on separate streams."""
+    from noize_job_b200 import tiles
+    cfg = tiles.TileWorldConfig(tiles_x=3, tiles_z=3, resolution=256, tile_resolution=250, octaves=6, noise_size=400)
+    seen = {}
+
+    def consume(tx, tz, h, e, v, i):
+        seen[(tx, tz)] = (h.cpu().numpy().copy(), e.cpu().numpy().copy(), v.cpu().numpy().copy(), i.cpu().numpy().view(np.uint32).copy())
+
+    for rank in range(2):
+        tw = tiles.TileWorld(cfg, tiles.TileCudaEngine(3), rank, 2, slots=3)
+        assert tw.run(consume) == len(tw.mine)
+    assert sorted(seen) == sorted(cfg.tiles())
+    for (tx, tz), (h, e, v, i) in seen.items():
+        ref = oracle.kernel_filter(oracle.fractal(256, 256, 4, 0.4, octaves=6, xpos=250 * tx, zpos=250 * tz, noise_size=400), 3, 3)
+        assert np.abs(h - ref).max() <= 1e-6
+        assert np.abs(e - oracle.kernel_filter(ref, 11, 1)).max() <= 2e-6
+        rv, ri = oracle.heightmap_mesh(1, h, cfg.R, 4, cfg.tile_height, cfg.tile_size)
+        assert np.array_equal(i, ri) and np.abs(v - rv).max() <= 1e-5 * cfg.tile_height
