@@ -188,9 +188,15 @@ __device__ __forceinline__ float cnoise2(float Px, float Py, const float2* gtab)
 // ---- psrnoise(float2, float2 per, float rot) --------------------------------------------------
 // The hash arguments are half-integers that can exceed float's exact-product range, so the hashes keep the
 // canonical float-floor form; only the (cos, sin) of the final hash value comes from the table.
-template <int TYPE>
+// FAST (wrapped coordinates are exact half-integers, |px| <= 1061, |py| < 102): both hashes use the round-to-nearest
+// residue.  The inner product (34x+1)x exceeds 2^24 and is rounded, but both residue forms subtract an exact multiple of
+// 289 from the SAME rounded product, so they are congruent; the outer hash argument is then a small exact integer and
+// its centred residue indexes the table directly (no floor, no range check).
+template <int TYPE, bool FAST>
 __device__ __forceinline__ void rgrad2(float px, float py, const float2* rtab, float& gx, float& gy) {
-    const float2 g = table_lookup<TYPE, false>(rtab, permute(permute(px) + py));
+    float2 g;
+    if (FAST) g = rtab[__float2int_rn(permute_centered(permute_centered(px) + py)) + 144];
+    else g = table_lookup<TYPE, false>(rtab, permute(permute(px) + py));
     gx = g.x;
     gy = g.y;
 }
@@ -227,9 +233,9 @@ __device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, f
     float xw0 = fmod_period<FAST>(p0x, perx, ipx), xw1 = fmod_period<FAST>(p1x, perx, ipx), xw2 = fmod_period<FAST>(p2x, perx, ipx);
     float yw0 = fmod_period<FAST>(p0y, pery, ipy), yw1 = fmod_period<FAST>(p1y, pery, ipy), yw2 = fmod_period<FAST>(p2y, pery, ipy);
     float g0x, g0y, g1x, g1y, g2x, g2y;
-    rgrad2<TYPE>(fmaf(0.5f, yw0, xw0), yw0, rtab, g0x, g0y);
-    rgrad2<TYPE>(fmaf(0.5f, yw1, xw1), yw1, rtab, g1x, g1y);
-    rgrad2<TYPE>(fmaf(0.5f, yw2, xw2), yw2, rtab, g2x, g2y);
+    rgrad2<TYPE, FAST>(fmaf(0.5f, yw0, xw0), yw0, rtab, g0x, g0y);
+    rgrad2<TYPE, FAST>(fmaf(0.5f, yw1, xw1), yw1, rtab, g1x, g1y);
+    rgrad2<TYPE, FAST>(fmaf(0.5f, yw2, xw2), yw2, rtab, g2x, g2y);
     float w0 = dot2(g0x, g0y, d0x, d0y), w1 = dot2(g1x, g1y, d1x, d1y), w2 = dot2(g2x, g2y, d2x, d2y);
     float t0 = fmaxf(0.8f - dot2(d0x, d0y, d0x, d0y), 0.0f);
     float t1 = fmaxf(0.8f - dot2(d1x, d1y, d1x, d1y), 0.0f);
