@@ -101,7 +101,9 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
 #pragma unroll
         for (int u = 0; u < KS; u++) {
             const int r0 = base + u;
-            if (r0 <= r_end) {
+            // steady state: no guard, so the KS unrolled steps form one schedulable block (up to KS-1 surplus steps at the
+            // chunk end compute rows that are never stored)
+            if (!BORDER || r0 <= r_end) {
                 float v[VW];
                 if (BORDER) {
 #pragma unroll
