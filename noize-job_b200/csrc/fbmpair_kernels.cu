@@ -336,11 +336,117 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_cellular_pair_kernel(floa
     }
 }
 
+// =====================================================================================================================
+// classic Perlin (cnoise2) fBm, same two techniques.  The four lattice corners hash as permute(permute(Pix + i) + Piy + j):
+// T1[Pix + i] (two adjacent rows, once per thread and octave because the thread's cells share their column) and
+// T2[(T1 + Piy + j) mod 289] = the NORMALISED gradient (gx * norm, gy * norm), one bank-private LDS.64 per corner.
+constexpr int PT_ROWS = 290;
+constexpr int P_OFF_T1 = 0, P_OFF_T2 = PT_ROWS * 128;
+constexpr int PERLIN_SMEM = PT_ROWS * 128 + PT_ROWS * 256;
+
+__device__ void build_perlin_tables() {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < PT_ROWS; r += nwarps) {
+        *reinterpret_cast<uint32_t*>(sm + P_OFF_T1 + r * 128 + lane * 4) =
+            (uint32_t)(permute_int(r - 144) + 144) * 256 + lane * 8 - MAGIC_SHL8;
+        // gradient of hash value p with the operations of gradient_fold() / cnoise2() in noise_kernels.cu
+        const float p = (float)permute_int(r - 144);
+        const float fr = p * 0.024390243902439f;
+        const float g = fmaf(2.0f, fr - floorf(fr), -1.0f);
+        const float gy = fabsf(g) - 0.5f;
+        const float gx = g - ((g + MAGIC) - MAGIC);
+        const float norm = fmaf(-0.85373472095314f, fmaf(gy, gy, gx * gx), 1.79284291400159f);
+        *reinterpret_cast<float2*>(sm + P_OFF_T2 + r * 256 + lane * 8) = make_float2(gx * norm, gy * norm);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float2 lds_g2(uint32_t off) { return *reinterpret_cast<const float2*>(sm + P_OFF_T2 + off); }
+__device__ __forceinline__ float fade1(float t) { return t * t * t * fmaf(t, fmaf(t, 6.0f, -15.0f), 10.0f); }
+__device__ __forceinline__ P pfade(P t) { return pmul(pmul(pmul(t, t), t), pfma(t, pfma(t, bc(6.0f), bc(-15.0f)), bc(10.0f))); }
+
+template <int PAIRS>
+__global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_perlin_pair_kernel(float* __restrict__ dst, FractalParams p, int wshift,
+                                                                         int col_blocks, int n_items) {
+    build_perlin_tables();
+    const int lane = threadIdx.x & 31;
+    uint32_t c1 = P_OFF_T1 + 144 * 128 + lane * 4 - MAGIC_SHL7;
+    asm volatile("" : "+r"(c1));
+    const int tx = threadIdx.x & ((1 << wshift) - 1), ty = threadIdx.x >> wshift;
+    constexpr int CELLS = 2 * PAIRS;
+    const int rows_per_item = CELLS * (PAIR_THREADS >> wshift);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cb = item % col_blocks, rg = item / col_blocks;
+        const int x = (cb << wshift) + tx;
+        const int r0 = rg * rows_per_item + CELLS * ty;
+        const float xi = ((float)x + p.posx) / p.noise_size;
+        P zi[PAIRS], t[PAIRS];
+#pragma unroll
+        for (int q = 0; q < PAIRS; q++) {
+            zi[q].x = ((float)(p.z_first + r0 + 2 * q) + p.posz) / p.noise_size;
+            zi[q].y = ((float)(p.z_first + r0 + 2 * q + 1) + p.posz) / p.noise_size;
+            t[q] = bc(0.0f);
+        }
+        float detune = 0.0f, f = 1.0f, a = p.start_amp;
+        for (int i = 0; i < p.octaves; i++) {
+            // ---- x alone: once per thread ----
+            const float Px = f * xi;
+            const float flx = floorf(Px);
+            const float pfx0 = Px - flx, pfx1 = pfx0 - 1.0f;
+            const float fdx = fade1(pfx0);
+            const float rx = fmaf(-289.0f, fmaf(flx, 1.0f / 289.0f, MAGIC) - MAGIC, flx);
+            const uint32_t a1 = (__float_as_uint(rx + MAGIC) << 7) + c1;          // T1 row of Pix
+            const uint32_t t1a = lds_u32(a1), t1b = lds_u32(a1 + 128);             // permute(Pix), permute(Pix + 1)
+#pragma unroll
+            for (int q = 0; q < PAIRS; q++) {
+                const P Py = pmul(bc(f), zi[q]);
+                const P fly = pfloor(Py);
+                const P pfy0 = psub(Py, fly), pfy1 = psub(pfy0, bc(1.0f));
+                const P fdy = pfade(pfy0);
+                const P ry = pfma(bc(-289.0f), psub(pfma(fly, bc(1.0f / 289.0f), bc(MAGIC)), bc(MAGIC)), fly);
+                const P by = padd(ry, bc(MAGIC));
+                float n[4][2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t yb = __float_as_uint(e ? by.y : by.x) << 8;
+                    uint32_t ua = yb + t1a, ub = yb + t1b;                         // T2 rows of (x0, y0) and (x1, y0), unwrapped
+                    ua = min(ua, ua - WRAP8);
+                    ub = min(ub, ub - WRAP8);
+                    const float fy0 = e ? pfy0.y : pfy0.x, fy1 = e ? pfy1.y : pfy1.x;
+                    const float2 g0 = lds_g2(ua), g1 = lds_g2(ub), g2 = lds_g2(ua + 256), g3 = lds_g2(ub + 256);
+                    n[0][e] = fmaf(g0.y, fy0, g0.x * pfx0);                        // dot2(g * norm, (fx, fy))
+                    n[1][e] = fmaf(g1.y, fy0, g1.x * pfx1);
+                    n[2][e] = fmaf(g2.y, fy1, g2.x * pfx0);
+                    n[3][e] = fmaf(g3.y, fy1, g3.x * pfx1);
+                }
+                const P n0 = make_float2(n[0][0], n[0][1]), n1 = make_float2(n[1][0], n[1][1]);
+                const P n2 = make_float2(n[2][0], n[2][1]), n3 = make_float2(n[3][0], n[3][1]);
+                const P l01 = pfma(bc(fdx), psub(n1, n0), n0), l23 = pfma(bc(fdx), psub(n3, n2), n2);   // math.lerp
+                const P l = pfma(fdy, psub(l23, l01), l01);
+                // Rectify(2.3 * l) = (1 + 2.3 l) / 2.  The sum is written fma(product, 1, 1) — with the constant first ptxas
+                // folds 1*1 and then contracts the multiply into the add, which changes the rounding
+                const P basis = pmul(padd(pmul(bc(2.3f), l), bc(1.0f)), bc(0.5f));
+                t[q] = pfma(bc(a), basis, t[q]);
+            }
+            detune += p.detune_rate;
+            f *= (p.stepdown - detune);
+            a *= p.G;
+        }
+        if (x < p.width) {
+#pragma unroll
+            for (int q = 0; q < PAIRS; q++) {
+                const int r = r0 + 2 * q;
+                if (r < p.rows) dst[(size_t)r * p.width + x] = t[q].x / p.norm;
+                if (r + 1 < p.rows) dst[(size_t)(r + 1) * p.width + x] = t[q].y / p.norm;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 bool fractal_pair_supported(int noise_type, const FractalParams& p) {
-    return (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR) && p.fast_hash && p.width >= 32 &&
-           (long long)p.width * p.rows >= (1 << 19);
+    return (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR || noise_type == NZ_NOISE_PERLIN) && p.fast_hash &&
+           p.width >= 32 && (long long)p.width * p.rows >= (1 << 19);
 }
 
 int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s) {
@@ -355,6 +461,7 @@ int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p
         NZ_CUDA(cudaFuncSetAttribute(fbm_simplex_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(fbm_perlin_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PERLIN_SMEM));
         configured = true;
     }
     int wshift = 5;
@@ -370,7 +477,9 @@ int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p
     const long long n_items = (long long)col_blocks * cdiv(p.rows, rows_per_item);
     NZ_REQUIRE(n_items < (1ll << 31), "nz_fractal: window too large");
     const int grid = n_items < sms ? (int)n_items : sms;
-    if (noise_type == NZ_NOISE_CELLULAR) {
+    if (noise_type == NZ_NOISE_PERLIN) {
+        fbm_perlin_pair_kernel<2><<<grid, PAIR_THREADS, PERLIN_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
+    } else if (noise_type == NZ_NOISE_CELLULAR) {
         if (cells == 2)
             fbm_cellular_pair_kernel<1><<<grid, PAIR_THREADS, CELL_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
         else

@@ -83,21 +83,22 @@ def test_packed_pair_simplex_kernel_is_bit_identical_to_the_scalar_kernel(nz, or
 
 
 @pytest.mark.parametrize("res,pos", [(96, (0, 0)), (300, (-5000, 7777)), (1031, (100000, 3)), (2048, (14336, 14336))])
-def test_packed_pair_cellular_kernel_is_bit_identical_to_the_scalar_kernel(nz, oracle, fbm_path, res, pos):
+@pytest.mark.parametrize("noise_type", [5, 1])
+def test_packed_pair_cellular_and_perlin_kernels_are_bit_identical_to_the_scalar_kernel(nz, oracle, fbm_path, res, pos, noise_type):
     fbm_path("scalar")
-    a = gpu_fractal(nz, res, 5, *pos)
+    a = gpu_fractal(nz, res, noise_type, *pos)
     fbm_path("pair")
-    b = gpu_fractal(nz, res, 5, *pos)
+    b = gpu_fractal(nz, res, noise_type, *pos)
     fbm_path(None)
     assert np.isfinite(a).all()
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     if res <= 300:
-        assert np.abs(b - ref_fractal(oracle, res, 5, *pos)).max() <= TOL_NOISE
+        assert np.abs(b - ref_fractal(oracle, res, noise_type, *pos)).max() <= TOL_NOISE
 
 
 def test_packed_pair_simplex_kernel_detune_and_odd_parameters(nz, fbm_path):
     kw = dict(hurst=0.9001, octaves=6, noise_size=7475, stepdown=2.17, detune_rate=0.013, starting_amplitude=0.7)
-    for noise_type in (3, 5):
+    for noise_type in (3, 5, 1):
         fbm_path("scalar")
         a = gpu_fractal(nz, 777, noise_type, 12345, -999, **kw)
         fbm_path("pair")
