@@ -1,0 +1,44 @@
+"""Small invocation of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+Sizes are chosen to hit strip / chunk / tile seams and both border and interior code paths while staying sanitizer-sized."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import noize_job_b200 as nz  # noqa: E402
+
+d = nz.device
+n = 768
+a = torch.empty(n, n, device="cuda"); b = torch.empty_like(a)
+for nt in range(8):
+    d.fractal(a, nt, 0.4, octaves=3, noise_size=170)
+os.environ["NZ_FBM_PATH"] = "pair"
+for nt in (3, 5, 1):
+    d.fractal(a, nt, 0.4, octaves=3, noise_size=170)
+os.environ.pop("NZ_FBM_PATH")
+for path in ("walk", "fused", "generic"):
+    os.environ["NZ_SEP_PATH"] = path
+    d.kernel_filter(a, b, 2, 5)
+os.environ.pop("NZ_SEP_PATH")
+d.kernel_filter(a, b, 11, 1)
+for path, it in (("wave", 5), ("tile", 5), ("tile", 2), ("wave", 1)):
+    os.environ["NZ_FLOW_PATH"] = path
+    d.flowmap(a.clone(), b, None, it, 0.0, 0.005)
+os.environ.pop("NZ_FLOW_PATH")
+os.environ["NZ_FLOW_UNFUSED"] = "1"
+d.flowmap(a.clone(), b, torch.empty(5 * n * n * 4, dtype=torch.uint8, device="cuda"), 2, 0.0, 0.005)
+os.environ.pop("NZ_FLOW_UNFUSED")
+d.min_erosion(a, b, 5)
+d.thermal_erosion(a, 45.0, 0.5, 0.75, 2)
+d.constant(a, 0, 0.5); d.reduce(a, b, 3); d.curve(a, torch.linspace(0, 1, 64, device="cuda")); d.normalize(a, 0.1, 0.5)
+print(d.map_range(a).cpu().numpy())
+c = torch.empty(300, 300, device="cuda"); d.crop(a, c, 100)
+R = n - 8
+v = torch.empty((R + 1) * (R + 1), 12, device="cuda"); i = torch.empty(6 * R * R, dtype=torch.int32, device="cuda")
+for mt in (0, 1):
+    d.heightmap_mesh(mt, v, i, R, n, 4, 2000.0, 1500.0, b)
+torch.cuda.synchronize()
+print("sanitize_run ok")
