@@ -362,6 +362,8 @@ static int32_t fractal_params(FractalParams* p, int width, int rows, int z_first
         const double cx = fabs((double)xpos) + width, cz = fabs((double)zpos) + fabs((double)z_first) + rows;
         const double vmax = fmax * (cx > cz ? cx : cz) / fabs((double)noise_size);
         p->fast_hash = (1.74 * vmax + 2.0) < 2097152.0;   // also false for NaN/inf parameters
+        // domain-rotated bases: |xr|, |zr| <= 1.42 vmax, |yr| <= 1.16 vmax, simplex skew adds (xr+yr+zr)/3: below 3 vmax
+        p->fast_hash3d = (3.0 * vmax + 2.0) < 2097152.0;
     }
     return NZ_OK;
 }

@@ -286,7 +286,25 @@ __device__ __forceinline__ float cellular2_rectified(float Px, float Py, const f
 }
 
 // ---- snoise(float3) ---------------------------------------------------------------------------
-__device__ float snoise3(float vx, float vy, float vz) {
+// The normalised corner gradient is a pure function of the final hash value p in [0,288]; simplex3_gradient() is the
+// straight-line code (it costs 5 floors per corner).  FAST (host-checked lattice range): the kernel evaluates it once
+// per CTA into a 289-entry float4 table and every hash of the chain keeps a centred residue (no floor), as in 2-D.
+__device__ __forceinline__ float4 simplex3_gradient(float p) {
+    const float n_ = 0.142857142857f;
+    const float nsx = n_ * 2.0f - 0.0f, nsy = n_ * 0.5f - 1.0f, nsz = n_ * 1.0f - 0.0f;
+    float j = fmaf(-49.0f, floorf(p * nsz * nsz), p);
+    float x_ = floorf(j * nsz);
+    float y_ = floorf(fmaf(-7.0f, x_, j));
+    float X = fmaf(x_, nsx, nsy), Y = fmaf(y_, nsx, nsy);
+    float H = 1.0f - fabsf(X) - fabsf(Y);
+    float sh = -stepf_(H, 0.0f);
+    float sx = fmaf(floorf(X), 2.0f, 1.0f), sy = fmaf(floorf(Y), 2.0f, 1.0f);
+    float Px = fmaf(sx, sh, X), Py = fmaf(sy, sh, Y), Pz = H;
+    float norm = taylorInvSqrt(dot3(Px, Py, Pz, Px, Py, Pz));
+    return make_float4(Px * norm, Py * norm, Pz * norm, 0.0f);
+}
+template <bool FAST>
+__device__ float snoise3(float vx, float vy, float vz, const float4* gtab3) {
     const float Cx = 1.0f / 6.0f, Cy = 1.0f / 3.0f;
     float s = dot3(vx, vy, vz, Cy, Cy, Cy);
     float i0 = floorf(vx + s), i1_ = floorf(vy + s), i2_ = floorf(vz + s);
@@ -304,41 +322,43 @@ __device__ float snoise3(float vx, float vy, float vz) {
         xs[2][k] = x0[k] - i2[k] + Cy;
         xs[3][k] = x0[k] - 0.5f;
     }
-    float ii[3] = {mod289(i0), mod289(i1_), mod289(i2_)};
+    float ii[3] = {lattice_residue<FAST>(i0), lattice_residue<FAST>(i1_), lattice_residue<FAST>(i2_)};
     const float oz[4] = {0.0f, i1[2], i2[2], 1.0f}, oy[4] = {0.0f, i1[1], i2[1], 1.0f}, ox[4] = {0.0f, i1[0], i2[0], 1.0f};
-    const float n_ = 0.142857142857f;
-    const float nsx = n_ * 2.0f - 0.0f, nsy = n_ * 0.5f - 1.0f, nsz = n_ * 1.0f - 0.0f;
     float m[4], pd[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        float p = permute(permute(permute(ii[2] + oz[k]) + ii[1] + oy[k]) + ii[0] + ox[k]);
-        float j = fmaf(-49.0f, floorf(p * nsz * nsz), p);
-        float x_ = floorf(j * nsz);
-        float y_ = floorf(fmaf(-7.0f, x_, j));
-        float X = fmaf(x_, nsx, nsy), Y = fmaf(y_, nsx, nsy);
-        float H = 1.0f - fabsf(X) - fabsf(Y);
-        float sh = -stepf_(H, 0.0f);
-        float sx = fmaf(floorf(X), 2.0f, 1.0f), sy = fmaf(floorf(Y), 2.0f, 1.0f);
-        float Px = fmaf(sx, sh, X), Py = fmaf(sy, sh, Y), Pz = H;
-        float norm = taylorInvSqrt(dot3(Px, Py, Pz, Px, Py, Pz));
-        Px *= norm; Py *= norm; Pz *= norm;
+        float p = hash_last<FAST>(hash_inner<FAST>(hash_inner<FAST>(ii[2] + oz[k]) + ii[1] + oy[k]) + ii[0] + ox[k]);
+        const float4 G = FAST ? gtab3[__float2int_rn(p) + 144] : simplex3_gradient(p);
         float mm = fmaxf(0.6f - dot3(xs[k][0], xs[k][1], xs[k][2], xs[k][0], xs[k][1], xs[k][2]), 0.0f);
         mm = mm * mm;
         m[k] = mm * mm;
-        pd[k] = dot3(Px, Py, Pz, xs[k][0], xs[k][1], xs[k][2]);
+        pd[k] = dot3(G.x, G.y, G.z, xs[k][0], xs[k][1], xs[k][2]);
     }
     return 42.0f * dot4(m[0], m[1], m[2], m[3], pd[0], pd[1], pd[2], pd[3]);
 }
 
 // ---- cnoise(float3) ---------------------------------------------------------------------------
-__device__ float cnoise3(float Px, float Py, float Pz) {
+// Same scheme: the normalised gradient of a corner is a pure function of its final hash value.
+__device__ __forceinline__ float4 perlin3_gradient(float ixyz) {
+    float gx = ixyz * (1.0f / 7.0f);
+    float gy = fracf_(floorf(gx) * (1.0f / 7.0f)) - 0.5f;
+    gx = fracf_(gx);
+    float gz = 0.5f - fabsf(gx) - fabsf(gy);
+    float sz = stepf_(gz, 0.0f);
+    gx = gx - sz * (stepf_(0.0f, gx) - 0.5f);
+    gy = gy - sz * (stepf_(0.0f, gy) - 0.5f);
+    float norm = taylorInvSqrt(dot3(gx, gy, gz, gx, gy, gz));
+    return make_float4(gx * norm, gy * norm, gz * norm, 0.0f);
+}
+template <bool FAST>
+__device__ float cnoise3(float Px, float Py, float Pz, const float4* gtab3) {
     float P[3] = {Px, Py, Pz};
     float Pi0[3], Pi1[3], Pf0[3], Pf1[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         float fl = floorf(P[k]);
-        Pi0[k] = mod289(fl);
-        Pi1[k] = mod289(fl + 1.0f);
+        Pi0[k] = lattice_residue<FAST>(fl);
+        Pi1[k] = lattice_residue<FAST>(fl + 1.0f);
         Pf0[k] = P[k] - fl;
         Pf1[k] = Pf0[k] - 1.0f;
     }
@@ -346,20 +366,13 @@ __device__ float cnoise3(float Px, float Py, float Pz) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         float ix = (k & 1) ? Pi1[0] : Pi0[0], iy = (k >> 1) ? Pi1[1] : Pi0[1];
-        float ixy = permute(permute(ix) + iy);
+        float ixy = hash_inner<FAST>(hash_inner<FAST>(ix) + iy);
 #pragma unroll
         for (int sl = 0; sl < 2; sl++) {
-            float ixyz = permute(ixy + (sl ? Pi1[2] : Pi0[2]));
-            float gx = ixyz * (1.0f / 7.0f);
-            float gy = fracf_(floorf(gx) * (1.0f / 7.0f)) - 0.5f;
-            gx = fracf_(gx);
-            float gz = 0.5f - fabsf(gx) - fabsf(gy);
-            float sz = stepf_(gz, 0.0f);
-            gx = gx - sz * (stepf_(0.0f, gx) - 0.5f);
-            gy = gy - sz * (stepf_(0.0f, gy) - 0.5f);
-            float norm = taylorInvSqrt(dot3(gx, gy, gz, gx, gy, gz));
+            float ixyz = hash_last<FAST>(ixy + (sl ? Pi1[2] : Pi0[2]));
+            const float4 G = FAST ? gtab3[__float2int_rn(ixyz) + 144] : perlin3_gradient(ixyz);
             float fx = (k & 1) ? Pf1[0] : Pf0[0], fy = (k >> 1) ? Pf1[1] : Pf0[1], fz = sl ? Pf1[2] : Pf0[2];
-            n[sl][k] = dot3(gx * norm, gy * norm, gz * norm, fx, fy, fz);
+            n[sl][k] = dot3(G.x, G.y, G.z, fx, fy, fz);
         }
     }
     float fdx = fade(Pf0[0]), fdy = fade(Pf0[1]), fdz = fade(Pf0[2]);
@@ -370,7 +383,7 @@ __device__ float cnoise3(float Px, float Py, float Pz) {
 
 // ---- basis getters, Fractal.cs:141-278 ----------------------------------------------------------
 template <int TYPE, bool FAST>
-__device__ __forceinline__ float basis_value(float x, float z, const float2* gtab) {
+__device__ __forceinline__ float basis_value(float x, float z, const float2* gtab, const float4* gtab3) {
     if (TYPE == NZ_NOISE_SIN) {
         float vx = fmaf(0.5f, sinf(x), 0.5f), vz = fmaf(0.5f, sinf(z), 0.5f);
         return vx * vz;
@@ -389,7 +402,7 @@ __device__ __forceinline__ float basis_value(float x, float z, const float2* gta
         float s2 = xz * -0.211324865405187f;
         float xr = x + s2, zr = z + s2;
         float yr = xz * -0.577350269189626f;
-        return rectify(TYPE == NZ_NOISE_DOMAIN_ROTATED_PERLIN ? cnoise3(xr, zr, yr) : snoise3(xr, zr, yr));
+        return rectify(TYPE == NZ_NOISE_DOMAIN_ROTATED_PERLIN ? cnoise3<FAST>(xr, zr, yr, gtab3) : snoise3<FAST>(xr, zr, yr, gtab3));
     }
 }
 
@@ -400,6 +413,16 @@ template <int TYPE, int CELLS, bool FAST>
 __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__ dst, FractalParams p) {
     __shared__ float2 gtab[uses_table<TYPE>() ? NZ_TAB : 1];
     if (uses_table<TYPE>()) build_table<TYPE>(gtab);
+    constexpr bool TAB3 = FAST && (TYPE == NZ_NOISE_DOMAIN_ROTATED_PERLIN || TYPE == NZ_NOISE_DOMAIN_ROTATED_SIMPLEX);
+    __shared__ float4 gtab3[TAB3 ? NZ_TAB : 1];
+    if (TAB3) {
+        for (int i = threadIdx.x; i < NZ_TAB; i += blockDim.x) {
+            const int c = i - 144;
+            const float pv = (float)(c < 0 ? c + 289 : c);
+            gtab3[i] = TYPE == NZ_NOISE_DOMAIN_ROTATED_PERLIN ? perlin3_gradient(pv) : simplex3_gradient(pv);
+        }
+        __syncthreads();
+    }
     const int r = blockIdx.y;
     const int xbase = blockIdx.x * (NZ_FBM_THREADS * CELLS) + threadIdx.x;
     const float zi = ((float)(p.z_first + r) + p.posz) / p.noise_size;
@@ -413,7 +436,7 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
     for (int i = 0; i < p.octaves; i++) {
         const float zV = f * zi;
 #pragma unroll
-        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE, FAST>(f * xi[c], zV, gtab), t[c]);
+        for (int c = 0; c < CELLS; c++) t[c] = fmaf(a, basis_value<TYPE, FAST>(f * xi[c], zV, gtab, gtab3), t[c]);
         detune += p.detune_rate;
         f *= (p.stepdown - detune);
         a *= p.G;
@@ -429,8 +452,9 @@ __global__ void __launch_bounds__(NZ_FBM_THREADS) fbm_kernel(float* __restrict__
 template <int TYPE, int CELLS>
 int32_t launch_typed(float* d_dst, const FractalParams& p, cudaStream_t s) {
     dim3 grid(cdiv(p.width, NZ_FBM_THREADS * CELLS), p.rows);
+    const bool is3d = TYPE == NZ_NOISE_DOMAIN_ROTATED_PERLIN || TYPE == NZ_NOISE_DOMAIN_ROTATED_SIMPLEX;
     if ((TYPE == NZ_NOISE_SIMPLEX || TYPE == NZ_NOISE_PERLIN || TYPE == NZ_NOISE_CELLULAR || TYPE == NZ_NOISE_PERIODIC_PERLIN ||
-         TYPE == NZ_NOISE_ROTATED_SIMPLEX) && p.fast_hash)
+         TYPE == NZ_NOISE_ROTATED_SIMPLEX || is3d) && (is3d ? p.fast_hash3d : p.fast_hash))
         fbm_kernel<TYPE, CELLS, true><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);
     else
         fbm_kernel<TYPE, CELLS, false><<<grid, NZ_FBM_THREADS, 0, s>>>(d_dst, p);

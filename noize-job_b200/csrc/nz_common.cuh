@@ -52,6 +52,7 @@ struct FractalParams {
     float G;     // exp2f(-hurst), computed on the host with the same libm call the oracle uses
     float norm;  // CalcFractalNormValue
     int fast_hash;  // every lattice index of this launch is below 2^21 (simplex may use the magic-number residue)
+    int fast_hash3d;  // the same for the domain-rotated 3-D bases (their rotated / skewed coordinates are up to 3x larger)
 };
 int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
 bool fractal_pair_supported(int noise_type, const FractalParams& p);

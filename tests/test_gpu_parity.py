@@ -143,7 +143,7 @@ def test_every_basis_matches_oracle(nz, oracle, noise_type):
     assert np.abs(got - ref).max() <= TOL_NOISE
 
 
-@pytest.mark.parametrize("noise_type", [3, 5, 4, 1, 2])
+@pytest.mark.parametrize("noise_type", [3, 5, 4, 1, 2, 6, 7])
 def test_noise_far_from_origin_c5_coordinates(nz, oracle, noise_type):
     # the last 160 rows/cols of the 16384^2 grid: lattice coordinates up to 4096*16384/1700
     got = gpu_fractal(nz, 160, noise_type, 16384 - 160, 16384 - 160)
@@ -451,7 +451,7 @@ def test_kernels_actually_launch(nz):
     assert t["kernel_launches"] == 1 and t["ms_kernel"] > 0
 
 
-@pytest.mark.parametrize("noise_type", [3, 1, 5])
+@pytest.mark.parametrize("noise_type", [3, 1, 5, 6, 7])
 def test_beyond_the_fast_hash_domain_the_exact_residue_is_used(nz, oracle, noise_type):
     # lattice indices above 2^21 switch the kernels to the float-floor mod289 (same as the oracle)
     got = gpu_fractal(nz, 64, noise_type, 30000, 30000, octaves=24, noise_size=5, stepdown=2.2)
