@@ -315,6 +315,15 @@ def run_ours(args):
                 "flop_per_cell": FLOP_PER_CELL_SIMPLEX13, "cells_per_launch": own_cells, "ms_per_launch": round(own_noise_ms, 4),
                 "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src}
 
+    # the dominant HBM-bound kernel (mesh_kernel: one launch per step) in the same shape as `roofline`
+    mesh_ms = sum(evs[k][4].elapsed_time(evs[k][5]) for k in range(args.steps)) / args.steps
+    nvr = chain.vz1 - chain.vz0
+    mesh_bytes = 4 * (nvr + 2) * N + 48 * nvr * (R + 1) + 24 * R * max(chain.vz1 - max(chain.vz0, 1), 0)
+    roofline_hbm = {"kernel": "mesh_kernel", "bound": "hbm", "achieved": round(mesh_bytes / mesh_ms / 1e6, 1), "peak": hbm_peak,
+                    "unit": "GB/s", "frac": round(mesh_bytes / mesh_ms / 1e6 / hbm_peak, 4),
+                    "traffic": stage_traffic.get("mesh") if (N == N_GRID and world == 1) else None,
+                    "bytes_per_launch": int(mesh_bytes), "ms_per_launch": round(mesh_ms, 4), "peak_source": hbm_src}
+
     cpu = None
     if not args.no_cpu and world == 1:
         r = cpu_reference(1, 1)
@@ -329,7 +338,7 @@ def run_ours(args):
         "config": {"workload": f"BASELINE.json configs[4]: one {N}^2 heightmap in {world} row band(s), full chain, mode={args.mode}",
                    "l2": "every field is 1 GiB (> 126 MB L2): inputs larger than L2, no flush needed",
                    "parallelism": f"row bands x{world}, halo {'exchange over NCCL' if args.mode == 'exchange' else 'recompute'}"},
-        "stages": stages, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "stages": stages, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "halo_bytes_per_step": int(chain.bytes_exchanged // max(1, args.steps + args.warmup)),
         "clocks": sampler.report() if sampler else None,
     }
