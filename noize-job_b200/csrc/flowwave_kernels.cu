@@ -106,6 +106,36 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
     oN = pos ? flN * K : 0.0f;
 }
 
+// The two columns of a lane as one f32x2 pair (sm_100 FADD2 / FMUL2: one issue slot, two IEEE operations — the same
+// bits as flow_cell() on each column).  Only max, the comparisons and the rare quotient stay scalar.  The pair
+// (west neighbours) = (HWl, H0.x) and (east neighbours) = (H0.y, HEr) are the only operands that need assembling.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 max0(float2 a) { return make_float2(fmaxf(0.0f, a.x), fmaxf(0.0f, a.y)); }
+__device__ __forceinline__ float quot_k(float sum_, float d, float w0) {
+    const bool pos = sum_ > 0.0f;
+    const bool full = w0 >= d;
+    float K = 0.0f;
+    if (pos && !full && w0 > 0.0f) K = fminf(w0 / d, 1.0f);
+    return (pos && full) ? 1.0f : K;
+}
+__device__ __forceinline__ void flow_cell2(float2 H0, float HWl, float HEr, float2 HS, float2 HN, float2 w0, float2 fW, float2 fE,
+                                           float2 fS, float2 fN, float2& oW, float2& oE, float2& oS, float2& oN) {
+    const float2 flW = max0(__fadd2_rn(fW, sub2(H0, f2(HWl, H0.x))));
+    const float2 flE = max0(__fadd2_rn(fE, sub2(H0, f2(H0.y, HEr))));
+    const float2 flS = max0(__fadd2_rn(fS, sub2(H0, HS)));
+    const float2 flN = max0(__fadd2_rn(fN, sub2(H0, HN)));
+    const float2 sum_ = __fadd2_rn(__fadd2_rn(flW, flE), __fadd2_rn(flS, flN));
+    const float2 d = __fmul2_rn(sum_, f2(TIMESTEP, TIMESTEP));
+    const float2 K = f2(quot_k(sum_.x, d.x, w0.x), quot_k(sum_.y, d.y, w0.y));
+    const bool p0 = sum_.x > 0.0f, p1 = sum_.y > 0.0f;
+    const float2 a = __fmul2_rn(flW, K), b = __fmul2_rn(flE, K), c = __fmul2_rn(flS, K), e = __fmul2_rn(flN, K);
+    oW = f2(p0 ? a.x : 0.0f, p1 ? a.y : 0.0f);
+    oE = f2(p0 ? b.x : 0.0f, p1 ? b.y : 0.0f);
+    oS = f2(p0 ? c.x : 0.0f, p1 ? c.y : 0.0f);
+    oN = f2(p0 ? e.x : 0.0f, p1 ? e.y : 0.0f);
+}
+
 // ---- shared-memory rings -------------------------------------------------------------------------------
 // Every ring holds RING = 5 rows of FLW floats; ring q starts at float offset q*RING*FLW.
 //   F(t,k)  t=1..I, k=W,E,S,N   outflows of level t
@@ -169,10 +199,14 @@ __device__ __forceinline__ void stage_outflow(const Lane& L, int s, int zc0, int
         fS = ld4<RG::F(P, 2)>(o0); fN = ld4<RG::F(P, 3)>(o0);
     }
     V4 oW, oE, oS, oN;
-#pragma unroll
-    for (int q = 0; q < VW; q++)
-        flow_cell(H0.v[q], q == 0 ? HWl : H0.v[q > 0 ? q - 1 : 0], q == VW - 1 ? HEr : H0.v[q < VW - 1 ? q + 1 : 0], HS.v[q],
-                  HN.v[q], w0.v[q], fW.v[q], fE.v[q], fS.v[q], fN.v[q], oW.v[q], oE.v[q], oS.v[q], oN.v[q]);
+    {
+        static_assert(VW == 2, "flow_cell2 pairs the two columns of a lane");
+        float2 pW, pE, pS, pN;
+        flow_cell2(f2(H0.v[0], H0.v[1]), HWl, HEr, f2(HS.v[0], HS.v[1]), f2(HN.v[0], HN.v[1]), f2(w0.v[0], w0.v[1]),
+                   f2(fW.v[0], fW.v[1]), f2(fE.v[0], fE.v[1]), f2(fS.v[0], fS.v[1]), f2(fN.v[0], fN.v[1]), pW, pE, pS, pN);
+        oW.v[0] = pW.x; oW.v[1] = pW.y; oE.v[0] = pE.x; oE.v[1] = pE.y;
+        oS.v[0] = pS.x; oS.v[1] = pS.y; oN.v[0] = pN.x; oN.v[1] = pN.y;
+    }
     st4<RG::F(T, 0)>(o0, oW);
     st4<RG::F(T, 1)>(o0, oE);
     st4<RG::F(T, 2)>(o0, oS);
@@ -195,12 +229,16 @@ __device__ __forceinline__ void stage_water(const Lane& L, int s, int zc0, int z
     const V4 w = (T == 1) ? splat(WATER0) : ld4<RG::Wt(P)>(o0);
     const V4 hh = ld4<RG::HC(T - 1)>(o0);
     V4 nw, nH;
-#pragma unroll
-    for (int q = 0; q < VW; q++) {
-        const float out = ((fW.v[q] + fE.v[q]) + fS.v[q]) + fN.v[q];
-        const float in = (((q == 0 ? fE_l : fE.v[q > 0 ? q - 1 : 0]) + (q == VW - 1 ? fW_r : fW.v[q < VW - 1 ? q + 1 : 0])) + fN_s.v[q]) + fS_n.v[q];
-        nw.v[q] = fmaxf(0.0f, fmaf(in - out, TIMESTEP, w.v[q]));
-        nH.v[q] = nw.v[q] + hh.v[q];
+    {
+        // the lane's two columns as one f32x2 pair (same operations, same order, same bits as the scalar form)
+        const float2 pW = f2(fW.v[0], fW.v[1]), pE = f2(fE.v[0], fE.v[1]);
+        const float2 out = __fadd2_rn(__fadd2_rn(__fadd2_rn(pW, pE), f2(fS.v[0], fS.v[1])), f2(fN.v[0], fN.v[1]));
+        const float2 in = __fadd2_rn(__fadd2_rn(__fadd2_rn(f2(fE_l, fE.v[0]), f2(fW.v[1], fW_r)), f2(fN_s.v[0], fN_s.v[1])),
+                                     f2(fS_n.v[0], fS_n.v[1]));
+        const float2 w2 = max0(__ffma2_rn(sub2(in, out), f2(TIMESTEP, TIMESTEP), f2(w.v[0], w.v[1])));
+        const float2 H2 = __fadd2_rn(w2, f2(hh.v[0], hh.v[1]));
+        nw.v[0] = w2.x; nw.v[1] = w2.y;
+        nH.v[0] = H2.x; nH.v[1] = H2.y;
     }
     st4<RG::Wt(T)>(o0, nw);
     st4<RG::Ht(T)>(o0, nH);
