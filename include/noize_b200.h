@@ -220,6 +220,14 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
 NZ_API int32_t nz_thermal_erosion(nz_slice_f32 src, float talus, float increment_ratio,
                                   float mesh_height_width_ratio, int32_t iterations, int32_t resolution);
 
+/* ErosionStageSubtractiveFlow.Schedule -> ScheduleAll -> ScheduleCycle, Geologic/Stage/ErosionStageSubtractiveFlow.cs:138-245
+ * (the whole stage is commented-out code upstream; this entry follows its text).  Cycle n = 0..erosive_iterations-1:
+ * water := 1e-4, n + 1 x (outflow step, water step) on flow fields that persist across the cycles (zero before the
+ * first), then height -= erosive_factor * (|velocity| - norm_min) / (norm_max - norm_min).  The stage's
+ * `flowIterations` field is never read upstream (:19-20) and has no argument here. */
+NZ_API int32_t nz_subtractive_flow_erosion(nz_slice_f32 height, int32_t resolution, int32_t erosive_iterations,
+                                           float erosive_factor, float norm_min, float norm_max);
+
 /* ConstantJobScheduleDelegate, Filter/ConstantJob.cs:49-55 (operators Operators/SimpleMutation.cs:16-54):
  * MULTIPLY: v * value;  BINARIZE: v >= value ? 1 : 0.  `tmp` is accepted for signature parity, never touched. */
 NZ_API int32_t nz_constant(nz_slice_f32 src, nz_slice_f32 tmp, int32_t operation, float constant_value,
@@ -313,6 +321,11 @@ NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32
                                      int32_t vz_begin, int32_t vz_end, void* stream);
 
 /* Device-layer forms of the section-8f rows (n = number of cells; all in place). */
+/* d_scratch: nz_dev_subtractive_flow_scratch_bytes() bytes (water + 4 flow fields, live for the whole call) */
+NZ_API size_t  nz_dev_subtractive_flow_scratch_bytes(int32_t width, int32_t rows);
+NZ_API int32_t nz_dev_subtractive_flow_erosion(float* d_height, void* d_scratch, int32_t width, int32_t rows,
+                                               int32_t erosive_iterations, float erosive_factor,
+                                               float norm_min, float norm_max, void* stream);
 NZ_API int32_t nz_dev_thermal_erosion(float* d_data, int32_t resolution, float talus, float increment_ratio,
                                       float mesh_height_width_ratio, int32_t iterations, void* stream);
 NZ_API int32_t nz_dev_constant(float* d_data, size_t n, int32_t operation, float constant_value, void* stream);

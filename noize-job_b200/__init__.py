@@ -14,5 +14,5 @@ from .lib import NzError, load, build  # noqa: F401
 from .stages import (FractalNoise, KernelFilterType, GaussSigma, MeshType, JobHandle, StageIO, GeneratorData,  # noqa: F401
                      MeshStageData, Mesh, PipelineWorkItem, PipelineStage, NoiseStage, KernelFilterStage,
                      StageGaussianBlur, StageSmoothBlur, ErosionFilterStage, FlowMapStage, MeshTileStage, BasePipeline,
-                     ConstantOperationType, ReductionType, ReduceData, DownsampleData, StageThermalErosion,
+                     ConstantOperationType, ReductionType, ReduceData, DownsampleData, StageThermalErosion, ErosionStageSubtractiveFlow,
                      ConstantStage, ReduceStage, CurveStage, CropStage)

@@ -538,6 +538,18 @@ NZ_API int32_t nz_dev_thermal_erosion(float* d_data, int32_t resolution, float t
     NZ_REQUIRE(iterations >= 0, "nz_dev_thermal_erosion: iterations %d < 0", iterations);
     return launch_thermal_erosion(d_data, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, (cudaStream_t)stream);
 }
+NZ_API size_t nz_dev_subtractive_flow_scratch_bytes(int32_t width, int32_t rows) {
+    if (width <= 0 || rows <= 0) return 0;
+    return subtractive_flow_scratch_bytes(width, rows);
+}
+NZ_API int32_t nz_dev_subtractive_flow_erosion(float* d_height, void* d_scratch, int32_t width, int32_t rows,
+                                               int32_t erosive_iterations, float erosive_factor, float norm_min,
+                                               float norm_max, void* stream) {
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    return launch_subtractive_flow_erosion(d_height, d_scratch, width, rows, erosive_iterations, erosive_factor, norm_min,
+                                           norm_max, (cudaStream_t)stream);
+}
 NZ_API int32_t nz_dev_constant(float* d_data, size_t n, int32_t operation, float constant_value, void* stream) {
     NZ_REQUIRE(d_data || n == 0, "nz_dev_constant: null grid");
     return launch_constant(d_data, n, operation, constant_value, (cudaStream_t)stream);
@@ -879,6 +891,25 @@ NZ_API int32_t nz_thermal_erosion(nz_slice_f32 src, float talus, float increment
     return run_inplace_stage(src, resolution, "nz_thermal_erosion", false, [&](Mirror& m, float**) {
         return launch_thermal_erosion(m.d, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, t_state.stream);
     });
+}
+
+NZ_API int32_t nz_subtractive_flow_erosion(nz_slice_f32 height, int32_t resolution, int32_t erosive_iterations,
+                                           float erosive_factor, float norm_min, float norm_max) {
+    NZ_REQUIRE(erosive_iterations >= 0, "nz_subtractive_flow_erosion: erosiveIterations %d < 0", erosive_iterations);
+    void* scratch = nullptr;
+    int32_t rc = run_inplace_stage(height, resolution, "nz_subtractive_flow_erosion", false, [&](Mirror& m, float**) {
+        if (erosive_iterations > 0) {
+            int32_t r = pool_alloc(&scratch, subtractive_flow_scratch_bytes(resolution, resolution));
+            if (r != NZ_OK) return r;
+        }
+        return launch_subtractive_flow_erosion(m.d, scratch, resolution, resolution, erosive_iterations, erosive_factor,
+                                               norm_min, norm_max, t_state.stream);
+    });
+    if (scratch) {
+        if (in_scope()) cudaStreamSynchronize(t_state.stream);   // order the release after the work (see nz_flowmap)
+        pool_free(scratch);
+    }
+    return rc;
 }
 
 NZ_API int32_t nz_constant(nz_slice_f32 src, nz_slice_f32 tmp, int32_t operation, float constant_value, int32_t resolution) {

@@ -29,7 +29,10 @@ struct FlowFields {
     float* fN;
 };
 
-template <bool FIRST>
+// FIRST: water is still the fill value everywhere (nothing to read); ZERO: the flow fields are still all zero.
+// FlowMapStage has both in its first iteration; a later cycle of the subtractive-flow erosion refills the water
+// but keeps its flows (FIRST && !ZERO).
+template <bool FIRST, bool ZERO = FIRST>
 __global__ void __launch_bounds__(TX) flow_step_kernel(const float* __restrict__ height, FlowFields f, int width, int rows) {
     const int z = blockIdx.y;
     const int x = blockIdx.x * TX + threadIdx.x;
@@ -37,7 +40,6 @@ __global__ void __launch_bounds__(TX) flow_step_kernel(const float* __restrict__
     const size_t i = (size_t)z * width + x;
     const int xW = max(x - 1, 0), xE = min(x + 1, width - 1);
     const size_t rS = (size_t)max(z - 1, 0) * width, rN = (size_t)min(z + 1, rows - 1) * width, r0 = (size_t)z * width;
-    // FIRST iteration: water is the fill value everywhere and flows are zero -> nothing to read but height
     const float w0 = FIRST ? 0.0001f : f.water[i];
     const float h0 = __ldg(height + i);
     const float totalHt = w0 + h0;
@@ -45,10 +47,10 @@ __global__ void __launch_bounds__(TX) flow_step_kernel(const float* __restrict__
     const float dE = totalHt - ((FIRST ? 0.0001f : f.water[r0 + xE]) + __ldg(height + r0 + xE));
     const float dS = totalHt - ((FIRST ? 0.0001f : f.water[rS + x]) + __ldg(height + rS + x));
     const float dN = totalHt - ((FIRST ? 0.0001f : f.water[rN + x]) + __ldg(height + rN + x));
-    const float flW = fmaxf(0.0f, (FIRST ? 0.0f : f.fW[i]) + dW);
-    const float flE = fmaxf(0.0f, (FIRST ? 0.0f : f.fE[i]) + dE);
-    const float flS = fmaxf(0.0f, (FIRST ? 0.0f : f.fS[i]) + dS);
-    const float flN = fmaxf(0.0f, (FIRST ? 0.0f : f.fN[i]) + dN);
+    const float flW = fmaxf(0.0f, (ZERO ? 0.0f : f.fW[i]) + dW);
+    const float flE = fmaxf(0.0f, (ZERO ? 0.0f : f.fE[i]) + dE);
+    const float flS = fmaxf(0.0f, (ZERO ? 0.0f : f.fS[i]) + dS);
+    const float flN = fmaxf(0.0f, (ZERO ? 0.0f : f.fN[i]) + dN);
     const float sum_ = (flW + flE) + (flS + flN);  // math.csum(float4)
     // clamp(w0 / (sum*dt), 0, 1) without dividing when the clamp decides (see flowwave_kernels.cu flow_cell)
     const float d = sum_ * TIMESTEP;
@@ -98,6 +100,28 @@ __global__ void __launch_bounds__(TX) velocity_norm_kernel(float* __restrict__ o
     float v = sqrtf(fmaf(vy, vy, vx * vx));
     if (norm_range < 1e-12f) v = 0.0f;
     out[i] = (v - norm_min) / norm_range;
+}
+
+// One cycle's epilogue of the subtractive-flow erosion, fused: velocity magnitude -> NormalizeMap -> ConstantMultiply ->
+// SubtractTiles (ErosionStageSubtractiveFlow.cs:196-222).  Each of the four is one rounding, so the fused form has the
+// bits of the four separate jobs.
+__global__ void __launch_bounds__(TX) velocity_erode_kernel(float* __restrict__ height, FlowFields f, int width, int rows,
+                                                            float norm_min, float norm_range, float erosive_factor) {
+    const int z = blockIdx.y;
+    const int x = blockIdx.x * TX + threadIdx.x;
+    if (x >= width) return;
+    const size_t i = (size_t)z * width + x;
+    const int xW = max(x - 1, 0), xE = min(x + 1, width - 1);
+    const size_t rS = (size_t)max(z - 1, 0) * width, rN = (size_t)min(z + 1, rows - 1) * width, r0 = (size_t)z * width;
+    const float dl = f.fE[r0 + xW] - f.fW[i];
+    const float dr = f.fE[i] - f.fW[r0 + xE];
+    const float dt = f.fS[rN + x] - f.fN[i];
+    const float db = f.fS[i] - f.fN[rS + x];
+    const float vx = (dl + dr) * 0.5f, vy = (dt + db) * 0.5f;
+    float v = sqrtf(fmaf(vy, vy, vx * vx));
+    if (norm_range < 1e-12f) v = 0.0f;
+    v = (v - norm_min) / norm_range;
+    height[i] = height[i] - v * erosive_factor;
 }
 
 // iterations == 0: velocity of an all-zero flow field is 0
@@ -165,6 +189,40 @@ int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width
     velocity_norm_kernel<<<grid, TX, 0, s>>>(d_height, f, width, rows, norm_min, norm_range);
     NZ_LAUNCHED();
     if (d_result) *d_result = d_height;
+    return NZ_OK;
+}
+
+// ErosionStageSubtractiveFlow.ScheduleAll / ScheduleCycle (Geologic/Stage/ErosionStageSubtractiveFlow.cs:138-230; SURVEY 8f
+// rank 3 — commented-out code upstream, built from its text): cycle n runs n + 1 flow iterations on refilled water and
+// PERSISTING flow fields, then erodes the heights by erosive_factor x the normalised velocity magnitude.  The heights
+// change between cycles and the flows carry over, so the cycles run on the per-iteration kernels with water + 4 flows in
+// d_scratch (5 fields).  The erosion of cycle n reads only the flows, so it may update the heights in place.
+size_t subtractive_flow_scratch_bytes(int width, int rows) { return (size_t)width * rows * sizeof(float) * 5; }
+
+int32_t launch_subtractive_flow_erosion(float* d_height, void* d_scratch, int width, int rows, int erosive_iterations,
+                                        float erosive_factor, float norm_min, float norm_max, cudaStream_t s) {
+    NZ_REQUIRE(d_height, "subtractive flow erosion: null height buffer");
+    NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && erosive_iterations >= 0, "subtractive flow erosion: bad arguments");
+    if (erosive_iterations == 0) return NZ_OK;
+    NZ_REQUIRE(d_scratch, "subtractive flow erosion: null scratch buffer (need nz_dev_subtractive_flow_scratch_bytes)");
+    const size_t n = (size_t)width * rows;
+    const float norm_range = norm_max - norm_min;
+    float* sc = (float*)d_scratch;
+    FlowFields f = {sc, sc + n, sc + 2 * n, sc + 3 * n, sc + 4 * n};
+    dim3 grid(cdiv(width, TX), rows);
+    for (int c = 0; c < erosive_iterations; c++) {
+        for (int it = 0; it <= c; it++) {
+            if (it == 0 && c == 0) flow_step_kernel<true, true><<<grid, TX, 0, s>>>(d_height, f, width, rows);
+            else if (it == 0) flow_step_kernel<true, false><<<grid, TX, 0, s>>>(d_height, f, width, rows);
+            else flow_step_kernel<false, false><<<grid, TX, 0, s>>>(d_height, f, width, rows);
+            NZ_LAUNCHED();
+            if (it == 0) water_step_kernel<true><<<grid, TX, 0, s>>>(f, width, rows);
+            else water_step_kernel<false><<<grid, TX, 0, s>>>(f, width, rows);
+            NZ_LAUNCHED();
+        }
+        velocity_erode_kernel<<<grid, TX, 0, s>>>(d_height, f, width, rows, norm_min, norm_range, erosive_factor);
+        NZ_LAUNCHED();
+    }
     return NZ_OK;
 }
 

@@ -73,6 +73,9 @@ int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int
 size_t flowmap_scratch_bytes(int width, int rows, int iterations);
 int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width, int rows, int iterations,
                        float norm_min, float norm_max, float** d_result, cudaStream_t s);
+size_t subtractive_flow_scratch_bytes(int width, int rows);
+int32_t launch_subtractive_flow_erosion(float* d_height, void* d_scratch, int width, int rows, int erosive_iterations,
+                                        float erosive_factor, float norm_min, float norm_max, cudaStream_t s);
 bool flow_wave_supported(int width, int rows, int iterations, const void* a, const void* b);
 int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
                          float norm_max, cudaStream_t s);

@@ -100,6 +100,19 @@ def thermal_erosion(data, talus=45.0, increment_ratio=0.5, mesh_height_width_rat
     return data
 
 
+def subtractive_flow_erosion(height, erosive_iterations=5, erosive_factor=0.1, norm_min=-0.1, norm_max=0.1, stream=None):
+    """In place on a device grid; water + 4 flow fields live in a scratch tensor for the call."""
+    import torch
+    _grid(height, "height")
+    rows, width = height.shape
+    need = _l.load().nz_dev_subtractive_flow_scratch_bytes(width, rows)
+    scratch = torch.empty(need // 4, dtype=torch.float32, device=height.device) if erosive_iterations > 0 else None
+    _l.check(_l.load().nz_dev_subtractive_flow_erosion(height.data_ptr(), scratch.data_ptr() if scratch is not None else None,
+                                                       width, rows, erosive_iterations, erosive_factor, norm_min, norm_max,
+                                                       _l.stream_ptr(stream)))
+    return height
+
+
 def constant(data, operation, value, stream=None):
     _grid(data, "data")
     _l.check(_l.load().nz_dev_constant(data.data_ptr(), data.numel(), int(operation), value, _l.stream_ptr(stream)))

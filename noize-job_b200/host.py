@@ -128,6 +128,12 @@ def thermal_erosion(src, talus, increment_ratio, mesh_height_width_ratio, iterat
                                           resolution))
 
 
+def subtractive_flow_erosion(height, resolution, erosive_iterations, erosive_factor, norm_min, norm_max):
+    """ErosionStageSubtractiveFlow.ScheduleAll, Geologic/Stage/ErosionStageSubtractiveFlow.cs:224-230 (cycle :138-222)."""
+    _l.check(_l.load().nz_subtractive_flow_erosion(_l.as_slice(height), resolution, erosive_iterations, erosive_factor,
+                                                   norm_min, norm_max))
+
+
 def constant(src, tmp, operation, constant_value, resolution):
     """ConstantJobScheduleDelegate, Filter/ConstantJob.cs:49-55."""
     _l.check(_l.load().nz_constant(_l.as_slice(src), _l.as_slice(tmp), int(operation), constant_value, resolution))

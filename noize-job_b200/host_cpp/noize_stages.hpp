@@ -217,6 +217,19 @@ public:
     }
 };
 
+class ErosionStageSubtractiveFlow : public PipelineStage {   // Geologic/Stage/ErosionStageSubtractiveFlow.cs:17-247 (commented out upstream)
+public:
+    int flowIterations = 5;                              // serialised upstream, read by nothing (:19-20, :226-228)
+    float normMin = -0.1f, normMax = 0.1f, erosiveFactor = 0.1f;
+    int erosiveIterations = 5;
+    void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
+        GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
+        jobHandle = JobHandle::Chain(dependency);
+        check(nz_subtractive_flow_erosion(d->data, d->resolution, erosiveIterations, erosiveFactor, normMin, normMax),
+              "nz_subtractive_flow_erosion");
+    }
+};
+
 class ConstantStage : public PipelineStage {            // Filter/ConstantStage.cs:13-60
 public:
     ConstantOperationType operation = ConstantOperationType::MULTIPLY;

@@ -59,6 +59,7 @@ SIGNATURES = {
     "nz_flowmap": (_i32, [Slice, _i32, _i32, _f32, _f32]),
     "nz_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, Slice]),
     "nz_thermal_erosion": (_i32, [Slice, _f32, _f32, _f32, _i32, _i32]),
+    "nz_subtractive_flow_erosion": (_i32, [Slice, _i32, _i32, _f32, _f32, _f32]),
     "nz_constant": (_i32, [Slice, Slice, _i32, _f32, _i32]),
     "nz_reduce": (_i32, [Slice, Slice, Slice, _i32, _i32]),
     "nz_curve": (_i32, [Slice, Slice, Slice, _i32]),
@@ -82,6 +83,8 @@ SIGNATURES = {
     "nz_dev_flowmap": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, C.POINTER(_vp), _vp]),
     "nz_dev_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "nz_dev_thermal_erosion": (_i32, [_vp, _i32, _f32, _f32, _f32, _i32, _vp]),
+    "nz_dev_subtractive_flow_scratch_bytes": (_sz, [_i32, _i32]),
+    "nz_dev_subtractive_flow_erosion": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp]),
     "nz_dev_constant": (_i32, [_vp, _sz, _i32, _f32, _vp]),
     "nz_dev_reduce": (_i32, [_vp, _vp, _sz, _i32, _vp]),
     "nz_dev_curve": (_i32, [_vp, _sz, _vp, _i32, _vp]),

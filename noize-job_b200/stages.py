@@ -13,6 +13,7 @@ file side by side with the originals (paths relative to xshazwar/noize-job):
   MeshTileStage                     Mesh/Stage/MeshTileStage.cs:28-62
   BasePipeline (scheduling chain)   Pipeline/Executable/Pipeline.cs:104-181
   StageThermalErosion               Filter/Kernel/Blur/StageThermalErosion.cs:13-29
+  ErosionStageSubtractiveFlow       Geologic/Stage/ErosionStageSubtractiveFlow.cs:17-247 (commented out upstream)
   ConstantStage                     Filter/ConstantStage.cs:13-60
   ReduceStage, ReduceData           Filter/Reduce/ReduceStage.cs:12-68, Pipeline/Stage/StageIOTypes/ReduceData.cs
   CurveStage                        Filter/Curve/CurveStage.cs:13-73
@@ -289,6 +290,22 @@ class StageThermalErosion(PipelineStage):
         d = requirements.data
         self.jobHandle = _chain(dependency)
         _h.thermal_erosion(d.data, float(self.talus), self.increment, self.meshHeightWidthRatio, self.iterations, d.resolution)
+
+
+class ErosionStageSubtractiveFlow(PipelineStage):
+    """Fields and defaults of ErosionStageSubtractiveFlow.cs:19-27.  `flowIterations` is kept as a field because the
+    reference serialises it, but nothing reads it there either: cycle n runs n + 1 flow iterations (:226-228)."""
+
+    def __init__(self, flowIterations=5, normMin=-0.1, normMax=0.1, erosiveFactor=0.1, erosiveIterations=5):
+        super().__init__()
+        self.flowIterations, self.normMin, self.normMax = flowIterations, normMin, normMax
+        self.erosiveFactor, self.erosiveIterations = erosiveFactor, erosiveIterations
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        d = requirements.data
+        self.jobHandle = _chain(dependency)
+        _h.subtractive_flow_erosion(d.data, d.resolution, self.erosiveIterations, self.erosiveFactor, self.normMin, self.normMax)
 
 
 class ConstantStage(PipelineStage):

@@ -64,6 +64,9 @@ namespace xshazwar.noize.interop.b200 {
         // ThermalErosionFilterDelegate, Filter/Kernel/Blur/ThermalErosionFilter.cs:138-146
         [DllImport(LIB)] public static extern int nz_thermal_erosion(NzSlice src, float talus, float incrementRatio,
             float meshHeightWidthRatio, int iterations, int resolution);
+        // ErosionStageSubtractiveFlow.ScheduleAll, Geologic/Stage/ErosionStageSubtractiveFlow.cs:224-230 (cycle :138-222)
+        [DllImport(LIB)] public static extern int nz_subtractive_flow_erosion(NzSlice height, int resolution, int erosiveIterations,
+            float erosiveFactor, float normMin, float normMax);
         // ConstantJobScheduleDelegate, Filter/ConstantJob.cs:49-55
         [DllImport(LIB)] public static extern int nz_constant(NzSlice src, NzSlice tmp, int operation, float constantValue, int resolution);
         // ReductionJobScheduleDelegate, Filter/ReductionJob.cs:55-61
@@ -95,7 +98,7 @@ namespace xshazwar.noize.interop.b200 {
     /// One blocking native call, run where the Burst job body used to run.  Not [BurstCompile]: P/Invoke from a
     /// managed IJob is legal; the status code comes back through a NativeReference checked in OnStageComplete.
     public unsafe struct NativeCallJob : IJob {
-        public enum Op { Fractal, KernelFilter, GaussFilter, SmoothFilter, MinErosion, FlowMap, Mesh, ThermalErosion, Constant, Reduce, Curve, Crop }
+        public enum Op { Fractal, KernelFilter, GaussFilter, SmoothFilter, MinErosion, FlowMap, Mesh, ThermalErosion, Constant, Reduce, Curve, Crop, SubtractiveFlow }
         public Op op;
         [NativeDisableContainerSafetyRestriction] public NativeSlice<float> data;
         [NativeDisableContainerSafetyRestriction] public NativeSlice<float> data2;   // right operand / curve samples / crop input
@@ -119,6 +122,7 @@ namespace xshazwar.noize.interop.b200 {
                 case Op.FlowMap:      rc = Native.nz_flowmap(s, resolution, i1, f0, f1); break;
                 case Op.Mesh:         rc = Native.nz_heightmap_mesh(i0, vertices, indices, resolution, inputResolution, marginPix, f0, f1, s); break;
                 case Op.ThermalErosion: rc = Native.nz_thermal_erosion(s, f0, f1, f2, i1, resolution); break;
+                case Op.SubtractiveFlow: rc = Native.nz_subtractive_flow_erosion(s, resolution, i1, f2, f0, f1); break;
                 case Op.Constant:     rc = Native.nz_constant(s, NzSlice.Null, i0, f0, resolution); break;
                 case Op.Reduce:       rc = Native.nz_reduce(s, NzSlice.From(data2), NzSlice.Null, i0, resolution); break;
                 case Op.Curve:        rc = Native.nz_curve(s, NzSlice.Null, NzSlice.From(data2), resolution); break;
@@ -213,6 +217,25 @@ namespace xshazwar.noize.interop.b200 {
             jobHandle = new NativeCallJob {
                 op = NativeCallJob.Op.ThermalErosion, data = d.data, resolution = d.resolution, i1 = iterations,
                 f0 = (float) talus, f1 = increment, f2 = meshHeightWidthRatio, status = status
+            }.Schedule(dependency);
+        }
+    }
+
+    // ErosionStageSubtractiveFlow, Geologic/Stage/ErosionStageSubtractiveFlow.cs:17-247 (commented out upstream; same fields)
+    [CreateAssetMenu(fileName = "GpuErosionSubtractiveFlowStage", menuName = "Noize/B200/SubtractiveFlow", order = 2)]
+    public class GpuErosionStageSubtractiveFlow : GpuStage {
+        [Range(1, 32)] public int flowIterations = 5;   // unused upstream as well: cycle n runs n + 1 iterations
+        public float normMin = -.1f;
+        public float normMax = .1f;
+        public float erosiveFactor = .1f;
+        public int erosiveIterations = 5;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            EnsureStatus();
+            jobHandle = new NativeCallJob {
+                op = NativeCallJob.Op.SubtractiveFlow, data = d.data, resolution = d.resolution, i1 = erosiveIterations,
+                f0 = normMin, f1 = normMax, f2 = erosiveFactor, status = status
             }.Schedule(dependency);
         }
     }

@@ -58,6 +58,8 @@ def _bind(lib):
     lib.nzref_min_erosion.argtypes = [_f32p, _f32p, i32, i32, i32]
     lib.nzref_flowmap.restype = i32
     lib.nzref_flowmap.argtypes = [_f32p, i32, i32, i32, f32, f32]
+    lib.nzref_subtractive_flow_erosion.restype = i32
+    lib.nzref_subtractive_flow_erosion.argtypes = [_f32p, i32, i32, i32, f32, f32, f32]
     lib.nzref_heightmap_mesh.restype = i32
     lib.nzref_heightmap_mesh.argtypes = [i32, _f32p, _u32p, i32, i32, i32, f32, f32, _f32p]
     lib.nzref_tile_geometry.restype = i32
@@ -172,7 +174,13 @@ class Oracle:
         assert rc == 0, rc
         return d
 
-    # -- section 8f rows: thermal erosion and the element-wise stages ---------------------------
+    # -- section 8f rows: thermal erosion, subtractive-flow erosion and the element-wise stages --
+    def subtractive_flow_erosion(self, grid, erosive_iterations=5, erosive_factor=0.1, norm_min=-0.1, norm_max=0.1):
+        d = self._grid(grid)
+        rc = self.lib.nzref_subtractive_flow_erosion(d, d.shape[1], d.shape[0], erosive_iterations, erosive_factor, norm_min, norm_max)
+        assert rc == 0, rc
+        return d
+
     def thermal_max_diff(self, talus, height_ratio, resolution):
         return float(self.lib.nzref_thermal_max_diff(talus, height_ratio, resolution))
 

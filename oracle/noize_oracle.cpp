@@ -553,67 +553,73 @@ NZREF_API int32_t nzref_min_erosion(float* data, float* tmp, int32_t width, int3
 /* ------------------------------------------------------------------------------------------
  * Geologic/FlowMap — FlowMapComponents.cs:16-202, FlowMapJob.cs, Geologic/Stage/FlowMapStage.cs:124-195
  * ------------------------------------------------------------------------------------------ */
-NZREF_API int32_t nzref_flowmap(float* height, int32_t width, int32_t rows, int32_t iterations, float norm_min,
-                                float norm_max) {
-    if (!height || width <= 0 || rows <= 0 || iterations < 0) return -1;
-    const size_t n = (size_t)width * rows;
-    const float TIMESTEP = 0.2f;
-    /* water + 4 flows, each READ and WRITE (FlowMapStage.cs:42-66); flows start at 0 (reference:
-       uninitialised), water filled with 1e-4 (FillArrayJob, :129) */
-    float* buf = (float*)calloc(n * 11, sizeof(float));
-    if (!buf) return -3;
-    float *water = buf, *water_w = buf + n;
-    float *fN = buf + 2 * n, *fN_w = buf + 3 * n, *fS = buf + 4 * n, *fS_w = buf + 5 * n;
-    float *fE = buf + 6 * n, *fE_w = buf + 7 * n, *fW = buf + 8 * n, *fW_w = buf + 9 * n;
-    float* tmp = buf + 10 * n;
-    for (size_t i = 0; i < n; i++) water[i] = 0.0001f;
-    for (int it = 0; it < iterations; it++) {
-        { /* ComputeFlowStep.CalculateCell, FlowMapComponents.cs:20-65 */
-            Tile H = {height, width, rows}, Wt = {water, width, rows};
-#pragma omp parallel for schedule(dynamic, 1)
-            for (int z = 0; z < rows; z++)
-                for (int x = 0; x < width; x++) {
-                    size_t i = (size_t)z * width + x;
-                    float height_0 = H.get(x, z), water_0 = Wt.get(x, z);
-                    float totalHt = water_0 + height_0;
-                    float dW = totalHt - (Wt.get(x - 1, z) + H.get(x - 1, z));
-                    float dE = totalHt - (Wt.get(x + 1, z) + H.get(x + 1, z));
-                    float dS = totalHt - (Wt.get(x, z - 1) + H.get(x, z - 1));
-                    float dN = totalHt - (Wt.get(x, z + 1) + H.get(x, z + 1));
-                    float flW = fmaxf(0.0f, fW[i] + dW), flE = fmaxf(0.0f, fE[i] + dE);
-                    float flS = fmaxf(0.0f, fS[i] + dS), flN = fmaxf(0.0f, fN[i] + dN);
-                    float sum_ = (flW + flE) + (flS + flN); /* math.csum(float4) = (x+y)+(z+w) */
-                    if (sum_ > 0.0f) {
-                        float K = water_0 / (sum_ * TIMESTEP);
-                        K = fminf(fmaxf(K, 0.0f), 1.0f);
-                        fW_w[i] = flW * K; fE_w[i] = flE * K; fS_w[i] = flS * K; fN_w[i] = flN * K;
-                    } else {
-                        fW_w[i] = 0.0f; fE_w[i] = 0.0f; fS_w[i] = 0.0f; fN_w[i] = 0.0f;
-                    }
-                }
-            /* SWAP_RWTILE x4, FlowMapJob.cs:74-77 */
-            flush_write_slice(fN, fN_w, n); flush_write_slice(fS, fS_w, n);
-            flush_write_slice(fE, fE_w, n); flush_write_slice(fW, fW_w, n);
-        }
-        { /* UpdateWaterStep.CalculateCell, FlowMapComponents.cs:81-104 */
-            Tile tN = {fN, width, rows}, tS = {fS, width, rows}, tE = {fE, width, rows}, tW = {fW, width, rows};
-#pragma omp parallel for schedule(dynamic, 8)
-            for (int z = 0; z < rows; z++)
-                for (int x = 0; x < width; x++) {
-                    size_t i = (size_t)z * width + x;
-                    float flowOUT = ((tW.get(x, z) + tE.get(x, z)) + tS.get(x, z)) + tN.get(x, z);
-                    float flowIN = 0.0f;
-                    flowIN += tE.get(x - 1, z);
-                    flowIN += tW.get(x + 1, z);
-                    flowIN += tN.get(x, z - 1);
-                    flowIN += tS.get(x, z + 1);
-                    float ht = fmaf(flowIN - flowOUT, TIMESTEP, water[i]);
-                    water_w[i] = fmaxf(0.0f, ht);
-                }
-            flush_write_slice(water, water_w, n);
-        }
+/* One FlowMapStage / ErosionStageSubtractiveFlow scratch set: water + 4 flows, each READ and WRITE
+ * (FlowMapStage.cs:42-66), + tmp.  Flows start at 0 (reference: uninitialised). */
+struct FlowState {
+    size_t n; int width, rows;
+    float *buf, *water, *water_w, *fN, *fN_w, *fS, *fS_w, *fE, *fE_w, *fW, *fW_w, *tmp;
+    bool init(int w, int r) {
+        width = w; rows = r; n = (size_t)w * r;
+        buf = (float*)calloc(n * 11, sizeof(float));
+        if (!buf) return false;
+        water = buf; water_w = buf + n;
+        fN = buf + 2 * n; fN_w = buf + 3 * n; fS = buf + 4 * n; fS_w = buf + 5 * n;
+        fE = buf + 6 * n; fE_w = buf + 7 * n; fW = buf + 8 * n; fW_w = buf + 9 * n;
+        tmp = buf + 10 * n;
+        return true;
     }
-    { /* CreateVelocityField.CalculateCell, FlowMapComponents.cs:120-139 */
+    /* FillArrayJob, FlowMapComponents.cs:176-202 (FlowMapStage.cs:129) */
+    void fill_water(float v) { for (size_t i = 0; i < n; i++) water[i] = v; }
+    /* ComputeFlowStep.CalculateCell, FlowMapComponents.cs:20-65 */
+    void outflow_step(const float* height) {
+        const float TIMESTEP = 0.2f;
+        Tile H = {(float*)height, width, rows}, Wt = {water, width, rows};
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int z = 0; z < rows; z++)
+            for (int x = 0; x < width; x++) {
+                size_t i = (size_t)z * width + x;
+                float height_0 = H.get(x, z), water_0 = Wt.get(x, z);
+                float totalHt = water_0 + height_0;
+                float dW = totalHt - (Wt.get(x - 1, z) + H.get(x - 1, z));
+                float dE = totalHt - (Wt.get(x + 1, z) + H.get(x + 1, z));
+                float dS = totalHt - (Wt.get(x, z - 1) + H.get(x, z - 1));
+                float dN = totalHt - (Wt.get(x, z + 1) + H.get(x, z + 1));
+                float flW = fmaxf(0.0f, fW[i] + dW), flE = fmaxf(0.0f, fE[i] + dE);
+                float flS = fmaxf(0.0f, fS[i] + dS), flN = fmaxf(0.0f, fN[i] + dN);
+                float sum_ = (flW + flE) + (flS + flN); /* math.csum(float4) = (x+y)+(z+w) */
+                if (sum_ > 0.0f) {
+                    float K = water_0 / (sum_ * TIMESTEP);
+                    K = fminf(fmaxf(K, 0.0f), 1.0f);
+                    fW_w[i] = flW * K; fE_w[i] = flE * K; fS_w[i] = flS * K; fN_w[i] = flN * K;
+                } else {
+                    fW_w[i] = 0.0f; fE_w[i] = 0.0f; fS_w[i] = 0.0f; fN_w[i] = 0.0f;
+                }
+            }
+        /* SWAP_RWTILE x4, FlowMapJob.cs:74-77 */
+        flush_write_slice(fN, fN_w, n); flush_write_slice(fS, fS_w, n);
+        flush_write_slice(fE, fE_w, n); flush_write_slice(fW, fW_w, n);
+    }
+    /* UpdateWaterStep.CalculateCell, FlowMapComponents.cs:81-104 */
+    void water_step() {
+        const float TIMESTEP = 0.2f;
+        Tile tN = {fN, width, rows}, tS = {fS, width, rows}, tE = {fE, width, rows}, tW = {fW, width, rows};
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int z = 0; z < rows; z++)
+            for (int x = 0; x < width; x++) {
+                size_t i = (size_t)z * width + x;
+                float flowOUT = ((tW.get(x, z) + tE.get(x, z)) + tS.get(x, z)) + tN.get(x, z);
+                float flowIN = 0.0f;
+                flowIN += tE.get(x - 1, z);
+                flowIN += tW.get(x + 1, z);
+                flowIN += tN.get(x, z - 1);
+                flowIN += tS.get(x, z + 1);
+                float ht = fmaf(flowIN - flowOUT, TIMESTEP, water[i]);
+                water_w[i] = fmaxf(0.0f, ht);
+            }
+        flush_write_slice(water, water_w, n);
+    }
+    /* CreateVelocityField.CalculateCell, FlowMapComponents.cs:120-139 */
+    void velocity(float* out) {
         Tile tN = {fN, width, rows}, tS = {fS, width, rows}, tE = {fE, width, rows}, tW = {fW, width, rows};
 #pragma omp parallel for schedule(dynamic, 8)
         for (int z = 0; z < rows; z++)
@@ -623,22 +629,67 @@ NZREF_API int32_t nzref_flowmap(float* height, int32_t width, int32_t rows, int3
                 float dt = tS.get(x, z + 1) - tN.get(x, z);
                 float db = tS.get(x, z) - tN.get(x, z - 1);
                 float vx = (dl + dr) * 0.5f, vy = (dt + db) * 0.5f;
-                height[(size_t)z * width + x] = sqrtf(fmaf(vy, vy, vx * vx));
+                out[(size_t)z * width + x] = sqrtf(fmaf(vy, vy, vx * vx));
             }
     }
-    { /* NormalizeMap.CalculateCell, FlowMapComponents.cs:157-165; args FlowMapStage.cs:48-51 */
+    /* NormalizeMap.CalculateCell, FlowMapComponents.cs:157-165; args {min, max, max-min} FlowMapStage.cs:48-51 */
+    void normalize(float* map, float norm_min, float norm_max) {
         const float a0 = norm_min, a2 = norm_max - norm_min;
 #pragma omp parallel for schedule(dynamic, 8)
         for (int z = 0; z < rows; z++)
             for (int x = 0; x < width; x++) {
                 size_t i = (size_t)z * width + x;
-                float v = height[i];
+                float v = map[i];
                 if (a2 < 1e-12f) v = 0.0f;
                 tmp[i] = (v - a0) / a2;
             }
-        flush_write_slice(height, tmp, n);
+        flush_write_slice(map, tmp, n);
     }
-    free(buf);
+};
+
+/* FlowMapStage.ScheduleAll, Geologic/Stage/FlowMapStage.cs:124-195 */
+NZREF_API int32_t nzref_flowmap(float* height, int32_t width, int32_t rows, int32_t iterations, float norm_min,
+                                float norm_max) {
+    if (!height || width <= 0 || rows <= 0 || iterations < 0) return -1;
+    FlowState f;
+    if (!f.init(width, rows)) return -3;
+    f.fill_water(0.0001f);
+    for (int it = 0; it < iterations; it++) {
+        f.outflow_step(height);
+        f.water_step();
+    }
+    f.velocity(height);   /* the velocity magnitude overwrites the height slice */
+    f.normalize(height, norm_min, norm_max);
+    free(f.buf);
+    return 0;
+}
+
+/* ErosionStageSubtractiveFlow (the stage is commented-out code upstream, so this follows its text):
+ * ScheduleAll (Geologic/Stage/ErosionStageSubtractiveFlow.cs:224-230) runs cycle n = 0..erosiveIterations-1 with
+ * n + 1 flow iterations; ScheduleCycle (:138-222) refills the water with 1e-4 (:144), runs (outflow, water) steps on
+ * flow fields that PERSIST across the cycles (allocated once, :54-76), writes the velocity magnitude into its own
+ * velocityMap (:196-203), normalises it (:204-210), multiplies by erosiveFactor (ConstantMultiply, :211-217) and
+ * subtracts it from the heights (SubtractTiles, :218-222).  `flowIterations` (:19-20) is never read. */
+NZREF_API int32_t nzref_subtractive_flow_erosion(float* height, int32_t width, int32_t rows, int32_t erosive_iterations,
+                                                 float erosive_factor, float norm_min, float norm_max) {
+    if (!height || width <= 0 || rows <= 0 || erosive_iterations < 0) return -1;
+    FlowState f;
+    if (!f.init(width, rows)) return -3;
+    float* velocity = (float*)malloc(f.n * sizeof(float));
+    if (!velocity) { free(f.buf); return -3; }
+    for (int n = 0; n < erosive_iterations; n++) {
+        f.fill_water(0.0001f);
+        for (int it = 0; it < n + 1; it++) {
+            f.outflow_step(height);
+            f.water_step();
+        }
+        f.velocity(velocity);
+        f.normalize(velocity, norm_min, norm_max);
+        for (size_t i = 0; i < f.n; i++) velocity[i] = velocity[i] * erosive_factor;   /* ConstantMultiply */
+        for (size_t i = 0; i < f.n; i++) height[i] = height[i] - velocity[i];          /* SubtractTiles   */
+    }
+    free(velocity);
+    free(f.buf);
     return 0;
 }
 

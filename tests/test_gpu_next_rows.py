@@ -121,3 +121,33 @@ def test_crop_stage_reference_behaviour_and_center(nz, oracle):
     assert np.array_equal(out.reshape(64, 64), g[:64, :64])
     nz.BasePipeline([nz.CropStage("center")]).Run(nz.DownsampleData("c", out, 64, 96, g.reshape(-1)))
     assert np.array_equal(out.reshape(64, 64), g[16:80, 16:80])
+
+
+# ---- subtractive-flow erosion -------------------------------------------------------------------
+@pytest.mark.parametrize("res,cycles", [(64, 1), (130, 3), (512, 5), (33, 0)])
+def test_subtractive_flow_erosion_bit_exact(nz, oracle, res, cycles):
+    """Same operations in the same order as the oracle (IEEE add/mul/div/sqrt/fma, --fmad=false): bit-exact."""
+    g = oracle.kernel_filter(oracle.fractal(res, res, 3, 0.4, octaves=13, noise_size=170), 2, 3)
+    got = g.copy().reshape(-1)
+    nz.host.subtractive_flow_erosion(got, res, cycles, 0.1, 0.0, 0.005)
+    ref = oracle.subtractive_flow_erosion(g, cycles, 0.1, 0.0, 0.005)
+    assert np.array_equal(bits(got.reshape(res, res)), bits(ref))
+    assert (cycles == 0) == np.array_equal(got.reshape(res, res), g)
+
+
+def test_subtractive_flow_erosion_stage_and_device_layer(nz, oracle):
+    import torch
+    res = 256
+    g = oracle.kernel_filter(oracle.fractal(res, res, 5, 0.4, octaves=13, noise_size=170), 2, 3)
+    data = g.copy().reshape(-1)
+    stage = nz.ErosionStageSubtractiveFlow(erosiveIterations=4, erosiveFactor=0.05)   # default normalisation -0.1 / +0.1
+    nz.BasePipeline([stage]).Run(nz.GeneratorData("sub", data, res, 0, 0))
+    ref = oracle.subtractive_flow_erosion(g, 4, 0.05, -0.1, 0.1)
+    assert np.array_equal(bits(data.reshape(res, res)), bits(ref))
+    # rectangular window on the device layer, random (rough) field
+    r = np.random.default_rng(3).random((96, 200), dtype=np.float32)
+    t = torch.from_numpy(r).cuda()
+    nz.device.subtractive_flow_erosion(t, 3, 0.1, 0.0, 0.5)
+    assert np.array_equal(bits(t.cpu().numpy()), bits(oracle.subtractive_flow_erosion(r, 3, 0.1, 0.0, 0.5)))
+    with pytest.raises(nz.NzError):
+        nz.host.subtractive_flow_erosion(data, res, -1, 0.1, 0.0, 0.005)

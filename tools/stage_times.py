@@ -53,6 +53,11 @@ def main():
     d.fractal(b, 1, 0.4, octaves=2, noise_size=1700)
     ms = timeit(lambda: d.thermal_erosion(a, 45.0, 0.5, 0.75, 1), reps)
     rows.append(("thermal x1", ms, 32 * cells))
+    # subtractive-flow erosion, 3 cycles = 1 + 2 + 3 flow iterations on per-iteration kernels: 64 + 144 + 208 B/cell
+    # (outflow step 20/36/40 B, water step 20/24 B, fused erosion epilogue 24 B)
+    ms = timeit(lambda: d.subtractive_flow_erosion(a, 3, 0.001, 0.0, 0.005), max(2, reps // 4))
+    rows.append(("subtractive flow x3", ms, 416 * cells))
+    d.fractal(a, 3, 0.4, octaves=13, noise_size=1700)
     ms = timeit(lambda: d.constant(a, 0, 0.999), reps)
     rows.append(("constant mul", ms, 8 * cells))
     ms = timeit(lambda: d.reduce(a, b, 3), reps)
