@@ -309,6 +309,11 @@ NZ_API int32_t nz_dev_flowmap(float* d_height, float* d_tmp, void* d_scratch, in
                               int32_t iterations, float norm_min, float norm_max,
                               float** d_result, void* stream);
 
+/* Introspection: the register-resident flow kernel divides and takes square roots on guarded fast paths; a launch in
+ * which any cell left the guard (heights beyond ~1e18, quotients in the denormals) is rerun on the wavefront kernel.
+ * Returns how many launches on the current device were rerun so far (synchronises the device). */
+NZ_API int32_t nz_dev_flow_walk_reruns(uint64_t* count);
+
 /* Vertex rows [vz_begin, vz_end) (0 <= vz < resolution+1) and the triangle rows they close
  * (row z>0 writes the 2*resolution triangles between vertex rows z-1 and z).
  * d_heights points at input row `h_row_first` of the input_resolution^2 height grid and holds

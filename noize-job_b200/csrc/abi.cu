@@ -521,6 +521,16 @@ NZ_API int32_t nz_dev_flowmap(float* d_height, float* d_tmp, void* d_scratch, in
                           (cudaStream_t)stream);
 }
 
+NZ_API int32_t nz_dev_flow_walk_reruns(uint64_t* count) {
+    NZ_REQUIRE(count != nullptr, "nz_dev_flow_walk_reruns: null result pointer");
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) return rc;
+    unsigned long long c = 0;
+    rc = flow_walk_reruns(&c);
+    *count = c;
+    return rc;
+}
+
 NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32_t* d_indices, int32_t resolution,
                                      int32_t input_resolution, int32_t margin_pix, float tile_height, float tile_size,
                                      const float* d_heights, int32_t h_row_first, int32_t h_rows, int32_t vz_begin,

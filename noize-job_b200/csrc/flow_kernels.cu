@@ -145,12 +145,16 @@ int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width
     NZ_REQUIRE(d_height, "flowmap: null height buffer");
     NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "flowmap: bad arguments");
     // NZ_FLOW_UNFUSED=1 forces the per-iteration kernels (used by the tests to cross-check the two paths bit for bit)
-    // NZ_FLOW_PATH=tile|wave picks one of the two fused formulations (flowtile_kernels.cu / flowwave_kernels.cu)
+    // NZ_FLOW_PATH=tile|wave|reg picks one of the fused formulations (flowtile_ / flowwave_ / flowwalk_kernels.cu)
     if (d_tmp && !getenv("NZ_FLOW_UNFUSED") && flow_wave_supported(width, rows, iterations, d_height, d_tmp)) {
         const char* fp = getenv("NZ_FLOW_PATH");
-        // measured at 16384^2 (tile / wave, ms): I=1 1.83 / 4.03, I=2 3.02 / 4.29, I=3 4.51 / 5.04, I=4 5.96 / 6.16, I=5 8.08 / 7.35
+        // measured at 16384^2 (register walk / tile / wave, ms): I=1 0.78 / 1.70 / 3.89, I=2 1.42 / 2.82 / 4.15,
+        // I=3 2.32 / 4.25 / 4.71, I=4 3.17 / 5.62 / 5.91, I=5 4.73 / 7.63 / 6.89
+        const bool walk = fp ? fp[0] == 'r' : true;
         const bool tile = fp ? fp[0] == 't' : iterations <= 4;
-        int32_t rc = tile && flow_tile_supported(width, rows, iterations, d_height, d_tmp)
+        int32_t rc = walk && flow_walk_supported(width, rows, iterations, d_height, d_tmp) && flow_walk_range_ok(norm_min, norm_max)
+                         ? launch_flow_walk(d_height, d_tmp, width, rows, iterations, norm_min, norm_max, s)
+                     : tile && flow_tile_supported(width, rows, iterations, d_height, d_tmp)
                          ? launch_flow_tile(d_height, d_tmp, width, rows, iterations, norm_min, norm_max, s)
                          : launch_flow_wave(d_height, d_tmp, width, rows, iterations, norm_min, norm_max, s);
         if (rc != NZ_OK) return rc;

@@ -51,6 +51,9 @@ struct WaveParams {
     float nmin, nrange;
     float nsign;   // copysign(1, nrange)
     int zero_ok;   // nrange is finite and non-zero: 0/nrange == 0*nsign
+    const unsigned* gate;   // when set, the launch only runs if *gate == epoch (rerun requested by flow_walk_kernel)
+    unsigned epoch;
+    unsigned* reruns;       // with gate: counts the launches that did run
 };
 
 struct V4 {
@@ -300,6 +303,10 @@ __device__ __forceinline__ V4 load_row(const Lane& L, int row, int hlo, int hhi,
 template <int I>
 __global__ void __launch_bounds__(FL_THREADS, 2) flow_wave_kernel(WaveParams p) {
     extern __shared__ __align__(16) float sm[];
+    if (p.gate) {
+        if (*p.gate != p.epoch) return;
+        if (p.reruns && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(p.reruns, 1u);
+    }
     const int H = p.H;
     const int xs0 = blockIdx.x * p.swi - p.hx;           // grid x of strip column 0 (even)
     const int zc0 = blockIdx.y * p.zc, zc1 = min(zc0 + p.zc, H);
@@ -370,7 +377,7 @@ bool flow_wave_supported(int width, int rows, int iterations, const void* a, con
 
 // d_out must not alias d_height
 int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
-                         float norm_max, cudaStream_t s) {
+                         float norm_max, cudaStream_t s, const unsigned* gate, unsigned epoch, unsigned* reruns) {
     static bool attr_set = false;
     if (!attr_set) {
         NZ_CUDA(cudaFuncSetAttribute(flow_wave_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem_bytes(1)));
@@ -383,6 +390,7 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
     const int I = iterations;
     WaveParams p;
     p.h = d_height; p.out = d_out; p.W = width; p.H = rows;
+    p.gate = gate; p.epoch = epoch; p.reruns = reruns;
     p.hx = 2 * I;
     p.swi = FLW - 2 * p.hx;
     p.nmin = norm_min;

@@ -78,6 +78,12 @@ int32_t launch_subtractive_flow_erosion(float* d_height, void* d_scratch, int wi
                                         float erosive_factor, float norm_min, float norm_max, cudaStream_t s);
 bool flow_wave_supported(int width, int rows, int iterations, const void* a, const void* b);
 int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
+                         float norm_max, cudaStream_t s, const unsigned* gate = nullptr, unsigned epoch = 0,
+                         unsigned* reruns = nullptr);
+bool flow_walk_supported(int width, int rows, int iterations, const void* a, const void* b);
+bool flow_walk_range_ok(float norm_min, float norm_max);
+int32_t flow_walk_reruns(unsigned long long* count);
+int32_t launch_flow_walk(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
                          float norm_max, cudaStream_t s);
 bool flow_tile_supported(int width, int rows, int iterations, const void* a, const void* b);
 int32_t launch_flow_tile(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,

@@ -59,6 +59,13 @@ def min_erosion(data, tmp, iterations=1, stream=None):
     return _pick(res, data, tmp)
 
 
+def flow_walk_reruns():
+    """Launches of the register-resident flow kernel that were rerun on the wavefront kernel (guarded fast paths left)."""
+    n = C.c_uint64(0)
+    _l.check(_l.load().nz_dev_flow_walk_reruns(C.byref(n)))
+    return int(n.value)
+
+
 def flowmap_scratch_bytes(width, rows, iterations):
     return int(_l.load().nz_dev_flowmap_scratch_bytes(width, rows, iterations))
 

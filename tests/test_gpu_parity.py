@@ -301,6 +301,55 @@ def test_flow_tile_kernel_equals_wavefront_kernel_bitwise(nz, oracle, torch_cuda
     assert torch.equal(tile, wave)
 
 
+@pytest.mark.parametrize("rows,width,iters", [(700, 600, 5), (300, 1000, 4), (97, 236, 3), (40, 20, 2), (513, 472, 1), (33, 4, 5),
+                                              (1100, 1304, 5), (64, 44, 5), (600, 88, 5), (260, 132, 5), (2100, 2048, 5)])
+def test_flow_register_walk_kernel_equals_wavefront_kernel_bitwise(nz, oracle, torch_cuda, monkeypatch, rows, width, iters):
+    """The register-resident formulation (flowwalk_kernels.cu: warp strips of 64 columns, 44 useful at 5 iterations, chunks
+    of <= 256 rows, packed f32x2 arithmetic, reciprocal-sequence division and square root) against the wavefront one, over
+    strip and chunk seams, grid borders and partial strips.  No launch may need the wavefront rerun on ordinary heights."""
+    torch = torch_cuda
+    h = torch.from_numpy(oracle.kernel_filter(rand_grid(rows, width), 3, 2) * np.float32(0.05)).cuda()
+    monkeypatch.setenv("NZ_FLOW_PATH", "wave")
+    wave = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    before = nz.device.flow_walk_reruns()
+    monkeypatch.setenv("NZ_FLOW_PATH", "reg")
+    reg = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    rough = torch.rand(rows, width, device="cuda")                 # white noise: every cell divides, many drain
+    reg_rough = nz.device.flowmap(rough.clone(), torch.empty_like(rough), None, iters, -0.1, 0.1).clone()
+    monkeypatch.setenv("NZ_FLOW_PATH", "wave")
+    wave_rough = nz.device.flowmap(rough.clone(), torch.empty_like(rough), None, iters, -0.1, 0.1).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(reg, wave)
+    assert torch.equal(reg_rough, wave_rough)
+    assert nz.device.flow_walk_reruns() == before
+
+
+def test_flow_register_walk_reruns_when_a_quotient_leaves_the_guard(nz, oracle, torch_cuda, monkeypatch):
+    """Heights near 1e37 push water / (sum * dt) into the denormals, where the reciprocal sequence is not exact: the launch
+    must notice, rerun on the wavefront kernel and still equal the per-iteration kernels bit for bit.  A degenerate or
+    negative normalisation range never reaches the register kernel."""
+    torch = torch_cuda
+    rows, width = 300, 400
+    h = (torch.rand(rows, width, device="cuda") * 3e37).contiguous()
+    h[100:140, 50:200] = 1e37                                      # a plateau: still water
+    monkeypatch.setenv("NZ_FLOW_UNFUSED", "1")
+    scratch = torch.empty(5 * rows * width * 4, dtype=torch.uint8, device="cuda")
+    plain = nz.device.flowmap(h.clone(), torch.empty_like(h), scratch, 5, 0.0, 0.005).clone()
+    monkeypatch.delenv("NZ_FLOW_UNFUSED")
+    before = nz.device.flow_walk_reruns()
+    got = nz.device.flowmap(h.clone(), torch.empty_like(h), None, 5, 0.0, 0.005).clone()
+    torch.cuda.synchronize()
+    assert nz.device.flow_walk_reruns() == before + 1
+    assert torch.equal(got, plain)
+    for nmin, nmax in ((0.25, 0.25), (0.1, -0.1), (0.0, 1e-9)):   # handled by the wavefront kernel from the start
+        a = nz.device.flowmap(h.clone() * 1e-37, torch.empty_like(h), None, 3, nmin, nmax).clone()
+        monkeypatch.setenv("NZ_FLOW_UNFUSED", "1")
+        b = nz.device.flowmap(h.clone() * 1e-37, torch.empty_like(h), scratch, 3, nmin, nmax).clone()
+        monkeypatch.delenv("NZ_FLOW_UNFUSED")
+        assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all()
+    assert nz.device.flow_walk_reruns() == before + 1
+
+
 def test_flow_row_band_with_ghost_rows_equals_full_grid_bitwise(nz, oracle, torch_cuda):
     torch = torch_cuda
     n, iters = 640, 5
