@@ -24,13 +24,15 @@ for path in ("walk", "fused", "generic"):
     d.kernel_filter(a, b, 2, 5)
 os.environ.pop("NZ_SEP_PATH")
 d.kernel_filter(a, b, 11, 1)
-for path, it in (("wave", 5), ("tile", 5), ("tile", 2), ("wave", 1)):
+for path, it in (("reg", 5), ("reg", 3), ("reg", 1), ("wave", 5), ("tile", 5), ("tile", 2), ("wave", 1)):
     os.environ["NZ_FLOW_PATH"] = path
     d.flowmap(a.clone(), b, None, it, 0.0, 0.005)
 os.environ.pop("NZ_FLOW_PATH")
 os.environ["NZ_FLOW_UNFUSED"] = "1"
 d.flowmap(a.clone(), b, torch.empty(5 * n * n * 4, dtype=torch.uint8, device="cuda"), 2, 0.0, 0.005)
 os.environ.pop("NZ_FLOW_UNFUSED")
+d.subtractive_flow_erosion(a.clone(), 2, 0.1, 0.0, 0.005)
+d.flowmap(a.clone() * 3e37, b, None, 5, 0.0, 0.005)   # leaves the register kernel's guard: rerun on the wavefront kernel
 d.min_erosion(a, b, 5)
 d.thermal_erosion(a, 45.0, 0.5, 0.75, 2)
 d.constant(a, 0, 0.5); d.reduce(a, b, 3); d.curve(a, torch.linspace(0, 1, 64, device="cuda")); d.normalize(a, 0.1, 0.5)
