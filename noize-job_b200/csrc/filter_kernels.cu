@@ -58,6 +58,28 @@ __global__ void __launch_bounds__(TX) sep_z_kernel(const float* __restrict__ src
 //   A = Z{1,2,1}( X{-1,0,1}(src) ),  B = Z{1,0,-1}( X{1,2,1}(src) ),  out = sqrt(A*A + B*B)
 // fused into one 3x3 pass in the exact order of the two separable branches.
 // ---------------------------------------------------------------------------------------------
+// the two X passes of one cell (taps HX {-1,0,1} and VX {1,2,1}, accumulated from 0 in tap order, factor 1)
+__device__ __forceinline__ void sobel_x(float l, float c, float rr, float& a, float& b) {
+    float ta = fmaf(l, -1.0f, 0.0f);
+    ta = fmaf(c, 0.0f, ta);
+    ta = fmaf(rr, 1.0f, ta);
+    a = ta * 1.0f;
+    float tb = fmaf(l, 1.0f, 0.0f);
+    tb = fmaf(c, 2.0f, tb);
+    tb = fmaf(rr, 1.0f, tb);
+    b = tb * 1.0f;
+}
+// the two Z passes (descending k: taps pair K[0] with z+1, K[1] with z, K[2] with z-1) and the root-sum-squares
+__device__ __forceinline__ float sobel_z(float a0, float a1, float a2, float b0, float b1, float b2) {
+    float A = fmaf(a2, 1.0f, 0.0f);
+    A = fmaf(a1, 2.0f, A);
+    A = fmaf(a0, 1.0f, A);
+    float B = fmaf(b2, 1.0f, 0.0f);
+    B = fmaf(b1, 0.0f, B);
+    B = fmaf(b0, -1.0f, B);
+    return sqrtf(fmaf(B, B, A * A));
+}
+
 __global__ void __launch_bounds__(TX) sobel2d_kernel(const float* __restrict__ src, float* __restrict__ dst, int width,
                                                      int rows) {
     const int z = blockIdx.y;
@@ -68,26 +90,65 @@ __global__ void __launch_bounds__(TX) sobel2d_kernel(const float* __restrict__ s
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const float* row = src + (size_t)clampi(z + j - 1, 0, rows - 1) * width;
-        const float l = __ldg(row + xl), c = __ldg(row + x), rr = __ldg(row + xr);
-        // total = 0; total = fma(v, K, total) for K = HX {-1,0,1}
-        float ta = fmaf(l, -1.0f, 0.0f);
-        ta = fmaf(c, 0.0f, ta);
-        ta = fmaf(rr, 1.0f, ta);
-        ax[j] = ta * 1.0f;
-        // VX {1,2,1}
-        float tb = fmaf(l, 1.0f, 0.0f);
-        tb = fmaf(c, 2.0f, tb);
-        tb = fmaf(rr, 1.0f, tb);
-        bx[j] = tb * 1.0f;
+        sobel_x(__ldg(row + xl), __ldg(row + x), __ldg(row + xr), ax[j], bx[j]);
     }
-    // Z pass, descending k: taps pair K[0] with z+1, K[1] with z, K[2] with z-1
-    float A = fmaf(ax[2], 1.0f, 0.0f);
-    A = fmaf(ax[1], 2.0f, A);
-    A = fmaf(ax[0], 1.0f, A);
-    float B = fmaf(bx[2], 1.0f, 0.0f);
-    B = fmaf(bx[1], 0.0f, B);
-    B = fmaf(bx[0], -1.0f, B);
-    dst[(size_t)z * width + x] = sqrtf(fmaf(B, B, A * A));
+    dst[(size_t)z * width + x] = sobel_z(ax[0], ax[1], ax[2], bx[0], bx[1], bx[2]);
+}
+
+// Row walk: a warp owns a 128-column strip (lane = 4 adjacent columns, one float4 per row) and streams down a chunk of
+// rows keeping the X-pass results of the last three rows in registers: 4 B read + 4 B written per cell (+ 2 rows per
+// chunk), west/east neighbours by shuffle (the strip's outer neighbours are one scalar load in lanes 0 and 31).
+constexpr int SW_WARPS = 4, SW_ZC = 64, SW_PF = 3;
+__global__ void __launch_bounds__(SW_WARPS * 32) sobel2d_walk_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                     int width, int rows) {
+    const int lane = threadIdx.x & 31;
+    const int x0 = (blockIdx.x * SW_WARPS + (threadIdx.x >> 5)) * 128;
+    if (x0 >= width) return;
+    const int gx = x0 + 4 * lane;
+    const bool in = gx < width;                           // width % 4 == 0: a lane's columns are all in or all out
+    const int zc0 = blockIdx.y * SW_ZC, zc1 = min(zc0 + SW_ZC, rows);
+    const int ex = lane == 0 ? max(x0 - 1, 0) : min(x0 + 128, width - 1);   // outer neighbour column (lanes 0 / 31)
+    const bool has_e = lane == 0 || lane == 31;
+
+    auto load = [&](int r, float4& v, float& e) {
+        const float* row = src + (size_t)clampi(r, 0, rows - 1) * width;
+        v = in ? __ldg(reinterpret_cast<const float4*>(row + gx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        e = has_e ? __ldg(row + ex) : 0.0f;
+    };
+    float4 pv[SW_PF];
+    float pe[SW_PF];
+#pragma unroll
+    for (int j = 0; j < SW_PF; j++) load(zc0 - 1 + j, pv[j], pe[j]);
+    float ax[3][4], bx[3][4];
+    // rows r = zc0-1 .. zc1 ; row r lands in window slot (r - (zc0-1)) % 3 ; after row r the row r-1 is complete
+    for (int base = zc0 - 1; base <= zc1; base += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int r = base + u;
+            if (r <= zc1) {
+                const float4 v = pv[u];
+                const float e = pe[u];
+                load(r + SW_PF, pv[u], pe[u]);           // SW_PF == 3: the slot just consumed
+                float L = __shfl_up_sync(0xffffffffu, v.w, 1), R = __shfl_down_sync(0xffffffffu, v.x, 1);
+                if (lane == 0) L = e;
+                if (lane == 31) R = e;
+                if (gx == 0) L = v.x;
+                if (gx + 4 >= width) R = v.w;
+                sobel_x(L, v.x, v.y, ax[u][0], bx[u][0]);
+                sobel_x(v.x, v.y, v.z, ax[u][1], bx[u][1]);
+                sobel_x(v.y, v.z, v.w, ax[u][2], bx[u][2]);
+                sobel_x(v.z, v.w, R, ax[u][3], bx[u][3]);
+                const int z = r - 1;                      // rows z-1, z, z+1 sit in slots (u+1)%3, (u+2)%3, u
+                if (z >= zc0 && in) {
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        o[q] = sobel_z(ax[(u + 1) % 3][q], ax[(u + 2) % 3][q], ax[u][q], bx[(u + 1) % 3][q], bx[(u + 2) % 3][q], bx[u][q]);
+                    *reinterpret_cast<float4*>(dst + (size_t)z * width + gx) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -238,8 +299,15 @@ int32_t launch_sobel2d(float* d_data, float* d_tmp, int width, int rows, int ite
     NZ_REQUIRE(width > 0 && rows > 0 && rows <= 65535 && iterations >= 0, "sobel2d: bad arguments");
     dim3 grid(cdiv(width, TX), rows);
     float *a = d_data, *b = d_tmp;
+    // NZ_SOBEL_PATH=plain forces the one-thread-per-cell kernel (the tests compare the two bit for bit)
+    const char* sp = getenv("NZ_SOBEL_PATH");
+    const bool walk = !(sp && sp[0] == 'p') && (width & 3) == 0 && (((uintptr_t)d_data | (uintptr_t)d_tmp) & 15) == 0;
     for (int it = 0; it < iterations; it++) {
-        sobel2d_kernel<<<grid, TX, 0, s>>>(a, b, width, rows);
+        if (walk) {
+            dim3 wgrid(cdiv(cdiv(width, 128), SW_WARPS), cdiv(rows, SW_ZC));
+            sobel2d_walk_kernel<<<wgrid, SW_WARPS * 32, 0, s>>>(a, b, width, rows);
+        } else
+            sobel2d_kernel<<<grid, TX, 0, s>>>(a, b, width, rows);
         NZ_LAUNCHED();
         float* t = a; a = b; b = t;
     }

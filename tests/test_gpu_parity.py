@@ -301,6 +301,21 @@ def test_flow_tile_kernel_equals_wavefront_kernel_bitwise(nz, oracle, torch_cuda
     assert torch.equal(tile, wave)
 
 
+@pytest.mark.parametrize("rows,width", [(70, 128), (200, 516), (65, 4), (1, 260), (130, 1024), (257, 2052)])
+def test_sobel_walk_kernel_equals_plain_kernel_bitwise(nz, oracle, torch_cuda, monkeypatch, rows, width):
+    """Sobel3_2D as a register row walk (float4 strips, 64-row chunks) against the one-thread-per-cell kernel and the
+    oracle: strip and chunk seams, grid borders, partial strips, two iterations."""
+    torch = torch_cuda
+    h = torch.from_numpy(rand_grid(rows, width)).cuda()
+    walk = nz.device.kernel_filter(h.clone(), torch.empty_like(h), 11, 2).clone()
+    monkeypatch.setenv("NZ_SOBEL_PATH", "plain")
+    plain = nz.device.kernel_filter(h.clone(), torch.empty_like(h), 11, 2).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(walk, plain)
+    ref = oracle.kernel_filter(h.cpu().numpy(), 11, 2)
+    assert np.abs(walk.cpu().numpy() - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("rows,width,iters", [(700, 600, 5), (300, 1000, 4), (97, 236, 3), (40, 20, 2), (513, 472, 1), (33, 4, 5),
                                               (1100, 1304, 5), (64, 44, 5), (600, 88, 5), (260, 132, 5), (2100, 2048, 5)])
 def test_flow_register_walk_kernel_equals_wavefront_kernel_bitwise(nz, oracle, torch_cuda, monkeypatch, rows, width, iters):
