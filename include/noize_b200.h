@@ -331,8 +331,11 @@ NZ_API size_t  nz_dev_subtractive_flow_scratch_bytes(int32_t width, int32_t rows
 NZ_API int32_t nz_dev_subtractive_flow_erosion(float* d_height, void* d_scratch, int32_t width, int32_t rows,
                                                int32_t erosive_iterations, float erosive_factor,
                                                float norm_min, float norm_max, void* stream);
-NZ_API int32_t nz_dev_thermal_erosion(float* d_data, int32_t resolution, float talus, float increment_ratio,
-                                      float mesh_height_width_ratio, int32_t iterations, void* stream);
+/* d_tmp (may be NULL): ping-pong partner of d_data; with it each iteration is one fused launch (the four phases on a
+ * shared-memory tile) and the result lands in *d_result (d_data or d_tmp; copied back into d_data when d_result is
+ * NULL).  Without it the phases are four in-place launches per iteration. */
+NZ_API int32_t nz_dev_thermal_erosion(float* d_data, float* d_tmp, int32_t resolution, float talus, float increment_ratio,
+                                      float mesh_height_width_ratio, int32_t iterations, float** d_result, void* stream);
 NZ_API int32_t nz_dev_constant(float* d_data, size_t n, int32_t operation, float constant_value, void* stream);
 NZ_API int32_t nz_dev_reduce(float* d_left, const float* d_right, size_t n, int32_t operation, void* stream);
 NZ_API int32_t nz_dev_curve(float* d_data, size_t n, const float* d_curve, int32_t curve_size, void* stream);

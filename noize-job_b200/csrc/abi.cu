@@ -542,11 +542,13 @@ NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32
                        h_row_first, h_rows, vz_begin, vz_end, (cudaStream_t)stream);
 }
 
-NZ_API int32_t nz_dev_thermal_erosion(float* d_data, int32_t resolution, float talus, float increment_ratio,
-                                      float mesh_height_width_ratio, int32_t iterations, void* stream) {
+NZ_API int32_t nz_dev_thermal_erosion(float* d_data, float* d_tmp, int32_t resolution, float talus, float increment_ratio,
+                                      float mesh_height_width_ratio, int32_t iterations, float** d_result, void* stream) {
     NZ_REQUIRE(d_data && resolution > 0, "nz_dev_thermal_erosion: bad arguments");
     NZ_REQUIRE(iterations >= 0, "nz_dev_thermal_erosion: iterations %d < 0", iterations);
-    return launch_thermal_erosion(d_data, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, (cudaStream_t)stream);
+    NZ_REQUIRE(d_tmp != d_data, "nz_dev_thermal_erosion: d_tmp aliases d_data");
+    return launch_thermal_erosion(d_data, d_tmp, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, d_result,
+                                  (cudaStream_t)stream);
 }
 NZ_API size_t nz_dev_subtractive_flow_scratch_bytes(int32_t width, int32_t rows) {
     if (width <= 0 || rows <= 0) return 0;
@@ -898,8 +900,9 @@ extern "C" {
 NZ_API int32_t nz_thermal_erosion(nz_slice_f32 src, float talus, float increment_ratio, float mesh_height_width_ratio,
                                   int32_t iterations, int32_t resolution) {
     NZ_REQUIRE(iterations >= 0, "nz_thermal_erosion: iterations %d < 0", iterations);
-    return run_inplace_stage(src, resolution, "nz_thermal_erosion", false, [&](Mirror& m, float**) {
-        return launch_thermal_erosion(m.d, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, t_state.stream);
+    return run_inplace_stage(src, resolution, "nz_thermal_erosion", true, [&](Mirror& m, float** res) {
+        return launch_thermal_erosion(m.d, m.d_tmp, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, res,
+                                      t_state.stream);
     });
 }
 

@@ -92,8 +92,8 @@ int32_t launch_mesh(int mesh_type, void* d_vtx, uint32_t* d_idx, int R, int inRe
                     float tile_size, const float* d_heights, int h_row_first, int h_rows, int vz_begin, int vz_end,
                     cudaStream_t s);
 float thermal_max_diff(float talus_deg, float height_ratio, int resolution);
-int32_t launch_thermal_erosion(float* d_data, int res, float talus_deg, float increment, float height_ratio, int iterations,
-                               cudaStream_t s);
+int32_t launch_thermal_erosion(float* d_data, float* d_tmp, int res, float talus_deg, float increment, float height_ratio,
+                               int iterations, float** d_result, cudaStream_t s);
 int32_t launch_constant(float* d, size_t n, int op, float value, cudaStream_t s);
 int32_t launch_reduce(float* d_left, const float* d_right, size_t n, int op, cudaStream_t s);
 int32_t launch_curve(float* d, size_t n, const float* d_curve, int curve_size, cudaStream_t s);

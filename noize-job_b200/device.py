@@ -99,12 +99,19 @@ def heightmap_mesh(mesh_type, vertices, indices, resolution, input_resolution, m
 
 
 # ---- SURVEY.md section 8f rows (all in place on a square or rectangular device grid) -----------------------
-def thermal_erosion(data, talus=45.0, increment_ratio=0.5, mesh_height_width_ratio=0.75, iterations=1, stream=None):
+def thermal_erosion(data, talus=45.0, increment_ratio=0.5, mesh_height_width_ratio=0.75, iterations=1, stream=None, tmp=None):
+    """Without `tmp`: in place (four launches per iteration).  With `tmp` (same shape): one fused launch per iteration,
+    ping-pong; returns the tensor (data or tmp) that holds the result."""
     _grid(data, "data")
     assert data.shape[0] == data.shape[1], "thermal erosion works on a square tile"
-    _l.check(_l.load().nz_dev_thermal_erosion(data.data_ptr(), data.shape[0], talus, increment_ratio, mesh_height_width_ratio,
-                                              iterations, _l.stream_ptr(stream)))
-    return data
+    if tmp is not None:
+        _grid(tmp, "tmp")
+        assert tmp.shape == data.shape
+    res = C.c_void_p()
+    _l.check(_l.load().nz_dev_thermal_erosion(data.data_ptr(), None if tmp is None else tmp.data_ptr(), data.shape[0], talus,
+                                              increment_ratio, mesh_height_width_ratio, iterations, C.byref(res),
+                                              _l.stream_ptr(stream)))
+    return tmp if tmp is not None and res.value == tmp.data_ptr() else data
 
 
 def subtractive_flow_erosion(height, erosive_iterations=5, erosive_factor=0.1, norm_min=-0.1, norm_max=0.1, stream=None):

@@ -83,7 +83,7 @@ SIGNATURES = {
     "nz_dev_flowmap": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, C.POINTER(_vp), _vp]),
     "nz_dev_flow_walk_reruns": (_i32, [C.POINTER(C.c_uint64)]),
     "nz_dev_heightmap_mesh": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "nz_dev_thermal_erosion": (_i32, [_vp, _i32, _f32, _f32, _f32, _i32, _vp]),
+    "nz_dev_thermal_erosion": (_i32, [_vp, _vp, _i32, _f32, _f32, _f32, _i32, C.POINTER(_vp), _vp]),
     "nz_dev_subtractive_flow_scratch_bytes": (_sz, [_i32, _i32]),
     "nz_dev_subtractive_flow_erosion": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp]),
     "nz_dev_constant": (_i32, [_vp, _sz, _i32, _f32, _vp]),

@@ -36,6 +36,22 @@ def test_thermal_erosion_on_smooth_terrain_and_device_layer(nz, oracle):
     assert np.array_equal(bits(t.cpu().numpy()), bits(ref))
 
 
+@pytest.mark.parametrize("res,iters,talus", [(64, 1, 45), (257, 2, 30), (1024, 3, 60), (130, 8, 10), (131, 3, 20), (6, 2, 45),
+                                             (3, 1, 45), (200, 5, 5), (1500, 2, 25)])
+def test_thermal_erosion_fused_tile_kernel_bit_exact(nz, oracle, res, iters, talus):
+    """One launch per iteration (the four phases on a shared-memory tile with a 4-cell halo, ping-pong buffers) against
+    the oracle and, through it, the four-launch path: tile seams, odd resolutions, grids smaller than a tile."""
+    import torch
+    g = rnd(res, res + iters)
+    t, tmp = torch.from_numpy(g).cuda(), torch.full((res, res), float("nan"), device="cuda")
+    out = nz.device.thermal_erosion(t, float(talus), 0.5, 0.75, iters, tmp=tmp)
+    ref = oracle.thermal_erosion(g, talus, 0.5, 0.75, iters)
+    assert np.array_equal(bits(out.cpu().numpy()), bits(ref))
+    inplace = torch.from_numpy(g).cuda()
+    nz.device.thermal_erosion(inplace, float(talus), 0.5, 0.75, iters)
+    assert torch.equal(out, inplace)
+
+
 @pytest.mark.parametrize("res", [33, 256])
 def test_constant_reduce_bit_exact(nz, oracle, res):
     a, b = rnd(res, 1), rnd(res, 2, -0.5, 0.5)

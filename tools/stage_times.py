@@ -52,7 +52,10 @@ def main():
     d.fractal(a, 3, 0.4, octaves=13, noise_size=1700)
     d.fractal(b, 1, 0.4, octaves=2, noise_size=1700)
     ms = timeit(lambda: d.thermal_erosion(a, 45.0, 0.5, 0.75, 1), reps)
-    rows.append(("thermal x1", ms, 32 * cells))
+    rows.append(("thermal x1 (4 phase launches)", ms, 32 * cells))
+    ms = timeit(lambda: d.thermal_erosion(a, 45.0, 0.5, 0.75, 1, tmp=b), reps)
+    rows.append(("thermal x1 (fused tile)", ms, 8 * cells))
+    d.fractal(b, 1, 0.4, octaves=2, noise_size=1700)
     # subtractive-flow erosion, 3 cycles = 1 + 2 + 3 flow iterations on per-iteration kernels: 64 + 144 + 208 B/cell
     # (outflow step 20/36/40 B, water step 20/24 B, fused erosion epilogue 24 B)
     ms = timeit(lambda: d.subtractive_flow_erosion(a, 3, 0.001, 0.0, 0.005), max(2, reps // 4))
