@@ -206,6 +206,9 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    numa = bands.bind_host_to_gpu_numa_node(local) if world > 1 else ""
+    if numa:
+        print(f"[rank {rank}] {numa}", file=sys.stderr)
     nz.host.init(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

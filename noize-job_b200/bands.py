@@ -249,3 +249,32 @@ class BandChain:
     def owned(self, buf=None):
         buf = self.result if buf is None else buf
         return buf[self.above: self.above + self.own]
+
+def bind_host_to_gpu_numa_node(device_index):
+    """Pin this process (and so the pages of every pinned host buffer it allocates afterwards: first touch) to the NUMA
+    node the GPU hangs off.  With one process per GPU and 20 GB of mesh per step going device -> host, buffers that
+    land on the other socket make every rank's download cross the inter-socket link.  Returns a short description of
+    what was done ('' when the topology cannot be read: the process is left alone)."""
+    import glob
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        paths = glob.glob(f"/sys/bus/pci/devices/{bus}/numa_node")
+        if not paths:
+            return ""
+        node = int(open(paths[0]).read().strip())
+        if node < 0:
+            return ""
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return ""
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {device_index} ({bus}) -> numa node {node}, {len(cpus)} cpus"
+    except Exception:                      # unreadable sysfs, no such attribute: not an error for the caller
+        return ""
