@@ -365,6 +365,29 @@ def test_flow_register_walk_reruns_when_a_quotient_leaves_the_guard(nz, oracle, 
     assert nz.device.flow_walk_reruns() == before + 1
 
 
+def test_flow_register_walk_rerun_flags_are_per_launch_on_concurrent_streams(nz, oracle, torch_cuda):
+    """Four flow maps in flight on four streams, one of them leaving the guard: only that launch is rerun, and every
+    result equals what the same call gives alone (the rerun flag is one word per launch, not per device)."""
+    torch = torch_cuda
+    rows, width = 512, 768
+    hs = [torch.rand(rows, width, device="cuda") * (3e37 if i == 2 else 0.05 * (i + 1)) for i in range(4)]
+    alone = [nz.device.flowmap(h.clone(), torch.empty_like(h), None, 5, 0.0, 0.005).clone() for h in hs]
+    torch.cuda.synchronize()
+    before = nz.device.flow_walk_reruns()
+    streams = [torch.cuda.Stream() for _ in hs]
+    outs, keep = [None] * 4, []
+    for rep in range(3):
+        for i, (h, st) in enumerate(zip(hs, streams)):
+            with torch.cuda.stream(st):
+                a, b = h.clone(), torch.empty_like(h)
+                keep.append((a, b))
+                outs[i] = nz.device.flowmap(a, b, None, 5, 0.0, 0.005, stream=st)
+    torch.cuda.synchronize()
+    for got, want in zip(outs, alone):
+        assert torch.equal(got, want)
+    assert nz.device.flow_walk_reruns() == before + 3
+
+
 def test_flow_row_band_with_ghost_rows_equals_full_grid_bitwise(nz, oracle, torch_cuda):
     torch = torch_cuda
     n, iters = 640, 5
