@@ -230,8 +230,24 @@ __device__ __forceinline__ float psrnoise2(float posx, float posy, float perx, f
     float d1x = posx - p1x, d1y = posy - p1y;
     float d2x = posx - p2x, d2y = posy - p2y;
     const float ipx = 1.0f / perx, ipy = 1.0f / pery;      // compile-time constants at both call sites
-    float xw0 = fmod_period<FAST>(p0x, perx, ipx), xw1 = fmod_period<FAST>(p1x, perx, ipx), xw2 = fmod_period<FAST>(p2x, perx, ipx);
-    float yw0 = fmod_period<FAST>(p0y, pery, ipy), yw1 = fmod_period<FAST>(p1y, pery, ipy), yw2 = fmod_period<FAST>(p2y, pery, ipy);
+    float xw0 = fmod_period<FAST>(p0x, perx, ipx), yw0 = fmod_period<FAST>(p0y, pery, ipy);
+    float xw1, xw2, yw1, yw2;
+    if (FAST && p0x >= 1.0f && p0y >= 0.0f) {
+        // All three corners are non-negative here (p1x >= p0x - 0.5, p1y >= p0y, p2 = p0 + (0.5, 1)), every value is a
+        // multiple of 0.5 below 2^22 (exact), and the corners differ by less than one period, so the other two residues
+        // are the first one plus the offset with ONE wrap: the same values fmod gives, for 11 instructions instead of 40.
+        yw2 = yw0 + 1.0f;
+        yw2 = yw2 >= pery ? yw2 - pery : yw2;
+        yw1 = c ? yw0 : yw2;                                  // i1y = c ? 0 : 1
+        xw2 = xw0 + 0.5f;
+        xw2 = xw2 >= perx ? xw2 - perx : xw2;
+        xw1 = xw0 + (c ? 1.0f : -0.5f);                       // i1x - 0.5*i1y
+        xw1 = xw1 >= perx ? xw1 - perx : xw1;
+        xw1 = xw1 < 0.0f ? xw1 + perx : xw1;
+    } else {
+        xw1 = fmod_period<FAST>(p1x, perx, ipx); xw2 = fmod_period<FAST>(p2x, perx, ipx);
+        yw1 = fmod_period<FAST>(p1y, pery, ipy); yw2 = fmod_period<FAST>(p2y, pery, ipy);
+    }
     float g0x, g0y, g1x, g1y, g2x, g2y;
     rgrad2<TYPE, FAST>(fmaf(0.5f, yw0, xw0), yw0, rtab, g0x, g0y);
     rgrad2<TYPE, FAST>(fmaf(0.5f, yw1, xw1), yw1, rtab, g1x, g1y);
