@@ -301,7 +301,10 @@ int32_t launch_sobel2d(float* d_data, float* d_tmp, int width, int rows, int ite
     float *a = d_data, *b = d_tmp;
     // NZ_SOBEL_PATH=plain forces the one-thread-per-cell kernel (the tests compare the two bit for bit)
     const char* sp = getenv("NZ_SOBEL_PATH");
-    const bool walk = !(sp && sp[0] == 'p') && (width & 3) == 0 && (((uintptr_t)d_data | (uintptr_t)d_tmp) & 15) == 0;
+    // the walk needs ~600 warps of 64-row chunks to fill the machine: below 4M cells the per-cell kernel's parallelism wins
+    // (NZ_SOBEL_PATH=walk forces the walk, for the tests)
+    const bool big = (long long)width * rows >= (1LL << 22) || (sp && sp[0] == 'w');
+    const bool walk = big && !(sp && sp[0] == 'p') && (width & 3) == 0 && (((uintptr_t)d_data | (uintptr_t)d_tmp) & 15) == 0;
     for (int it = 0; it < iterations; it++) {
         if (walk) {
             dim3 wgrid(cdiv(cdiv(width, 128), SW_WARPS), cdiv(rows, SW_ZC));

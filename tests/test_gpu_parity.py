@@ -307,6 +307,7 @@ def test_sobel_walk_kernel_equals_plain_kernel_bitwise(nz, oracle, torch_cuda, m
     oracle: strip and chunk seams, grid borders, partial strips, two iterations."""
     torch = torch_cuda
     h = torch.from_numpy(rand_grid(rows, width)).cuda()
+    monkeypatch.setenv("NZ_SOBEL_PATH", "walk")                   # grids under 4M cells take the per-cell kernel by default
     walk = nz.device.kernel_filter(h.clone(), torch.empty_like(h), 11, 2).clone()
     monkeypatch.setenv("NZ_SOBEL_PATH", "plain")
     plain = nz.device.kernel_filter(h.clone(), torch.empty_like(h), 11, 2).clone()
