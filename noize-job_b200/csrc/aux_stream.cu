@@ -1,0 +1,68 @@
+// aux_stream.cu — a side stream per (host thread, device) for launches that are independent of the next launch on the
+// caller's stream.  The register-walk kernels (flowwalk_kernels.cu, sepwalk_kernels.cu) run their border warps as a
+// separate, short launch; enqueued on the caller's stream it would serialise with the interior launch (one chunk walk of
+// latency, ~35-90 us, per launch); forked onto the side stream it runs underneath it.
+//   aux_fork(main, &aux): everything enqueued on `main` so far happens before what is enqueued on `aux` next
+//   aux_join(main)      : everything enqueued on `aux` so far happens before what is enqueued on `main` next
+// Both are event record/wait pairs (legal inside stream capture).  NZ_NO_AUX_STREAM=1 makes aux == main.
+#include <stdlib.h>
+#include "nz_common.cuh"
+
+namespace nz {
+namespace {
+
+struct Aux {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local Aux t_aux[64];
+
+int32_t get_aux(Aux** out) {
+    int dev = 0;
+    NZ_CUDA(cudaGetDevice(&dev));
+    NZ_REQUIRE(dev >= 0 && dev < 64, "aux stream: device ordinal %d out of range", dev);
+    Aux& a = t_aux[dev];
+    if (!a.s) {
+        NZ_CUDA(cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking));
+        NZ_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+        NZ_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+    }
+    *out = &a;
+    return NZ_OK;
+}
+
+bool aux_disabled() {
+    static const bool off = [] {
+        const char* e = getenv("NZ_NO_AUX_STREAM");
+        return e && e[0] == '1';
+    }();
+    return off;
+}
+
+}  // namespace
+
+int32_t aux_fork(cudaStream_t main, cudaStream_t* aux) {
+    if (aux_disabled()) {
+        *aux = main;
+        return NZ_OK;
+    }
+    Aux* a;
+    int32_t rc = get_aux(&a);
+    if (rc != NZ_OK) return rc;
+    NZ_CUDA(cudaEventRecord(a->fork, main));
+    NZ_CUDA(cudaStreamWaitEvent(a->s, a->fork, 0));
+    *aux = a->s;
+    return NZ_OK;
+}
+
+int32_t aux_join(cudaStream_t main) {
+    if (aux_disabled()) return NZ_OK;
+    Aux* a;
+    int32_t rc = get_aux(&a);
+    if (rc != NZ_OK) return rc;
+    NZ_CUDA(cudaEventRecord(a->join, a->s));
+    NZ_CUDA(cudaStreamWaitEvent(main, a->join, 0));
+    return NZ_OK;
+}
+
+}  // namespace nz

@@ -104,6 +104,10 @@ int32_t launch_map_range(const float* d, size_t n, float lim_min, float lim_max,
 int32_t launch_fma_peak(float* d_sink, int grid, int iters, double* flops, cudaStream_t s);
 int32_t launch_gather_strided(float* d_dst, const unsigned char* d_src, int stride_bytes, size_t n, cudaStream_t s);
 
+// side stream of the calling thread on the current device (aux_stream.cu)
+int32_t aux_fork(cudaStream_t main, cudaStream_t* aux);
+int32_t aux_join(cudaStream_t main);
+
 // host-side table helpers (tables.cpp part of abi.cu)
 void gauss_table(double sigma, int width, float* out);
 int32_t kernel_filter_table(int filter, float* kx, float* kz, int* ksize, float* factor);

@@ -194,24 +194,59 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     }
 }
 
+// Interior and border warps are separate LAUNCHES: the clamp logic of the border body raises the kernel from 96 to 128
+// registers, and in one kernel every warp pays for it in occupancy (Gauss5 x17 at 16384^2: 3.19 ms combined, 2.56 ms for
+// the interior body alone, with 3 % of the warps on a border).
+struct WalkRanges {
+    int s_lo, s_hi, r_lo, r_hi;   // interior launch: strips [s_lo, s_hi) x rows [r_lo, r_hi) in chunks of zc
+    int ns, zcb;                  // border launch: flat (strip, chunk) items in chunks of zcb over the rest of the grid
+    int n_top, n_bot, n_items;    //   all strips x [0, r_lo), all strips x [r_hi, H), border strips x [r_lo, r_hi)
+};
+
 template <int R, int T, bool SCALE, int PFR>
-__global__ void __launch_bounds__(WALK_WARPS * 32)
+__global__ void __launch_bounds__(WALK_WARPS * 32, 5)
 sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz,
-                int zc) {
+                int zc, WalkRanges g) {
     constexpr int HALO = (R * T + 3) & ~3;
     constexpr int USE = STRIP - 2 * HALO;
-    const int strip = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
+    const int strip = g.s_lo + blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
+    if (strip >= g.s_hi) return;                 // whole warp
     const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
-    if (wx0 + HALO >= W) return;                 // whole warp: nothing to produce
-    const int zc0 = blockIdx.y * zc, zc1 = min(zc0 + zc, H);
-    // steady state: the strip lies inside the grid and so does the chunk with its warm-up and drain rows
-    const bool plain = wx0 >= 0 && wx0 + STRIP <= W && zc0 - R * T - (2 * R + 1) > 0 && zc1 - 1 + R * T <= H - 1;
+    const int zc0 = g.r_lo + blockIdx.y * zc, zc1 = min(zc0 + zc, g.r_hi);
+    // the host chose the ranges so that the strip lies inside the grid and so does the chunk with its warm-up and drain rows
     extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP]
     const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (PFR * STRIP));
-    if (plain)
-        walk_body<R, T, SCALE, false, PFR>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
-    else
-        walk_body<R, T, SCALE, true, PFR>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+    walk_body<R, T, SCALE, false, PFR>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+}
+
+template <int R, int T, bool SCALE>
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+sep_walk_border_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx,
+                       TapsW<R> kz, WalkRanges g) {
+    constexpr int HALO = (R * T + 3) & ~3;
+    constexpr int USE = STRIP - 2 * HALO;
+    int item = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
+    if (item >= g.n_items) return;
+    int strip, zc0, zc1;
+    if (item < g.n_top) {
+        strip = item % g.ns;
+        zc0 = (item / g.ns) * g.zcb;
+        zc1 = min(zc0 + g.zcb, g.r_lo);
+    } else if (item < g.n_top + g.n_bot) {
+        item -= g.n_top;
+        strip = item % g.ns;
+        zc0 = g.r_hi + (item / g.ns) * g.zcb;
+        zc1 = min(zc0 + g.zcb, H);
+    } else {
+        item -= g.n_top + g.n_bot;
+        const int nbs = g.s_lo + (g.ns - g.s_hi);
+        const int b = item % nbs;
+        strip = b < g.s_lo ? b : g.s_hi + (b - g.s_lo);
+        zc0 = g.r_lo + (item / nbs) * g.zcb;
+        zc1 = min(zc0 + g.zcb, g.r_hi);
+    }
+    const int wx0 = strip * USE - HALO;
+    walk_body<R, T, SCALE, true, 2>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, 0u);   // the border body does not use the ring
 }
 
 template <int R, int T>
@@ -227,7 +262,38 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     const char* ez = getenv("NZ_WALK_ZC");
     const char* ep = getenv("NZ_WALK_PFR");
     const int pfr = ep ? atoi(ep) : 16;
-    const int ctas_x = cdiv(cdiv(width, USE), WALK_WARPS);
+    // ranges: strip k covers grid columns [k*USE - HALO, k*USE - HALO + 128); interior strips lie inside the grid, interior
+    // rows leave a band of WB rows (> R*T + 2R + 1) at the top and the bottom to the border launch
+    constexpr int WB = 32;
+    WalkRanges g;
+    g.ns = cdiv(width, USE);
+    g.s_lo = 1; g.s_hi = 0;
+    for (int k = g.ns - 1; k >= 1; k--)
+        if (k * USE - HALO + STRIP <= width) { g.s_hi = k + 1; break; }
+    g.r_lo = WB; g.r_hi = rows - WB;
+    if (g.s_hi <= g.s_lo || g.r_hi - g.r_lo < 32) { g.s_lo = g.s_hi = 0; g.r_lo = g.r_hi = rows; }
+    g.zcb = WB;
+    g.n_top = g.ns * cdiv(g.r_lo, g.zcb);
+    g.n_bot = g.ns * cdiv(rows - g.r_hi, g.zcb);
+    g.n_items = g.n_top + g.n_bot + (g.s_lo + (g.ns - g.s_hi)) * cdiv(g.r_hi - g.r_lo, g.zcb);
+    // the border launch reads the same input and writes other cells than the interior launch: it runs underneath it on
+    // the side stream when there is an interior launch to hide it under
+    const bool forked = g.n_items > 0 && g.s_hi > g.s_lo;
+    if (g.n_items > 0) {
+        cudaStream_t bs = s;
+        if (forked) {
+            int32_t rc = aux_fork(s, &bs);
+            if (rc != NZ_OK) return rc;
+        }
+        if (factor == 1.0f)
+            sep_walk_border_kernel<R, T, false><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, 0, bs>>>(in, out, width, rows, factor, tx, tz, g);
+        else
+            sep_walk_border_kernel<R, T, true><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, 0, bs>>>(in, out, width, rows, factor, tx, tz, g);
+        NZ_LAUNCHED();
+    }
+    if (g.s_hi <= g.s_lo) return NZ_OK;
+    const int irows = g.r_hi - g.r_lo;
+    const int ctas_x = cdiv(g.s_hi - g.s_lo, WALK_WARPS);
     // Rows per chunk.  A CTA walks its chunk serially (~0.7 us per row), so the launch ends with a tail unless there are
     // several waves of CTAs: aim for ~8 waves of the resident slots, within [48, 128] rows (shorter chunks pay more
     // warm-up rows, R*T + 2R + 1 each).  Measured at width 16384: 16384 rows -> 128 (3.28 ms), 4164 -> 48 (1.05 ms vs
@@ -238,19 +304,19 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     } else {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        const int slots = sms * 4;                       // 4 CTAs of 128 threads x 128 registers per SM
+        const int slots = sms * 5;                       // 5 CTAs of 128 threads x 96 registers per SM
         const int chunks = cdiv(8LL * slots, ctas_x);
-        zc = cdiv(rows, chunks < 1 ? 1 : chunks);
+        zc = cdiv(irows, chunks < 1 ? 1 : chunks);
         zc = zc < 48 ? 48 : (zc > WALK_ZC ? WALK_ZC : zc);
         if (rows <= 1536 && zc < 64) zc = 64;
     }
-    dim3 grid(ctas_x, cdiv(rows, zc));
+    dim3 grid(ctas_x, cdiv(irows, zc));
 #define NZ_WALK_LAUNCH(SC, PF)                                                                                          \
     do {                                                                                                               \
         const size_t sm = (size_t)WALK_WARPS * PF * STRIP * sizeof(float);                                             \
         if (sm > 48 * 1024)                                                                                            \
             NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, SC, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-        sep_walk_kernel<R, T, SC, PF><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc);     \
+        sep_walk_kernel<R, T, SC, PF><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);  \
     } while (0)
     if (factor == 1.0f) {
         if (pfr == 8) NZ_WALK_LAUNCH(false, 8);
@@ -261,6 +327,7 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     }
 #undef NZ_WALK_LAUNCH
     NZ_LAUNCHED();
+    if (forked) return aux_join(s);
     return NZ_OK;
 }
 
