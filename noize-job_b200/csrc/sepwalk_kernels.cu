@@ -294,21 +294,26 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     if (g.s_hi <= g.s_lo) return NZ_OK;
     const int irows = g.r_hi - g.r_lo;
     const int ctas_x = cdiv(g.s_hi - g.s_lo, WALK_WARPS);
-    // Rows per chunk.  A CTA walks its chunk serially (~0.7 us per row), so the launch ends with a tail unless there are
-    // several waves of CTAs: aim for ~8 waves of the resident slots, within [48, 128] rows (shorter chunks pay more
-    // warm-up rows, R*T + 2R + 1 each).  Measured at width 16384: 16384 rows -> 128 (3.28 ms), 4164 -> 48 (1.05 ms vs
-    // 1.13 at 128), 2116 -> 48 (0.64 vs 0.69), 1024 -> 64 (0.40 vs 0.57).
+    // Rows per chunk.  A CTA walks its chunk serially and 5 CTAs are resident per SM, so the launch takes about
+    // waves x (zc + warm-up rows) steps: take the chunk count that minimises it, within [48, 448] rows.  Measured at
+    // 16384^2 (Gauss5 x17, ms): 64 2.93, 96 2.77, 128 2.68, 192 2.66, 256 2.58, 408 2.57 (two whole waves), 544 2.70.
     int zc = WALK_ZC;
     if (ez) {
         zc = atoi(ez);
     } else {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        const int slots = sms * 5;                       // 5 CTAs of 128 threads x 96 registers per SM
-        const int chunks = cdiv(8LL * slots, ctas_x);
-        zc = cdiv(irows, chunks < 1 ? 1 : chunks);
-        zc = zc < 48 ? 48 : (zc > WALK_ZC ? WALK_ZC : zc);
-        if (rows <= 1536 && zc < 64) zc = 64;
+        const long long slots = 5LL * sms;               // 5 CTAs of 128 threads x 96 registers per SM
+        const int warm = R * T + 2 * R + 1 + 3;
+        double best = 1e300;
+        for (int n = cdiv(irows, 448); n <= irows; n++) {
+            const int z = cdiv(irows, n);
+            if (z < 48 && n > 1) break;
+            const long long ctas = (long long)ctas_x * cdiv(irows, z);
+            const long long waves = (ctas + slots - 1) / slots;
+            const double cost = (double)waves * (z + warm);
+            if (cost < best) { best = cost; zc = z; }
+        }
     }
     dim3 grid(ctas_x, cdiv(irows, zc));
 #define NZ_WALK_LAUNCH(SC, PF)                                                                                          \
