@@ -646,3 +646,39 @@ def test_residency_scope_spans_threads(nz, oracle):
         nz.host.scope_enter(scope)       # closed scopes are gone
     with pytest.raises(nz.NzError):
         nz.host.scope_leave()
+
+
+def test_concurrent_host_threads_with_side_streams(nz, oracle):
+    """Four host threads run the chain at a size where both walk kernels split into an interior launch and a border launch
+    forked onto the calling thread's side stream (>= 8M cells): every thread's result equals the same call made alone."""
+    import threading
+    res = 3072
+
+    def chain(zpos, out):
+        nz.host.fractal(out, res, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, zpos, 1700)
+        nz.host.kernel_filter(out, None, 2, res, 17)
+        nz.host.flowmap(out, res, 5, 0.0, 0.005)
+        nz.host.min_erosion(out, res, 5)
+
+    want = [np.zeros(res * res, np.float32) for _ in range(4)]
+    for i, w in enumerate(want):
+        chain(1000 * i, w)
+    got = [np.zeros(res * res, np.float32) for _ in range(4)]
+    errors = []
+
+    def run(i):
+        try:
+            for _ in range(2):
+                chain(1000 * i, got[i])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert len({w.tobytes()[:4096] for w in want}) == 4      # the four inputs really differ
