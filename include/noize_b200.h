@@ -142,8 +142,10 @@ typedef struct {
 
 /* ---- lifecycle / introspection ------------------------------------------------------ */
 
-/* Select the CUDA device(s) this process drives; devices==NULL or n==0 -> device 0.  Optional:
- * the first compute call initialises device 0 lazily.  Safe to call again (re-initialises). */
+/* Select the CUDA device(s) this process drives; devices==NULL or n==0 -> device 0.  devices[0] is the device of the
+ * host layer; with nz_set_bands(k) large grids are split over devices[0..k).  Optional: the first compute call
+ * initialises device 0 lazily.  Safe to call again while no residency scope is open (NZ_E_STATE otherwise); a failed
+ * call keeps the previous configuration.  The device layer (nz_dev_*) never changes the caller's current device. */
 NZ_API int32_t nz_init(const int32_t* devices, int32_t n);
 NZ_API int32_t nz_shutdown(void);
 NZ_API const char* nz_last_error(void);
@@ -151,6 +153,8 @@ NZ_API const char* nz_version(void);
 /* number of kernels this library has launched since nz_init (monotonic, all threads) */
 NZ_API int64_t nz_kernel_launch_count(void);
 NZ_API int32_t nz_last_timing(nz_timing* out);
+/* Test hook (fault injection): after `skip` more device allocations of the library, the next `count` fail with NZ_E_NOMEM. */
+NZ_API int32_t nz_test_fail_allocs(int32_t skip, int32_t count);
 
 /* ---- host-side helpers that need no GPU (host logic of the stages) ------------------ */
 
@@ -278,8 +282,76 @@ NZ_API int32_t nz_flush_to_host(const float* host_ptr);
 NZ_API int32_t nz_pin(void* host_ptr, size_t bytes);
 NZ_API int32_t nz_unpin(void* host_ptr);
 
+/* ---- multi-GPU: row bands of one large heightmap -------------------------------------- */
+/* The reference generates one tile at a time on the CPU (Scripts/MeshTileGenerator.cs:125-138,184-192); a heightmap too
+ * large or too slow for one GPU is split into ROW BANDS: band b of g owns rows [b*n/g, (b+1)*n/g).  Noise needs no
+ * communication; the iterated filter, the flow map, the value erosion and the mesh consume ghost rows of their
+ * neighbours (r*iterations, 2*iterations+1, iterations above only, 1), exchanged ONCE per stage.  Results are bit-identical
+ * to the single-GPU chain.  Two ways to reach it, both behind this C ABI:
+ *   (1) nz_init(devices, n) + nz_set_bands(n): every host-layer stage call (nz_fractal, nz_kernel_filter, ...) on a grid of
+ *       at least NZ_BANDS_MIN_RESOLUTION rows transparently runs on n bands, one per device, in ONE process (what a Unity
+ *       host is); ghost rows move by peer-to-peer copies over NVLink, each band uploads / downloads its own rows.
+ *   (2) nz_band_chain_*: the whole BASELINE C5 chain on device-resident bands; one band per PROCESS with the ghost rows
+ *       exchanged by ncclSend/ncclRecv (nz_comm_*; libnccl.so.2 is bound at run time), or all bands in one process. */
+#define NZ_BANDS_MIN_RESOLUTION 4096
+#define NZ_COMM_ID_BYTES 128            /* sizeof(ncclUniqueId) */
+#define NZ_BANDS_EXCHANGE 0             /* ghost rows come from the neighbours, once per stage */
+#define NZ_BANDS_RECOMPUTE 1            /* the noise stage evaluates every ghost row the chain will consume: no communication */
+
+/* Host layer: split large grids over the first n_bands devices given to nz_init (0 or 1: off).  Devices may repeat
+ * (e.g. {0,0}: two bands on one GPU, which is how the banded path is tested on a one-GPU box). */
+NZ_API int32_t nz_set_bands(int32_t n_bands);
+
+/* The chain of BASELINE.json configs[4] (one resolution^2 heightmap): fBm noise -> separable filter -> flow map -> value
+ * erosion -> mesh, with the stage parameters of the reference stages (NoiseStage.cs:37-54, KernelFilterStage.cs:17-19,
+ * FlowMapStage.cs:18-23, ErosionKernelJob, MeshStageData.cs:9-20).  *_iterations == 0 skips that stage; mesh_resolution == 0
+ * skips the mesh. */
+typedef struct {
+    int32_t resolution;
+    int32_t noise_type; float hurst, starting_amplitude, stepdown, detune_rate; int32_t octaves, xpos, zpos, noise_size;
+    int32_t filter_type, filter_iterations;
+    int32_t flow_iterations; float norm_min, norm_max;
+    int32_t erosion_iterations;
+    int32_t mesh_type, mesh_resolution, mesh_margin_pix; float tile_height, tile_size;
+} nz_chain_config;
+
+typedef struct {
+    int32_t rank, world, device;
+    int32_t z0, z1;                 /* owned heightmap rows [z0, z1) */
+    int32_t vz0, vz1;               /* owned vertex rows [vz0, vz1); owned triangle rows [max(vz0,1), vz1) */
+    float* d_rows;                  /* DEVICE pointer of owned row z0 of the last run's result (contiguous rows) */
+    void* d_vertices;               /* DEVICE pointer of vertex row vz0 (48-byte vertices) */
+    uint32_t* d_indices;            /* DEVICE pointer of triangle row max(vz0,1) */
+    int64_t halo_bytes_per_run;     /* ghost-row bytes this band received per run */
+} nz_band_info;
+
+/* NCCL communicator over the band processes (one rank per GPU).  Rank 0 calls nz_comm_unique_id and hands the 128 bytes
+ * to the others through whatever channel the host has; every rank then calls nz_comm_create.  > 0: handle; < 0: NZ_E*. */
+NZ_API int32_t nz_comm_unique_id(void* id_bytes, int32_t capacity);
+NZ_API int64_t nz_comm_create(const void* id_bytes, int32_t world, int32_t rank, int32_t device);
+/* polls ncclCommGetAsyncError: NZ_OK, or NZ_E_CUDA with the NCCL error in nz_last_error() */
+NZ_API int32_t nz_comm_async_error(int64_t comm);
+NZ_API int32_t nz_comm_destroy(int64_t comm);
+
+/* One band of the chain in this process (rank/world/device of `comm`; comm == 0: a single band on `device`).  `stream` is
+ * the cudaStream_t the band's work is enqueued on (NULL: a stream of the library's own). */
+NZ_API int64_t nz_band_chain_create(const nz_chain_config* cfg, int64_t comm, int32_t device, int32_t mode, void* stream);
+/* All n_bands bands in this process, band b on devices[b] (entries may repeat); ghost rows move by peer copies. */
+NZ_API int64_t nz_band_chain_create_local(const nz_chain_config* cfg, const int32_t* devices, int32_t n_bands, int32_t mode);
+/* Enqueue one pass of the chain (asynchronous).  timed != 0 also records a CUDA event before every stage. */
+NZ_API int32_t nz_band_chain_run(int64_t chain, int32_t timed);
+NZ_API int32_t nz_band_chain_sync(int64_t chain);
+/* milliseconds of {noise, filter, flow, erosion, mesh} of the last timed run (max over this process's bands; synchronises) */
+NZ_API int32_t nz_band_chain_stage_ms(int64_t chain, float* ms5);
+NZ_API int32_t nz_band_chain_local_bands(int64_t chain);
+NZ_API int32_t nz_band_chain_info(int64_t chain, int32_t local_band, nz_band_info* out);
+/* Copy this process's bands into FULL-GRID host buffers (each band writes its own slice; any pointer may be NULL):
+ * h_heights resolution^2 floats, h_vertices (R+1)^2 * 48 bytes, h_indices 6*R^2 uint32.  Synchronises. */
+NZ_API int32_t nz_band_chain_download(int64_t chain, float* h_heights, void* h_vertices, uint32_t* h_indices);
+NZ_API int32_t nz_band_chain_destroy(int64_t chain);
+
 /* ---- device layer ------------------------------------------------------------------- */
-/* All pointers are DEVICE pointers unless named h_*.  `stream` is a cudaStream_t (NULL = legacy
+/* All pointers are DEVICE pointers unless named h_*. `stream` is a cudaStream_t (NULL = legacy
  * default stream).  Grids are width x rows, contiguous.  Calls only enqueue work.           */
 
 /* Noise rows [z_first, z_first+rows) of the tile whose origin is (xpos,zpos): cell (x,r) gets

@@ -151,6 +151,8 @@ class BandChain:
         self.flow_scratch = None
         self.vtx = self.idx = None
         self.bytes_exchanged = 0
+        self.runs = 0
+        self.name = f"bands.BandChain over torch.distributed ({engine.name} engine)"
 
     # -- helpers ---------------------------------------------------------------------------------------
     def _win(self, buf, above, below):
@@ -244,7 +246,25 @@ class BandChain:
             eng.mesh(self.vtx, self.idx, win, self.z0 - a, self.vz0, self.vz1, cfg)
         mark("end")
         self.result = cur
+        self.runs += 1
         return cur
+
+    STAGES = ("noise", "filter", "flow", "erosion", "mesh")
+
+    def run_timed(self):
+        """run() with a CUDA event before every stage (on the current torch stream); returns a callable that gives the
+        per-stage milliseconds [noise, filter, flow, erosion, mesh] once the work has been synchronised."""
+        import torch
+        names = list(self.STAGES) + ["end"]
+        evs = {n: torch.cuda.Event(enable_timing=True) for n in names}
+        self.run(lambda name: evs[name].record())
+        if not self.with_mesh:
+            evs["mesh"] = evs["end"]
+        return lambda: [evs[a].elapsed_time(evs[b]) for a, b in zip(names[:-1], names[1:])]
+
+    def release(self):
+        """Drop the device buffers (the object keeps its geometry)."""
+        self.buf_a = self.buf_b = self.vtx = self.idx = self.flow_scratch = self.result = None
 
     def owned(self, buf=None):
         buf = self.result if buf is None else buf
@@ -278,3 +298,140 @@ def bind_host_to_gpu_numa_node(device_index):
         return f"gpu {device_index} ({bus}) -> numa node {node}, {len(cpus)} cpus"
     except Exception:                      # unreadable sysfs, no such attribute: not an error for the caller
         return ""
+
+
+class LibBandChain:
+    """The same chain driven INSIDE libnoize_b200.so (nz_band_chain_*): this class only passes the configuration through the
+    C ABI and wraps the device pointers it gets back.  One band per process (`dist` = torch.distributed, used ONCE to hand
+    rank 0's NCCL unique id to the other ranks; the ghost rows then travel by ncclSend/ncclRecv issued by the library on
+    the caller's stream), or, with `devices`, every band in this process (peer copies)."""
+
+    STAGES = BandChain.STAGES
+
+    def __init__(self, cfg, rank=0, world=1, dist=None, mode="exchange", with_mesh=True, devices=None):
+        import ctypes as C
+        import torch
+        from . import lib as _l
+        if mode not in ("exchange", "recompute"):
+            raise ValueError("mode must be 'exchange' or 'recompute'")
+        self.torch, self._l, self._C = torch, _l, C
+        self.cfg, self.rank, self.world, self.mode, self.with_mesh = cfg, rank, world, mode, with_mesh
+        lib = _l.load()
+        c = _l.ChainConfig(cfg.N, cfg.noise_type, cfg.hurst, cfg.starting_amplitude, cfg.stepdown, cfg.detune_rate, cfg.octaves,
+                           cfg.xpos, cfg.zpos, cfg.noise_size, cfg.filter_type, cfg.filter_iterations, cfg.flow_iterations,
+                           cfg.norm_min, cfg.norm_max, cfg.erosion_iterations, cfg.mesh_type, cfg.R if with_mesh else 0,
+                           cfg.mesh_margin, cfg.tile_height, cfg.tile_size)
+        m = 0 if mode == "exchange" else 1
+        self.comm = 0
+        if devices is not None:
+            devs = (C.c_int32 * len(devices))(*devices)
+            self.world = len(devices)
+            self.handle = int(lib.nz_band_chain_create_local(C.byref(c), devs, len(devices), m))
+            self.name = f"nz_band_chain (C ABI), {len(devices)} bands in one process, peer copies"
+        else:
+            device = torch.cuda.current_device()
+            if world > 1:
+                # the communicator also tells the band its place (rank, world); recompute mode never transfers through it
+                if dist is None:
+                    raise ValueError("world > 1 needs torch.distributed to hand out the NCCL unique id")
+                ident = torch.zeros(128, dtype=torch.uint8)
+                if rank == 0:
+                    buf = C.create_string_buffer(128)
+                    _l.check(lib.nz_comm_unique_id(buf, 128))
+                    ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+                ident = ident.cuda()
+                dist.broadcast(ident, 0)
+                raw = bytes(ident.cpu().numpy().tobytes())
+                self.comm = int(lib.nz_comm_create(raw, world, rank, device))
+                if self.comm < 0:
+                    _l.check(self.comm)
+            self.handle = int(lib.nz_band_chain_create(C.byref(c), self.comm, device, m, _l.stream_ptr()))
+            self.name = ("nz_band_chain (C ABI), one band per process, ncclSend/ncclRecv issued by the library"
+                         if world > 1 else "nz_band_chain (C ABI), single band")
+        if self.handle < 0:
+            _l.check(self.handle)
+        self.nlocal = int(lib.nz_band_chain_local_bands(self.handle))
+        self.runs = 0
+        self._info = None
+        i = self.info(0)
+        self.z0, self.z1, self.own, self.vz0, self.vz1 = i.z0, i.z1, i.z1 - i.z0, i.vz0, i.vz1
+
+    def info(self, local_band=0):
+        i = self._l.BandInfo()
+        self._l.check(self._l.load().nz_band_chain_info(self.handle, local_band, self._C.byref(i)))
+        return i
+
+    def run(self, stages=None):
+        self._l.check(self._l.load().nz_band_chain_run(self.handle, 0))
+        self.runs += 1
+        self._info = None
+
+    def run_timed(self):
+        lib, C = self._l.load(), self._C
+        self._l.check(lib.nz_band_chain_run(self.handle, 1))
+        self.runs += 1
+        self._info = None
+        handle = self.handle
+
+        def result():
+            ms = (C.c_float * 5)()
+            self._l.check(lib.nz_band_chain_stage_ms(handle, ms))
+            return list(ms)
+        return result
+
+    def sync(self):
+        self._l.check(self._l.load().nz_band_chain_sync(self.handle))
+
+    @property
+    def bytes_exchanged(self):
+        return sum(self.info(k).halo_bytes_per_run for k in range(self.nlocal)) * max(1, self.runs)
+
+    def _wrap(self, ptr, nbytes, dtype, device):
+        """torch view of library-owned device memory (valid until the next run / destroy)."""
+        torch = self.torch
+        if nbytes == 0 or not ptr:
+            return torch.empty(0, dtype=dtype, device=f"cuda:{device}")
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2, "strides": None}
+        return torch.as_tensor(_Mem(), device=f"cuda:{device}").view(dtype)
+
+    def owned(self, local_band=0):
+        i = self.info(local_band)
+        N = self.cfg.N
+        return self._wrap(i.d_rows, (i.z1 - i.z0) * N * 4, self.torch.float32, i.device).view(i.z1 - i.z0, N)
+
+    def mesh_slice(self, local_band=0):
+        i = self.info(local_band)
+        R = self.cfg.R
+        nv = (i.vz1 - i.vz0) * (R + 1)
+        ni = 6 * R * max(i.vz1 - max(i.vz0, 1), 0)
+        return (self._wrap(i.d_vertices, nv * 48, self.torch.float32, i.device).view(nv, 12),
+                self._wrap(i.d_indices, ni * 4, self.torch.int32, i.device))
+
+    @property
+    def vtx(self):
+        return self.mesh_slice(0)[0]
+
+    @property
+    def idx(self):
+        return self.mesh_slice(0)[1]
+
+    def download(self, heights=None, vertices=None, indices=None):
+        """Full-grid host arrays (numpy, C-contiguous); every local band writes its own slice."""
+        p = lambda a: None if a is None else a.ctypes.data
+        self._l.check(self._l.load().nz_band_chain_download(self.handle, p(heights), p(vertices), p(indices)))
+
+    def release(self):
+        if self.handle:
+            self._l.check(self._l.load().nz_band_chain_destroy(self.handle))
+            self.handle = 0
+        if self.comm:
+            self._l.check(self._l.load().nz_comm_destroy(self.comm))
+            self.comm = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

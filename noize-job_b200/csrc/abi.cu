@@ -12,8 +12,11 @@
 #include <memory>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "nz_common.cuh"
+#include "bands.cuh"
 
 namespace nz {
 
@@ -85,14 +88,19 @@ int32_t kernel_filter_table(int filter, float* kx, float* kz, int* ksize, float*
 struct Context {
     std::mutex mu;
     bool ready = false;
-    int device = 0;
-    // device-buffer pool: freed blocks are kept, keyed by size (stage buffers repeat the same sizes)
-    std::multimap<size_t, void*> free_blocks;
-    std::unordered_map<void*, size_t> live;
+    int n_visible = 0;
+    std::vector<int> devices{0};   // nz_init's list; devices[0] is the device of the un-banded host layer
+    int n_bands = 0;               // nz_set_bands: > 1 splits large host-layer grids over devices[0..n_bands)
+    // device-buffer pool: freed blocks are kept, keyed by (device, size) (stage buffers repeat the same sizes)
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;
+    std::unordered_map<void*, std::pair<int, size_t>> live;
+    long long fail_skip = 0, fail_allocs = 0;   // fault injection (nz_test_fail_allocs): after fail_skip allocations the next fail_allocs fail
 };
 static Context g_ctx;
 
-static int32_t ensure_init() {
+// The CUDA runtime is usable and nz_init's devices exist.  Does NOT touch the calling thread's current device: the
+// device layer (nz_dev_*) runs on caller-owned buffers and streams, on whatever device the caller has made current.
+static int32_t ensure_runtime() {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     if (!g_ctx.ready) {
         int n = 0;
@@ -102,48 +110,98 @@ static int32_t ensure_init() {
                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
             return NZ_E_CUDA;
         }
-        if (g_ctx.device >= n) {
-            set_error("device %d requested but only %d visible", g_ctx.device, n);
-            return NZ_E_CUDA;
-        }
+        for (int d : g_ctx.devices)
+            if (d < 0 || d >= n) {
+                set_error("device %d requested but only %d visible", d, n);
+                return NZ_E_CUDA;
+            }
+        g_ctx.n_visible = n;
         g_ctx.ready = true;
     }
-    NZ_CUDA(cudaSetDevice(g_ctx.device));
     return NZ_OK;
 }
 
-static int32_t pool_alloc(void** p, size_t bytes) {
+static int primary_device() {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    return g_ctx.devices[0];
+}
+
+// Host layer: the runtime is usable and the calling thread's current device is the primary device of nz_init.
+static int32_t ensure_init() {
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    NZ_CUDA(cudaSetDevice(primary_device()));
+    return NZ_OK;
+}
+
+// The device layer trusts the caller's current device; a pointer that lives on ANOTHER device is the one mistake that
+// would otherwise surface as an illegal address inside a kernel, so it is checked here (cheap: one attribute query).
+static int32_t check_device_pointer(const void* p, const char* who) {
+    if (!p) return NZ_OK;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return NZ_OK;   // not a pointer the runtime knows (e.g. a VMM mapping): let the launch decide
+    }
+    if (a.type != cudaMemoryTypeDevice) return NZ_OK;
+    int cur = 0;
+    NZ_CUDA(cudaGetDevice(&cur));
+    if (a.device != cur) {
+        set_error("%s: the buffer lives on device %d but the calling thread's current device is %d (cudaSetDevice first)", who,
+                  a.device, cur);
+        return NZ_E_INVALID;
+    }
+    return NZ_OK;
+}
+
+// Allocates on the CURRENT device.
+int32_t dev_alloc(void** p, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
+    int dev = 0;
+    NZ_CUDA(cudaGetDevice(&dev));
     {
         std::lock_guard<std::mutex> lk(g_ctx.mu);
-        auto it = g_ctx.free_blocks.find(bytes);
+        if (g_ctx.fail_allocs > 0 && g_ctx.fail_skip-- <= 0) {
+            g_ctx.fail_skip = 0;
+            g_ctx.fail_allocs--;
+            set_error("device allocation of %zu bytes failed (injected fault)", bytes);
+            return NZ_E_NOMEM;
+        }
+        auto it = g_ctx.free_blocks.find({dev, bytes});
         if (it != g_ctx.free_blocks.end()) {
             *p = it->second;
             g_ctx.free_blocks.erase(it);
-            g_ctx.live[*p] = bytes;
+            g_ctx.live[*p] = {dev, bytes};
             return NZ_OK;
         }
     }
     cudaError_t e = cudaMalloc(p, bytes);
     if (e == cudaErrorMemoryAllocation) {
-        // give cached blocks back to the driver and retry once
+        // give this device's cached blocks back to the driver and retry once
         cudaGetLastError();
         std::vector<void*> drop;
         {
             std::lock_guard<std::mutex> lk(g_ctx.mu);
-            for (auto& kv : g_ctx.free_blocks) drop.push_back(kv.second);
-            g_ctx.free_blocks.clear();
+            for (auto it = g_ctx.free_blocks.begin(); it != g_ctx.free_blocks.end();) {
+                if (it->first.first == dev) {
+                    drop.push_back(it->second);
+                    it = g_ctx.free_blocks.erase(it);
+                } else {
+                    ++it;
+                }
+            }
         }
         for (void* d : drop) cudaFree(d);
         e = cudaMalloc(p, bytes);
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     std::lock_guard<std::mutex> lk(g_ctx.mu);
-    g_ctx.live[*p] = bytes;
+    g_ctx.live[*p] = {dev, bytes};
     return NZ_OK;
 }
 
-static void pool_free(void* p) {
+// Returns a block to the pool.  The caller has ordered every use of the block before this call (stream synchronised).
+void dev_free(void* p) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     auto it = g_ctx.live.find(p);
@@ -151,6 +209,8 @@ static void pool_free(void* p) {
     g_ctx.free_blocks.emplace(it->second, p);
     g_ctx.live.erase(it);
 }
+static inline int32_t pool_alloc(void** p, size_t bytes) { return dev_alloc(p, bytes); }
+static inline void pool_free(void* p) { dev_free(p); }
 
 // ---- per-thread state: stream, timing events, residency map ------------------------------------
 struct Mirror {
@@ -161,6 +221,9 @@ struct Mirror {
     bool dirty = false;  // device newer than host
     cudaEvent_t ready = nullptr;        // recorded after the last stage that touched the mirror (cross-thread ordering)
     cudaStream_t last_stream = nullptr;
+    // nz_set_bands: the mirror of a large square grid is a set of row bands, one per device, instead of d / d_tmp.  All
+    // work on a banded mirror runs on the bands' own streams, so stages issued from different threads stay ordered.
+    std::shared_ptr<BandSet> bands;
 };
 
 // A residency scope: the device mirrors of the host slices one chain of stages works on.  Scopes are process-wide
@@ -176,7 +239,10 @@ static std::atomic<long long> g_next_scope{1};
 
 struct ThreadState {
     cudaStream_t stream = nullptr;
+    int device = 0;                 // device `stream` and `ev` belong to
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after h2d, after kernels, after d2h
+    cudaStream_t copy_stream = nullptr;                         // D2H of mesh chunks while the next chunk is built
+    cudaEvent_t mesh_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // chunk built [slot], chunk downloaded [2 + slot]
     bool timed = false;
     long long launches_at_start = 0;
     int launches = 0;
@@ -193,9 +259,32 @@ static inline Scope& cur_scope() { return t_state.scope ? *t_state.scope : t_sta
 static int32_t thread_ready() {
     int32_t rc = ensure_init();
     if (rc != NZ_OK) return rc;
+    const int dev = primary_device();
+    if (t_state.stream && t_state.device != dev) {
+        // nz_init re-pointed the library at another device: this thread's stream and events belong to the old one
+        cudaSetDevice(t_state.device);
+        cudaStreamSynchronize(t_state.stream);
+        cudaStreamDestroy(t_state.stream);
+        for (auto& e : t_state.ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+        if (t_state.copy_stream) {
+            cudaStreamDestroy(t_state.copy_stream);
+            t_state.copy_stream = nullptr;
+            for (auto& e : t_state.mesh_ev) {
+                if (e) cudaEventDestroy(e);
+                e = nullptr;
+            }
+        }
+        t_state.stream = nullptr;
+        t_state.timed = false;
+        NZ_CUDA(cudaSetDevice(dev));
+    }
     if (!t_state.stream) {
         NZ_CUDA(cudaStreamCreateWithFlags(&t_state.stream, cudaStreamNonBlocking));
         for (auto& e : t_state.ev) NZ_CUDA(cudaEventCreate(&e));
+        t_state.device = dev;
     }
     return NZ_OK;
 }
@@ -241,9 +330,76 @@ static int32_t download(Mirror& m) {
     return NZ_OK;
 }
 
-// Obtain the device mirror of a host slice.  `need_contents`: the stage reads the slice (H2D unless a
-// resident mirror is already newer than the host).
-static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out) {
+// ---- banded mirrors (nz_set_bands) ------------------------------------------------------------------------------
+constexpr int BAND_GHOST_CAP = 288;     // ghost rows kept per band side: Gauss9 x 32 iterations = 128, flow x 128 = 257
+constexpr int BAND_MIN_ROWS = 64;       // a band narrower than this is not worth a device
+
+// the calling thread's stream waits for every band's last stage (before it reads the bands, or to time them)
+static int32_t banded_join(Mirror& m) {
+    for (Band& bd : m.bands->b) NZ_CUDA(cudaStreamWaitEvent(t_state.stream, bd.done, 0));
+    return NZ_OK;
+}
+
+static int32_t banded_copy_rows(Mirror& m, bool to_host) {
+    BandSet& bs = *m.bands;
+    const size_t W = bs.width;
+    int prev = 0;
+    NZ_CUDA(cudaGetDevice(&prev));
+    cudaError_t e = cudaSuccess;
+    for (Band& bd : bs.b) {
+        e = cudaSetDevice(bd.device);
+        if (e != cudaSuccess) break;
+        float* dev = bd.buf[bd.cur] + (size_t)bd.above * W;
+        float* host = m.host.ptr + (size_t)bd.z0 * W;
+        const size_t bytes = (size_t)bd.own * W * sizeof(float);
+        e = to_host ? cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, bd.s)
+                    : cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, bd.s);
+        if (e == cudaSuccess) e = cudaEventRecord(bd.done, bd.s);
+        if (e != cudaSuccess) break;
+    }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, to_host ? "banded download" : "banded upload");
+    if (to_host) m.dirty = false;
+    return NZ_OK;
+}
+
+// Gather a banded mirror into an ordinary one on the primary device (for a stage that has no banded form).
+static int32_t unband(Mirror& m) {
+    BandSet& bs = *m.bands;
+    const size_t W = bs.width;
+    int32_t rc = pool_alloc((void**)&m.d, m.n * sizeof(float));
+    if (rc != NZ_OK) return rc;
+    rc = banded_join(m);
+    cudaError_t e = cudaSuccess;
+    if (rc == NZ_OK)
+        for (Band& bd : bs.b) {
+            e = cudaMemcpyPeerAsync(m.d + (size_t)bd.z0 * W, t_state.device, bd.buf[bd.cur] + (size_t)bd.above * W, bd.device,
+                                    (size_t)bd.own * W * sizeof(float), t_state.stream);
+            if (e != cudaSuccess) break;
+        }
+    if (rc == NZ_OK && e == cudaSuccess) e = cudaStreamSynchronize(t_state.stream);   // the bands are freed next
+    if (rc != NZ_OK || e != cudaSuccess) {
+        pool_free(m.d);
+        m.d = nullptr;
+        return rc != NZ_OK ? rc : cuda_fail(e, "gathering a banded mirror");
+    }
+    m.bands.reset();
+    return NZ_OK;
+}
+
+static void release_mirror(Mirror& m) {
+    pool_free(m.d);
+    pool_free(m.d_tmp);
+    m.d = m.d_tmp = nullptr;
+    m.bands.reset();        // ~BandSet synchronises its streams and frees its buffers
+    if (m.ready) cudaEventDestroy(m.ready);
+    m.ready = nullptr;
+}
+
+// Obtain the device mirror of a host slice.  `need_contents`: the stage reads the slice (H2D unless a resident mirror is
+// already newer than the host).  `band_res` > 0: the slice is a band_res^2 grid and the calling stage has a banded form
+// (nz_set_bands); 0: the stage needs an ordinary single-device mirror (a banded one is gathered first).
+static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out, int band_res = 0) {
     Scope& sc = cur_scope();
     std::lock_guard<std::mutex> lk(sc.mu);
     auto& mirrors = sc.mirrors;
@@ -251,15 +407,16 @@ static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out) 
     if (it != mirrors.end() && it->second.ready && it->second.last_stream != t_state.stream)
         NZ_CUDA(cudaStreamWaitEvent(t_state.stream, it->second.ready, 0));   // previous stage ran on another thread's stream
     if (it != mirrors.end() && (it->second.n != (size_t)s.length || it->second.host.stride_bytes != s.stride_bytes)) {
-        // same base pointer, different shape: drop the stale mirror
-        if (it->second.dirty) {
-            int32_t rc = download(it->second);
+        // same base pointer, different shape: drop the stale mirror (after everything in flight on it has finished: the
+        // blocks go back to a pool other threads allocate from)
+        Mirror& old = it->second;
+        if (old.dirty) {
+            int32_t rc = old.bands ? banded_copy_rows(old, /*to_host=*/true) : download(old);
             if (rc != NZ_OK) return rc;
-            NZ_CUDA(cudaStreamSynchronize(t_state.stream));
         }
-        pool_free(it->second.d);
-        pool_free(it->second.d_tmp);
-        if (it->second.ready) cudaEventDestroy(it->second.ready);
+        if (old.ready && old.last_stream != t_state.stream) cudaEventSynchronize(old.ready);
+        NZ_CUDA(cudaStreamSynchronize(t_state.stream));
+        release_mirror(old);
         mirrors.erase(it);
         it = mirrors.end();
     }
@@ -267,17 +424,52 @@ static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out) 
         Mirror m;
         m.n = (size_t)s.length;
         m.host = s;
-        int32_t rc = pool_alloc((void**)&m.d, m.n * sizeof(float));
-        if (rc != NZ_OK) return rc;
-        it = mirrors.emplace(s.ptr, m).first;
-        if (need_contents) {
-            rc = upload(it->second);
-            if (rc != NZ_OK) return rc;
+        int n_bands = 0;
+        std::vector<int> devs;
+        {
+            std::lock_guard<std::mutex> lk2(g_ctx.mu);
+            n_bands = g_ctx.n_bands;
+            devs = g_ctx.devices;
         }
+        const bool banded = band_res >= NZ_BANDS_MIN_RESOLUTION && n_bands > 1 && s.stride_bytes == 4 &&
+                            band_res / n_bands >= BAND_MIN_ROWS;
+        int32_t rc;
+        if (banded) {
+            std::unique_ptr<BandSet> bs;
+            rc = bandset_create(&bs, band_res, band_res, n_bands, 0, n_bands, devs.data(), BAND_GHOST_CAP, nullptr, nullptr);
+            if (rc != NZ_OK) return rc;
+            m.bands = std::move(bs);
+            if (need_contents && (rc = banded_copy_rows(m, /*to_host=*/false)) != NZ_OK) return rc;   // m frees its bands
+        } else {
+            rc = pool_alloc((void**)&m.d, m.n * sizeof(float));
+            if (rc != NZ_OK) return rc;
+            if (need_contents && (rc = upload(m)) != NZ_OK) {
+                cudaStreamSynchronize(t_state.stream);
+                pool_free(m.d);
+                return rc;
+            }
+        }
+        // the mirror enters the map only once it is complete: a failed call must not leave a half-made mirror that a
+        // later call with the same host pointer would trust
+        it = mirrors.emplace(s.ptr, m).first;
+    } else if (it->second.bands && band_res == 0) {
+        int32_t rc = unband(it->second);
+        if (rc != NZ_OK) return rc;
     }
     *out = &it->second;
     return NZ_OK;
 }
+
+// Outside a scope a mirror lives for one call.  Every host-layer entry point holds one of these: whatever a failed (or
+// finished) call left in the thread-local map is released when the call returns, so a retry starts from the host data.
+struct UnscopedCleanup {
+    ~UnscopedCleanup() {
+        if (t_state.scope || t_state.local.mirrors.empty()) return;
+        if (t_state.stream) cudaStreamSynchronize(t_state.stream);
+        for (auto& kv : t_state.local.mirrors) release_mirror(kv.second);
+        t_state.local.mirrors.clear();
+    }
+};
 
 static int32_t ensure_tmp(Mirror& m) {
     if (!m.d_tmp) return pool_alloc((void**)&m.d_tmp, m.n * sizeof(float));
@@ -296,14 +488,30 @@ static void adopt_result(Mirror& m, float* result) {
 // End of a host-layer stage: outside a pipeline, bring the result home and drop the mirror.
 static int32_t finish(Mirror* m) {
     cudaStream_t s = t_state.stream;
+    if (m->bands) {
+        // the stage ran on the bands' streams: the thread's stream joins them (timing; and the download below)
+        int32_t rc = banded_join(*m);
+        if (rc != NZ_OK) return rc;
+        NZ_CUDA(cudaEventRecord(t_state.ev[2], s));
+        if (!in_scope()) {
+            if (m->dirty) rc = banded_copy_rows(*m, /*to_host=*/true);   // every band brings its own rows home
+            if (rc == NZ_OK) rc = bandset_sync(*m->bands);
+            release_mirror(*m);
+            t_state.local.mirrors.erase(m->host.ptr);
+            if (rc != NZ_OK) return rc;
+        }
+        NZ_CUDA(cudaEventRecord(t_state.ev[3], s));
+        t_state.timed = true;
+        t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
+        return NZ_OK;
+    }
     NZ_CUDA(cudaEventRecord(t_state.ev[2], s));
     if (!in_scope()) {
         int32_t rc = NZ_OK;
         if (m->dirty) rc = download(*m);
         cudaError_t e = cudaEventRecord(t_state.ev[3], s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        pool_free(m->d);
-        pool_free(m->d_tmp);
+        release_mirror(*m);
         t_state.local.mirrors.erase(m->host.ptr);
         if (rc != NZ_OK) return rc;
         if (e != cudaSuccess) return cuda_fail(e, "stage completion");
@@ -332,7 +540,7 @@ static int32_t mark_uploaded() {
     return NZ_OK;
 }
 
-static int32_t fractal_params(FractalParams* p, int width, int rows, int z_first, int noise_type, float hurst,
+int32_t fractal_params(FractalParams* p, int width, int rows, int z_first, int noise_type, float hurst,
                               float start_amp, float stepdown, float detune, int octaves, int xpos, int zpos,
                               int noise_size) {
     NZ_REQUIRE(noise_type >= 0 && noise_type < NZ_NOISE__COUNT, "fractal: noise_type %d out of range", noise_type);
@@ -378,22 +586,64 @@ using namespace nz;
 extern "C" {
 
 NZ_API int32_t nz_init(const int32_t* devices, int32_t n) {
+    NZ_REQUIRE(n >= 0 && n <= 64, "nz_init: device count %d out of range", n);
+    {
+        std::lock_guard<std::mutex> lk(g_scopes_mu);
+        if (!g_scopes.empty()) {
+            set_error("nz_init: %zu residency scope(s) are open; close them before re-initialising", g_scopes.size());
+            return NZ_E_STATE;
+        }
+    }
+    std::vector<int> old;
     {
         std::lock_guard<std::mutex> lk(g_ctx.mu);
-        g_ctx.device = (devices && n > 0) ? devices[0] : 0;
+        old = g_ctx.devices;
+        g_ctx.devices.assign(1, 0);
+        if (devices && n > 0) g_ctx.devices.assign(devices, devices + n);
+        if (g_ctx.n_bands > (int)g_ctx.devices.size()) g_ctx.n_bands = 0;
         g_ctx.ready = false;
     }
-    return ensure_init();
+    int32_t rc = ensure_init();
+    if (rc != NZ_OK) {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);   // keep the previous, working configuration
+        g_ctx.devices = old;
+        g_ctx.ready = false;
+    }
+    return rc;
+}
+
+NZ_API int32_t nz_set_bands(int32_t n_bands) {
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    NZ_REQUIRE(n_bands >= 0 && n_bands <= (int)g_ctx.devices.size(),
+               "nz_set_bands: %d bands but nz_init was given %zu device(s)", n_bands, g_ctx.devices.size());
+    g_ctx.n_bands = n_bands;
+    return NZ_OK;
 }
 
 NZ_API int32_t nz_shutdown(void) {
-    std::vector<void*> drop;
+    std::vector<std::pair<int, void*>> drop;
     {
         std::lock_guard<std::mutex> lk(g_ctx.mu);
-        for (auto& kv : g_ctx.free_blocks) drop.push_back(kv.second);
+        for (auto& kv : g_ctx.free_blocks) drop.push_back({kv.first.first, kv.second});
         g_ctx.free_blocks.clear();
     }
-    for (void* d : drop) cudaFree(d);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto& d : drop) {
+        cudaSetDevice(d.first);
+        cudaFree(d.second);
+    }
+    cudaSetDevice(prev);
+    return NZ_OK;
+}
+
+/* Fault injection for the tests: after `skip` more allocations the next `count` device allocations fail with NZ_E_NOMEM. */
+NZ_API int32_t nz_test_fail_allocs(int32_t skip, int32_t count) {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    g_ctx.fail_skip = skip > 0 ? skip : 0;
+    g_ctx.fail_allocs = count > 0 ? count : 0;
     return NZ_OK;
 }
 
@@ -473,24 +723,27 @@ NZ_API int32_t nz_dev_fractal(float* d_dst, int32_t width, int32_t rows, int32_t
     int32_t rc = fractal_params(&p, width, rows, z_first, noise_type, hurst, starting_amplitude, stepdown, detune_rate,
                                 octaves, xpos, zpos, noise_size);
     if (rc != NZ_OK) return rc;
-    rc = ensure_init();
+    rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_dst, "nz_dev_fractal")) != NZ_OK) return rc;
     return launch_fractal(d_dst, noise_type, p, (cudaStream_t)stream);
 }
 
 NZ_API int32_t nz_dev_separable(float* d_data, float* d_tmp, int32_t width, int32_t rows, int32_t ksize,
                                 const float* h_kx, const float* h_kz, float factor, int32_t iterations,
                                 float** d_result, void* stream) {
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_separable")) != NZ_OK) return rc;
     return launch_separable(d_data, d_tmp, width, rows, ksize, h_kx, h_kz, factor, iterations, d_result,
                             (cudaStream_t)stream);
 }
 
 NZ_API int32_t nz_dev_kernel_filter(float* d_data, float* d_tmp, int32_t width, int32_t rows, int32_t filter_type,
                                     int32_t iterations, float** d_result, void* stream) {
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_kernel_filter")) != NZ_OK) return rc;
     NZ_REQUIRE(filter_type >= 0 && filter_type < NZ_FILTER__COUNT, "kernel_filter: filter_type %d out of range", filter_type);
     if (filter_type == NZ_FILTER_SOBEL3_2D)
         return launch_sobel2d(d_data, d_tmp, width, rows, iterations, d_result, (cudaStream_t)stream);
@@ -503,8 +756,9 @@ NZ_API int32_t nz_dev_kernel_filter(float* d_data, float* d_tmp, int32_t width, 
 
 NZ_API int32_t nz_dev_min_erosion(float* d_data, float* d_tmp, int32_t width, int32_t rows, int32_t iterations,
                                   float** d_result, void* stream) {
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_min_erosion")) != NZ_OK) return rc;
     return launch_min_erosion(d_data, d_tmp, width, rows, iterations, d_result, (cudaStream_t)stream);
 }
 
@@ -515,15 +769,16 @@ NZ_API size_t nz_dev_flowmap_scratch_bytes(int32_t width, int32_t rows, int32_t 
 
 NZ_API int32_t nz_dev_flowmap(float* d_height, float* d_tmp, void* d_scratch, int32_t width, int32_t rows,
                               int32_t iterations, float norm_min, float norm_max, float** d_result, void* stream) {
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_height, "nz_dev_flowmap")) != NZ_OK) return rc;
     return launch_flowmap(d_height, d_tmp, d_scratch, width, rows, iterations, norm_min, norm_max, d_result,
                           (cudaStream_t)stream);
 }
 
 NZ_API int32_t nz_dev_flow_walk_reruns(uint64_t* count) {
     NZ_REQUIRE(count != nullptr, "nz_dev_flow_walk_reruns: null result pointer");
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
     unsigned long long c = 0;
     rc = flow_walk_reruns(&c);
@@ -536,8 +791,9 @@ NZ_API int32_t nz_dev_heightmap_mesh(int32_t mesh_type, void* d_vertices, uint32
                                      const float* d_heights, int32_t h_row_first, int32_t h_rows, int32_t vz_begin,
                                      int32_t vz_end, void* stream) {
     (void)margin_pix;  // consumed only by MarginScale(), which nothing calls (SquareGridHeightMap.cs:41-56)
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_heights, "nz_dev_heightmap_mesh")) != NZ_OK) return rc;
     return launch_mesh(mesh_type, d_vertices, d_indices, resolution, input_resolution, tile_height, tile_size, d_heights,
                        h_row_first, h_rows, vz_begin, vz_end, (cudaStream_t)stream);
 }
@@ -547,6 +803,9 @@ NZ_API int32_t nz_dev_thermal_erosion(float* d_data, float* d_tmp, int32_t resol
     NZ_REQUIRE(d_data && resolution > 0, "nz_dev_thermal_erosion: bad arguments");
     NZ_REQUIRE(iterations >= 0, "nz_dev_thermal_erosion: iterations %d < 0", iterations);
     NZ_REQUIRE(d_tmp != d_data, "nz_dev_thermal_erosion: d_tmp aliases d_data");
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_thermal_erosion")) != NZ_OK) return rc;
     return launch_thermal_erosion(d_data, d_tmp, resolution, talus, increment_ratio, mesh_height_width_ratio, iterations, d_result,
                                   (cudaStream_t)stream);
 }
@@ -557,43 +816,62 @@ NZ_API size_t nz_dev_subtractive_flow_scratch_bytes(int32_t width, int32_t rows)
 NZ_API int32_t nz_dev_subtractive_flow_erosion(float* d_height, void* d_scratch, int32_t width, int32_t rows,
                                                int32_t erosive_iterations, float erosive_factor, float norm_min,
                                                float norm_max, void* stream) {
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_height, "nz_dev_subtractive_flow_erosion")) != NZ_OK) return rc;
     return launch_subtractive_flow_erosion(d_height, d_scratch, width, rows, erosive_iterations, erosive_factor, norm_min,
                                            norm_max, (cudaStream_t)stream);
 }
 NZ_API int32_t nz_dev_constant(float* d_data, size_t n, int32_t operation, float constant_value, void* stream) {
     NZ_REQUIRE(d_data || n == 0, "nz_dev_constant: null grid");
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_constant")) != NZ_OK) return rc;
     return launch_constant(d_data, n, operation, constant_value, (cudaStream_t)stream);
 }
 NZ_API int32_t nz_dev_reduce(float* d_left, const float* d_right, size_t n, int32_t operation, void* stream) {
     NZ_REQUIRE((d_left && d_right) || n == 0, "nz_dev_reduce: null grid");
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_left, "nz_dev_reduce")) != NZ_OK) return rc;
     return launch_reduce(d_left, d_right, n, operation, (cudaStream_t)stream);
 }
 NZ_API int32_t nz_dev_curve(float* d_data, size_t n, const float* d_curve, int32_t curve_size, void* stream) {
     NZ_REQUIRE(d_data || n == 0, "nz_dev_curve: null grid");
     NZ_REQUIRE(d_curve && curve_size >= 2, "nz_dev_curve: the curve needs at least 2 samples (got %d)", curve_size);
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_curve")) != NZ_OK) return rc;
     return launch_curve(d_data, n, d_curve, curve_size, (cudaStream_t)stream);
 }
 NZ_API int32_t nz_dev_crop(const float* d_input, int32_t input_resolution, float* d_output, int32_t output_resolution,
                            int32_t offset, void* stream) {
     NZ_REQUIRE(d_input && d_output && input_resolution > 0 && output_resolution > 0 && output_resolution <= 65535,
                "nz_dev_crop: bad arguments");
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_input, "nz_dev_crop")) != NZ_OK) return rc;
     return launch_crop(d_input, input_resolution, d_output, output_resolution, offset, (cudaStream_t)stream);
 }
 NZ_API size_t nz_dev_map_range_scratch_bytes(void) { return map_range_scratch_bytes(); }
 NZ_API int32_t nz_dev_map_range(const float* d_map, size_t n, float lim_min, float lim_max, float* d_res3, void* d_scratch,
                                 void* stream) {
     NZ_REQUIRE(d_map && d_res3 && d_scratch && n > 0, "nz_dev_map_range: bad arguments");
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_map, "nz_dev_map_range")) != NZ_OK) return rc;
     return launch_map_range(d_map, n, lim_min, lim_max, d_res3, d_scratch, (cudaStream_t)stream);
 }
 NZ_API int32_t nz_dev_normalize(float* d_data, size_t n, float vmin, float range, void* stream) {
     NZ_REQUIRE(d_data || n == 0, "nz_dev_normalize: null grid");
+    int32_t rc = ensure_runtime();
+    if (rc != NZ_OK) return rc;
+    if ((rc = check_device_pointer(d_data, "nz_dev_normalize")) != NZ_OK) return rc;
     return launch_normalize(d_data, n, vmin, range, (cudaStream_t)stream);
 }
 
 NZ_API int32_t nz_dev_fma_peak(float* d_sink, int32_t grid, int32_t iters, double* flops, void* stream) {
-    int32_t rc = ensure_init();
+    int32_t rc = ensure_runtime();
     if (rc != NZ_OK) return rc;
     return launch_fma_peak(d_sink, grid, iters, flops, (cudaStream_t)stream);
 }
@@ -609,15 +887,15 @@ static int32_t scope_close(const std::shared_ptr<Scope>& sc) {
     cudaStream_t s = t_state.stream;
     for (auto& kv : sc->mirrors) {
         Mirror& m = kv.second;
+        if (m.bands) {
+            if (m.dirty && rc == NZ_OK) rc = banded_copy_rows(m, /*to_host=*/true);   // one D2H per band, in parallel
+            continue;
+        }
         if (m.ready && m.last_stream != s) cudaStreamWaitEvent(s, m.ready, 0);
         if (m.dirty && rc == NZ_OK) rc = download(m);
     }
     cudaError_t e = cudaStreamSynchronize(s);
-    for (auto& kv : sc->mirrors) {
-        pool_free(kv.second.d);
-        pool_free(kv.second.d_tmp);
-        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
-    }
+    for (auto& kv : sc->mirrors) release_mirror(kv.second);   // ~BandSet synchronises the bands' streams
     sc->mirrors.clear();
     if (rc != NZ_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "scope close");
@@ -704,6 +982,10 @@ NZ_API int32_t nz_flush_to_host(const float* host_ptr) {
     std::lock_guard<std::mutex> lk(sc.mu);
     auto it = sc.mirrors.find(host_ptr);
     if (it == sc.mirrors.end()) return NZ_OK;  // nothing resident: host is current
+    if (it->second.bands) {
+        if (it->second.dirty && (rc = banded_copy_rows(it->second, /*to_host=*/true)) != NZ_OK) return rc;
+        return bandset_sync(*it->second.bands);
+    }
     if (it->second.ready && it->second.last_stream != t_state.stream) NZ_CUDA(cudaStreamWaitEvent(t_state.stream, it->second.ready, 0));
     if (it->second.dirty) {
         rc = download(it->second);
@@ -725,7 +1007,7 @@ NZ_API int32_t nz_pin(void* host_ptr, size_t bytes) {
     int32_t rc = ensure_init();
     if (rc != NZ_OK) return rc;
     NZ_REQUIRE(host_ptr && bytes, "nz_pin: null/empty range");
-    NZ_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+    NZ_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));   // pinned for every device (banded mirrors)
     return NZ_OK;
 }
 NZ_API int32_t nz_unpin(void* host_ptr) {
@@ -745,11 +1027,17 @@ NZ_API int32_t nz_fractal(nz_slice_f32 dst, int32_t resolution, int32_t noise_ty
     rc = fractal_params(&p, resolution, resolution, 0, noise_type, hurst, starting_amplitude, stepdown, detune_rate,
                         octaves, xpos, zpos, noise_size);
     if (rc != NZ_OK) return rc;
+    UnscopedCleanup cleanup;
+    nvtxRangePushA("nz_fractal");
+    struct Pop { ~Pop() { nvtxRangePop(); } } pop;
     if ((rc = begin_stage()) != NZ_OK) return rc;
     Mirror* m;
-    if ((rc = acquire(dst, /*need_contents=*/false, &m)) != NZ_OK) return rc;
+    if ((rc = acquire(dst, /*need_contents=*/false, &m, resolution)) != NZ_OK) return rc;
     if ((rc = mark_uploaded()) != NZ_OK) return rc;
-    rc = launch_fractal(m->d, noise_type, p, t_state.stream);
+    if (m->bands)
+        rc = bandset_fractal(*m->bands, noise_type, hurst, starting_amplitude, stepdown, detune_rate, octaves, xpos, zpos, noise_size, 0, 0);
+    else
+        rc = launch_fractal(m->d, noise_type, p, t_state.stream);
     if (rc == NZ_OK) m->dirty = true;
     int32_t rc2 = finish(m);
     return rc != NZ_OK ? rc : rc2;
@@ -757,15 +1045,40 @@ NZ_API int32_t nz_fractal(nz_slice_f32 dst, int32_t resolution, int32_t noise_ty
 
 }  // extern "C"
 
-// shared body of the in-place two-buffer stages
-template <typename F>
-static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const char* who, bool need_tmp, F&& body) {
+// ghost rows a banded mirror of a resolution^2 grid keeps per band side under the current nz_set_bands (0: not banded)
+static int band_cap_for(int resolution) {
+    int n_bands;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        n_bands = g_ctx.n_bands;
+    }
+    if (n_bands < 2 || resolution < NZ_BANDS_MIN_RESOLUTION || resolution / n_bands < BAND_MIN_ROWS) return 0;
+    const int min_own = resolution / n_bands;
+    return BAND_GHOST_CAP < min_own ? BAND_GHOST_CAP : min_own;
+}
+
+// shared body of the in-place two-buffer stages.  `banded_body` (BandSet&) -> status is the stage's form on row bands
+// (nz_set_bands); pass can_band = false for a stage (or a parameter combination) that has none: a banded mirror is then
+// gathered onto the primary device first.
+template <typename F, typename B>
+static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const char* who, bool need_tmp, F&& body, bool can_band,
+                                 B&& banded_body) {
     NZ_REQUIRE(resolution > 0 && resolution <= 46340, "%s: resolution %d out of range", who, resolution);
     int32_t rc = check_slice(src, (long long)resolution * resolution, who);
     if (rc != NZ_OK) return rc;
+    UnscopedCleanup cleanup;
+    nvtxRangePushA(who);
+    struct Pop { ~Pop() { nvtxRangePop(); } } pop;
     if ((rc = begin_stage()) != NZ_OK) return rc;
     Mirror* m;
-    if ((rc = acquire(src, /*need_contents=*/true, &m)) != NZ_OK) return rc;
+    if ((rc = acquire(src, /*need_contents=*/true, &m, can_band ? resolution : 0)) != NZ_OK) return rc;
+    if (m->bands) {
+        if ((rc = mark_uploaded()) != NZ_OK) return rc;
+        rc = banded_body(*m->bands);
+        if (rc == NZ_OK) m->dirty = true;
+        int32_t rc2 = finish(m);
+        return rc != NZ_OK ? rc : rc2;
+    }
     if (need_tmp && (rc = ensure_tmp(*m)) != NZ_OK) return rc;
     if ((rc = mark_uploaded()) != NZ_OK) return rc;
     float* result = m->d;
@@ -774,15 +1087,21 @@ static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const cha
     int32_t rc2 = finish(m);
     return rc != NZ_OK ? rc : rc2;
 }
+template <typename F>
+static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const char* who, bool need_tmp, F&& body) {
+    return run_inplace_stage(src, resolution, who, need_tmp, body, false, [](BandSet&) { return (int32_t)NZ_E_UNSUPPORTED; });
+}
 
 extern "C" {
 
 NZ_API int32_t nz_separable(nz_slice_f32 src, nz_slice_f32 tmp, int32_t ksize, const float* kx, const float* kz,
                             float factor, int32_t resolution, int32_t iterations) {
     (void)tmp;
+    NZ_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= NZ_MAX_KERNEL_WIDTH && kx && kz && iterations >= 0,
+               "nz_separable: bad kernel (ksize %d, iterations %d)", ksize, iterations);
     return run_inplace_stage(src, resolution, "nz_separable", true, [&](Mirror& m, float** res) {
         return launch_separable(m.d, m.d_tmp, resolution, resolution, ksize, kx, kz, factor, iterations, res, t_state.stream);
-    });
+    }, true, [&](BandSet& bs) { return bandset_separable(bs, ksize, kx, kz, factor, iterations, 0, 0, true); });
 }
 
 NZ_API int32_t nz_kernel_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t filter_type, int32_t resolution,
@@ -792,6 +1111,13 @@ NZ_API int32_t nz_kernel_filter(nz_slice_f32 src, nz_slice_f32 tmp, int32_t filt
     NZ_REQUIRE(iterations >= 1, "nz_kernel_filter: iterations %d < 1", iterations);
     return run_inplace_stage(src, resolution, "nz_kernel_filter", true, [&](Mirror& m, float** res) {
         return nz_dev_kernel_filter(m.d, m.d_tmp, resolution, resolution, filter_type, iterations, res, t_state.stream);
+    }, true, [&](BandSet& bs) {
+        if (filter_type == NZ_FILTER_SOBEL3_2D) return bandset_sobel2d(bs, iterations, 0, 0, true);
+        float tkx[9], tkz[9], factor;
+        int ksize;
+        int32_t r = kernel_filter_table(filter_type, tkx, tkz, &ksize, &factor);
+        if (r != NZ_OK) return r;
+        return bandset_separable(bs, ksize, tkx, tkz, factor, iterations, 0, 0, true);
     });
 }
 
@@ -817,7 +1143,7 @@ NZ_API int32_t nz_min_erosion(nz_slice_f32 src, int32_t resolution, int32_t iter
     NZ_REQUIRE(iterations >= 0, "nz_min_erosion: iterations %d < 0", iterations);
     return run_inplace_stage(src, resolution, "nz_min_erosion", true, [&](Mirror& m, float** res) {
         return launch_min_erosion(m.d, m.d_tmp, resolution, resolution, iterations, res, t_state.stream);
-    });
+    }, true, [&](BandSet& bs) { return bandset_min_erosion(bs, iterations, 0, 0, true); });
 }
 
 NZ_API int32_t nz_flowmap(nz_slice_f32 height, int32_t resolution, int32_t iterations, float norm_min, float norm_max) {
@@ -830,11 +1156,104 @@ NZ_API int32_t nz_flowmap(nz_slice_f32 height, int32_t resolution, int32_t itera
             if (r != NZ_OK) return r;
         }
         return launch_flowmap(m.d, m.d_tmp, scratch, resolution, resolution, iterations, norm_min, norm_max, res, t_state.stream);
+    }, /*can_band=*/2 * iterations + 1 <= band_cap_for(resolution), [&](BandSet& bs) {
+        return bandset_flowmap(bs, iterations, norm_min, norm_max, 0, 0, true);
     });
     if (scratch) {
         // the stream may still be using it inside a pipeline: order the release after the work
         if (in_scope()) cudaStreamSynchronize(t_state.stream);
         pool_free(scratch);
+    }
+    return rc;
+}
+
+// The mesh of a large tile is 72 bytes per cell going to the HOST, i.e. PCIe time, not kernel time.  The mesh is therefore
+// built in chunks of vertex rows on the compute stream while the previous chunk goes home on a copy stream: two staging
+// slots of ~128 MB instead of a (R+1)^2 x 48 B + 6 R^2 x 4 B device buffer (19.3 GB at R = 16376), and the kernel time
+// disappears under the download.
+static int32_t mesh_chunked(int mesh_type, void* vertices, uint32_t* indices, int R, int in_res, float tile_height, float tile_size,
+                            const float* d_heights) {
+    cudaStream_t s = t_state.stream;
+    if (!t_state.copy_stream) {
+        NZ_CUDA(cudaStreamCreateWithFlags(&t_state.copy_stream, cudaStreamNonBlocking));
+        for (auto& e : t_state.mesh_ev) NZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = t_state.copy_stream;
+    const int VR = R + 1;
+    const size_t row_v = (size_t)VR * NZ_MESH_VERTEX_BYTES, row_i = (size_t)6 * R * sizeof(uint32_t);
+    long long per = (128ll << 20) / (long long)(row_v + row_i);
+    const int rows_per_chunk = (int)(per < 1 ? 1 : (per > VR ? VR : per));
+    const int n_chunks = cdiv(VR, rows_per_chunk);
+    void* d_v[2] = {nullptr, nullptr};
+    void* d_i[2] = {nullptr, nullptr};
+    int32_t rc = NZ_OK;
+    const int n_slots = n_chunks > 1 ? 2 : 1;
+    for (int k = 0; k < n_slots && rc == NZ_OK; k++) {
+        rc = pool_alloc(&d_v[k], rows_per_chunk * row_v);
+        if (rc == NZ_OK) rc = pool_alloc(&d_i[k], rows_per_chunk * row_i);
+    }
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < n_chunks && rc == NZ_OK && e == cudaSuccess; c++) {
+        const int slot = c & 1;
+        const int vz0 = c * rows_per_chunk, vz1 = vz0 + rows_per_chunk < VR ? vz0 + rows_per_chunk : VR;
+        const int t0 = vz0 > 1 ? vz0 : 1;
+        if (c >= 2) e = cudaStreamWaitEvent(s, t_state.mesh_ev[2 + slot], 0);      // the slot's previous chunk has gone home
+        if (e != cudaSuccess) break;
+        rc = launch_mesh(mesh_type, d_v[slot], (uint32_t*)d_i[slot], R, in_res, tile_height, tile_size, d_heights, 0, in_res, vz0, vz1, s);
+        if (rc != NZ_OK) break;
+        e = cudaEventRecord(t_state.mesh_ev[slot], s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, t_state.mesh_ev[slot], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char*)vertices + (size_t)vz0 * row_v, d_v[slot], (size_t)(vz1 - vz0) * row_v, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && vz1 > t0)
+            e = cudaMemcpyAsync((char*)indices + (size_t)(t0 - 1) * row_i, d_i[slot], (size_t)(vz1 - t0) * row_i, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(t_state.mesh_ev[2 + slot], cs);
+    }
+    if (e == cudaSuccess && rc == NZ_OK) e = cudaEventRecord(t_state.ev[2], s);
+    cudaError_t e2 = cudaStreamSynchronize(cs);
+    cudaError_t e3 = cudaStreamSynchronize(s);
+    for (int k = 0; k < 2; k++) {
+        pool_free(d_v[k]);
+        pool_free(d_i[k]);
+    }
+    if (rc != NZ_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "nz_heightmap_mesh");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "nz_heightmap_mesh (download)");
+    if (e3 != cudaSuccess) return cuda_fail(e3, "nz_heightmap_mesh");
+    return NZ_OK;
+}
+
+// heights live on row bands (nz_set_bands): every band builds its slice of the mesh and downloads it over its own PCIe link
+static int32_t mesh_banded(Mirror& m, int mesh_type, void* vertices, uint32_t* indices, int R, float tile_height, float tile_size) {
+    BandSet& bs = *m.bands;
+    int32_t rc = bandset_exchange(bs, 1, 1);
+    if (rc == NZ_OK) rc = bandset_mesh(bs, mesh_type, R, tile_height, tile_size);
+    if (rc != NZ_OK) return rc;
+    const size_t row_v = (size_t)(R + 1) * NZ_MESH_VERTEX_BYTES, row_i = (size_t)6 * R * sizeof(uint32_t);
+    int prev = 0;
+    NZ_CUDA(cudaGetDevice(&prev));
+    cudaError_t e = cudaSuccess;
+    for (Band& bd : bs.b) {
+        if (bd.vz1 <= bd.vz0) continue;
+        const int t0 = bd.vz0 > 1 ? bd.vz0 : 1;
+        e = cudaSetDevice(bd.device);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char*)vertices + (size_t)bd.vz0 * row_v, bd.vtx, (size_t)(bd.vz1 - bd.vz0) * row_v, cudaMemcpyDeviceToHost, bd.s);
+        if (e == cudaSuccess && bd.vz1 > t0)
+            e = cudaMemcpyAsync((char*)indices + (size_t)(t0 - 1) * row_i, bd.idx, (size_t)(bd.vz1 - t0) * row_i, cudaMemcpyDeviceToHost, bd.s);
+        if (e == cudaSuccess) e = cudaEventRecord(bd.done, bd.s);
+        if (e != cudaSuccess) break;
+    }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "nz_heightmap_mesh (banded download)");
+    rc = bandset_sync(bs);
+    // the mesh slices are per-call staging: give them back (19.3 GB / n_bands per device at R = 16376)
+    for (Band& bd : bs.b) {
+        dev_free(bd.vtx);
+        dev_free(bd.idx);
+        bd.vtx = nullptr;
+        bd.idx = nullptr;
+        bd.vtx_bytes = bd.idx_bytes = 0;
     }
     return rc;
 }
@@ -847,37 +1266,22 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
     NZ_REQUIRE(resolution > 0 && input_resolution > 0 && input_resolution <= 46340, "nz_heightmap_mesh: bad resolution");
     int32_t rc = check_slice(heights, (long long)input_resolution * input_resolution, "nz_heightmap_mesh");
     if (rc != NZ_OK) return rc;
+    UnscopedCleanup cleanup;
+    nvtxRangePushA("nz_heightmap_mesh");
+    struct Pop { ~Pop() { nvtxRangePop(); } } pop;
     if ((rc = begin_stage()) != NZ_OK) return rc;
     Mirror* m;
-    if ((rc = acquire(heights, /*need_contents=*/true, &m)) != NZ_OK) return rc;
+    if ((rc = acquire(heights, /*need_contents=*/true, &m, input_resolution)) != NZ_OK) return rc;
     if ((rc = mark_uploaded()) != NZ_OK) return rc;
-    const size_t vbytes = (size_t)(resolution + 1) * (resolution + 1) * NZ_MESH_VERTEX_BYTES;
-    const size_t ibytes = (size_t)6 * resolution * resolution * sizeof(uint32_t);
-    void *d_v = nullptr, *d_i = nullptr;
-    cudaStream_t s = t_state.stream;
-    rc = pool_alloc(&d_v, vbytes);
-    if (rc == NZ_OK) rc = pool_alloc(&d_i, ibytes);
-    if (rc == NZ_OK)
-        rc = launch_mesh(mesh_type, d_v, (uint32_t*)d_i, resolution, input_resolution, tile_height, tile_size, m->d, 0,
-                         input_resolution, 0, resolution + 1, s);
-    cudaError_t e = cudaSuccess;
-    if (rc == NZ_OK) {
-        e = cudaEventRecord(t_state.ev[2], s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(vertices, d_v, vbytes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(indices, d_i, ibytes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaEventRecord(t_state.ev[3], s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (m->bands) {
+        rc = mesh_banded(*m, mesh_type, vertices, indices, resolution, tile_height, tile_size);
+        if (rc == NZ_OK) rc = banded_join(*m);
+        if (rc == NZ_OK) NZ_CUDA(cudaEventRecord(t_state.ev[2], t_state.stream));
+    } else {
+        rc = mesh_chunked(mesh_type, vertices, indices, resolution, input_resolution, tile_height, tile_size, m->d);
     }
-    pool_free(d_v);
-    pool_free(d_i);
-    if (!in_scope()) {
-        // heights were only read: nothing to bring home
-        pool_free(m->d);
-        pool_free(m->d_tmp);
-        t_state.local.mirrors.erase(heights.ptr);
-    }
-    if (rc != NZ_OK) return rc;
-    if (e != cudaSuccess) return cuda_fail(e, "nz_heightmap_mesh");
+    if (rc != NZ_OK) return rc;     // heights were only read: outside a scope the cleanup guard drops their mirror
+    NZ_CUDA(cudaEventRecord(t_state.ev[3], t_state.stream));
     t_state.timed = true;
     t_state.launches = (int)(g_launches.load() - t_state.launches_at_start);
     return NZ_OK;
@@ -886,15 +1290,6 @@ NZ_API int32_t nz_heightmap_mesh(int32_t mesh_type, void* vertices, uint32_t* in
 }  // extern "C"
 
 // ---- the section-8f rows ----------------------------------------------------------------------------------
-// a slice that a stage only reads: outside a pipeline nothing keeps its mirror alive after the call
-static void drop_if_unscoped(Mirror* m) {
-    if (in_scope() || !m) return;
-    const void* key = m->host.ptr;
-    pool_free(m->d);
-    pool_free(m->d_tmp);
-    t_state.local.mirrors.erase(key);
-}
-
 extern "C" {
 
 NZ_API int32_t nz_thermal_erosion(nz_slice_f32 src, float talus, float increment_ratio, float mesh_height_width_ratio,
@@ -930,6 +1325,10 @@ NZ_API int32_t nz_constant(nz_slice_f32 src, nz_slice_f32 tmp, int32_t operation
     NZ_REQUIRE(operation >= 0 && operation < NZ_CONSTANT__COUNT, "nz_constant: operation %d out of range", operation);
     return run_inplace_stage(src, resolution, "nz_constant", false, [&](Mirror& m, float**) {
         return launch_constant(m.d, m.n, operation, constant_value, t_state.stream);
+    }, true, [&](BandSet& bs) {
+        return bandset_stage(bs, 0, 0, [&](Band& bd, float* cur, float*, int rows, int, float**) {
+            return launch_constant(cur, (size_t)rows * bs.width, operation, constant_value, bd.s);
+        });
     });
 }
 
@@ -939,6 +1338,10 @@ NZ_API int32_t nz_normalize(nz_slice_f32 src, nz_slice_f32 tmp, const float* arg
     const float vmin = args3[0], range = args3[2];
     return run_inplace_stage(src, resolution, "nz_normalize", false, [&](Mirror& m, float**) {
         return launch_normalize(m.d, m.n, vmin, range, t_state.stream);
+    }, true, [&](BandSet& bs) {
+        return bandset_stage(bs, 0, 0, [&](Band& bd, float* cur, float*, int rows, int, float**) {
+            return launch_normalize(cur, (size_t)rows * bs.width, vmin, range, bd.s);
+        });
     });
 }
 
@@ -955,8 +1358,7 @@ NZ_API int32_t nz_reduce(nz_slice_f32 left, nz_slice_f32 right, nz_slice_f32 tmp
         if (rr != NZ_OK) return rr;
         return launch_reduce(m.d, r->d, m.n, operation, t_state.stream);
     });
-    drop_if_unscoped(r);    // run_inplace_stage synchronised the stream when no scope is open
-    return rc;
+    return rc;              // outside a scope run_inplace_stage's cleanup guard has released the right operand's mirror
 }
 
 NZ_API int32_t nz_curve(nz_slice_f32 src, nz_slice_f32 tmp, nz_slice_f32 curve, int32_t resolution) {
@@ -969,7 +1371,6 @@ NZ_API int32_t nz_curve(nz_slice_f32 src, nz_slice_f32 tmp, nz_slice_f32 curve, 
         if (rr != NZ_OK) return rr;
         return launch_curve(m.d, m.n, c->d, curve.length, t_state.stream);
     });
-    drop_if_unscoped(c);
     return rc;
 }
 
@@ -981,6 +1382,7 @@ NZ_API int32_t nz_crop(nz_slice_f32 input, int32_t input_resolution, nz_slice_f3
     if (rc != NZ_OK) return rc;
     if ((rc = check_slice(output, (long long)output_resolution * output_resolution, "nz_crop(output)")) != NZ_OK) return rc;
     NZ_REQUIRE(input.ptr != output.ptr, "nz_crop: input and output are the same slice");
+    UnscopedCleanup cleanup;
     if ((rc = begin_stage()) != NZ_OK) return rc;
     Mirror *in = nullptr, *out = nullptr;
     if ((rc = acquire(input, /*need_contents=*/true, &in)) != NZ_OK) return rc;
@@ -989,13 +1391,13 @@ NZ_API int32_t nz_crop(nz_slice_f32 input, int32_t input_resolution, nz_slice_f3
     rc = launch_crop(in->d, input_resolution, out->d, output_resolution, offset, t_state.stream);
     if (rc == NZ_OK) out->dirty = true;
     int32_t rc2 = finish(out);
-    drop_if_unscoped(in);
     return rc != NZ_OK ? rc : rc2;
 }
 
 NZ_API int32_t nz_map_range(nz_slice_f32 map, float* res3, float lim_min, float lim_max) {
     NZ_REQUIRE(res3 != nullptr, "nz_map_range: result pointer is null");
     NZ_REQUIRE(map.ptr && map.length > 0 && map.stride_bytes >= 4, "nz_map_range: empty map");
+    UnscopedCleanup cleanup;
     int32_t rc = begin_stage();
     if (rc != NZ_OK) return rc;
     Mirror* m = nullptr;
@@ -1016,7 +1418,6 @@ NZ_API int32_t nz_map_range(nz_slice_f32 map, float* res3, float lim_min, float 
         }
     }
     pool_free(scratch);
-    drop_if_unscoped(m);
     if (rc != NZ_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "nz_map_range");
     t_state.timed = true;

@@ -41,6 +41,18 @@ bool aux_disabled() {
 
 }  // namespace
 
+int sm_count() {
+    static std::atomic<int> cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 int32_t aux_fork(cudaStream_t main, cudaStream_t* aux) {
     if (aux_disabled()) {
         *aux = main;

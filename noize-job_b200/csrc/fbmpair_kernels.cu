@@ -450,19 +450,14 @@ bool fractal_pair_supported(int noise_type, const FractalParams& p) {
 }
 
 int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s) {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        NZ_CUDA(cudaGetDevice(&dev));
-        NZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    static bool configured = false;   // per-process; the attribute is per-function and sticky
-    if (!configured) {
+    const int sms = sm_count();
+    static DeviceOnce configured;     // the attribute is per function AND per device, and sticky
+    if (configured.need()) {
         NZ_CUDA(cudaFuncSetAttribute(fbm_simplex_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_perlin_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PERLIN_SMEM));
-        configured = true;
+        configured.mark();
     }
     int wshift = 5;
     while ((1 << wshift) < p.width && wshift < 10) wshift++;

@@ -350,11 +350,11 @@ int32_t launch_min_erosion(float* d_data, float* d_tmp, int width, int rows, int
     if (iterations > 0 && iterations <= MIN_FUSED_MAX_N) {
         const int n = iterations;
         const size_t smem = ((size_t)(MH + n) * (MW + n) + (size_t)(MH + n) * MW) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_set;
+        if (attr_set.need()) {
             NZ_CUDA(cudaFuncSetAttribute(min_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(((MH + MIN_FUSED_MAX_N) * (MW + MIN_FUSED_MAX_N) + (MH + MIN_FUSED_MAX_N) * MW) * sizeof(float))));
-            attr_set = true;
+            attr_set.mark();
         }
         dim3 grid(cdiv(width, MW), cdiv(rows, MH));
         min_window_kernel<<<grid, MTHREADS, smem, s>>>(d_data, d_tmp, width, rows, n);

@@ -217,14 +217,14 @@ bool flow_tile_supported(int width, int rows, int iterations, const void* a, con
 // d_out must not alias d_height
 int32_t launch_flow_tile(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min, float norm_max,
                          cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.need()) {
         NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-        attr_set = true;
+        attr_set.mark();
     }
     const int I = iterations;
     TileParams p;
@@ -237,8 +237,7 @@ int32_t launch_flow_tile(const float* d_height, float* d_out, int width, int row
     p.nrange = norm_max - norm_min;
     p.nsign = copysignf(1.0f, p.nrange);
     p.zero_ok = (p.nrange != 0.0f) && isfinite(p.nrange);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = sm_count();
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     switch (I) {
         case 1: flow_tile_kernel<1><<<grid, FT_THREADS, FT_SMEM, s>>>(p); break;

@@ -378,14 +378,14 @@ bool flow_wave_supported(int width, int rows, int iterations, const void* a, con
 // d_out must not alias d_height
 int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
                          float norm_max, cudaStream_t s, const unsigned* gate, unsigned epoch, unsigned* reruns) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.need()) {
         NZ_CUDA(cudaFuncSetAttribute(flow_wave_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem_bytes(1)));
         NZ_CUDA(cudaFuncSetAttribute(flow_wave_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem_bytes(2)));
         NZ_CUDA(cudaFuncSetAttribute(flow_wave_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem_bytes(3)));
         NZ_CUDA(cudaFuncSetAttribute(flow_wave_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem_bytes(4)));
         NZ_CUDA(cudaFuncSetAttribute(flow_wave_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem_bytes(5)));
-        attr_set = true;
+        attr_set.mark();
     }
     const int I = iterations;
     WaveParams p;
@@ -399,8 +399,7 @@ int32_t launch_flow_wave(const float* d_height, float* d_out, int width, int row
     p.zero_ok = (p.nrange != 0.0f) && isfinite(p.nrange);
     const int strips = cdiv(width, p.swi);
     // rows per chunk: long enough to amortise the 6I-row pipeline fill, and a CTA count that fills whole waves
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = sm_count();
     int best_nz = 1;
     double best_cost = 1e300;
     for (int nz = 1; nz <= rows && nz <= 4096; nz++) {

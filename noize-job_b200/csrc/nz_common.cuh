@@ -54,6 +54,8 @@ struct FractalParams {
     int fast_hash;  // every lattice index of this launch is below 2^21 (simplex may use the magic-number residue)
     int fast_hash3d;  // the same for the domain-rotated 3-D bases (their rotated / skewed coordinates are up to 3x larger)
 };
+int32_t fractal_params(FractalParams* p, int width, int rows, int z_first, int noise_type, float hurst, float start_amp,
+                       float stepdown, float detune, int octaves, int xpos, int zpos, int noise_size);   // abi.cu
 int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
 bool fractal_pair_supported(int noise_type, const FractalParams& p);
 int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
@@ -104,6 +106,10 @@ int32_t launch_map_range(const float* d, size_t n, float lim_min, float lim_max,
 int32_t launch_fma_peak(float* d_sink, int grid, int iters, double* flops, cudaStream_t s);
 int32_t launch_gather_strided(float* d_dst, const unsigned char* d_src, int stride_bytes, size_t n, cudaStream_t s);
 
+// device-buffer pool (abi.cu): blocks of the CURRENT device; dev_free expects every use of the block to be complete
+int32_t dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+
 // side stream of the calling thread on the current device (aux_stream.cu)
 int32_t aux_fork(cudaStream_t main, cudaStream_t* aux);
 int32_t aux_join(cudaStream_t main);
@@ -113,5 +119,20 @@ void gauss_table(double sigma, int width, float* out);
 int32_t kernel_filter_table(int filter, float* kx, float* kz, int* ksize, float* factor);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// One-time setup that is PER DEVICE (cudaFuncSetAttribute applies to the current device only): need() is true until
+// mark() has been called on the current device.  The setups guarded by it are idempotent, so a race repeats one, no more.
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    static unsigned long long bit() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return 1ull << (dev & 63);
+    }
+    bool need() const { return !(done.load(std::memory_order_acquire) & bit()); }
+    void mark() { done.fetch_or(bit(), std::memory_order_release); }
+};
+// multiprocessor count of the CURRENT device (cached per device)
+int sm_count();
 
 }  // namespace nz

@@ -171,11 +171,11 @@ sep_fused_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, 
 template <int R>
 int32_t launch_fused_r(float* d_data, float* d_tmp, int width, int rows, const float* kx, const float* kz, float factor,
                        int iterations, float** d_result, cudaStream_t s) {
-    static bool attr_set = false;  // benign race: the attribute is idempotent
-    if (!attr_set) {
+    static DeviceOnce attr_set;  // benign race: the attribute is idempotent
+    if (attr_set.need()) {
         NZ_CUDA(cudaFuncSetAttribute(sep_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         NZ_CUDA(cudaFuncSetAttribute(sep_fused_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
+        attr_set.mark();
     }
     TapsR<R> tx, tz;
     for (int i = 0; i < 2 * R + 1; i++) {

@@ -301,8 +301,7 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     if (ez) {
         zc = atoi(ez);
     } else {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int sms = sm_count();
         const long long slots = 5LL * sms;               // 5 CTAs of 128 threads x 96 registers per SM
         const int warm = R * T + 2 * R + 1 + 3;
         double best = 1e300;

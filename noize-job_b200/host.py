@@ -17,8 +17,20 @@ def version():
 
 
 def init(device=0):
-    arr = (C.c_int32 * 1)(device)
-    _l.check(_l.load().nz_init(arr, 1))
+    """nz_init: `device` is one ordinal or a list of them (devices[0] runs the host layer; see set_bands)."""
+    devs = [int(device)] if isinstance(device, int) else [int(d) for d in device]
+    arr = (C.c_int32 * len(devs))(*devs)
+    _l.check(_l.load().nz_init(arr, len(devs)))
+
+
+def set_bands(n_bands):
+    """nz_set_bands: host-layer stage calls on grids of >= 4096 rows run on n_bands row bands, one per device of init()."""
+    _l.check(_l.load().nz_set_bands(int(n_bands)))
+
+
+def test_fail_allocs(skip, count):
+    """Fault injection (tests): after `skip` more device allocations the next `count` fail with NZ_E_NOMEM."""
+    _l.check(_l.load().nz_test_fail_allocs(int(skip), int(count)))
 
 
 def kernel_launch_count():

@@ -31,6 +31,25 @@ class Slice(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("stride_bytes", C.c_int32), ("length", C.c_int32)]
 
 
+class ChainConfig(C.Structure):
+    """nz_chain_config: the BASELINE C5 chain on one resolution^2 heightmap."""
+    _fields_ = [("resolution", C.c_int32),
+                ("noise_type", C.c_int32), ("hurst", C.c_float), ("starting_amplitude", C.c_float), ("stepdown", C.c_float),
+                ("detune_rate", C.c_float), ("octaves", C.c_int32), ("xpos", C.c_int32), ("zpos", C.c_int32), ("noise_size", C.c_int32),
+                ("filter_type", C.c_int32), ("filter_iterations", C.c_int32),
+                ("flow_iterations", C.c_int32), ("norm_min", C.c_float), ("norm_max", C.c_float),
+                ("erosion_iterations", C.c_int32),
+                ("mesh_type", C.c_int32), ("mesh_resolution", C.c_int32), ("mesh_margin_pix", C.c_int32),
+                ("tile_height", C.c_float), ("tile_size", C.c_float)]
+
+
+class BandInfo(C.Structure):
+    """nz_band_info"""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32), ("z0", C.c_int32), ("z1", C.c_int32),
+                ("vz0", C.c_int32), ("vz1", C.c_int32), ("d_rows", C.c_void_p), ("d_vertices", C.c_void_p),
+                ("d_indices", C.c_void_p), ("halo_bytes_per_run", C.c_int64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("ms_h2d", C.c_float), ("ms_kernel", C.c_float), ("ms_d2h", C.c_float), ("kernel_launches", C.c_int32)]
 
@@ -45,6 +64,21 @@ SIGNATURES = {
     "nz_version": (C.c_char_p, []),
     "nz_kernel_launch_count": (C.c_int64, []),
     "nz_last_timing": (_i32, [C.POINTER(Timing)]),
+    "nz_test_fail_allocs": (_i32, [_i32, _i32]),
+    "nz_set_bands": (_i32, [_i32]),
+    "nz_comm_unique_id": (_i32, [_vp, _i32]),
+    "nz_comm_create": (C.c_int64, [_vp, _i32, _i32, _i32]),
+    "nz_comm_async_error": (_i32, [C.c_int64]),
+    "nz_comm_destroy": (_i32, [C.c_int64]),
+    "nz_band_chain_create": (C.c_int64, [C.POINTER(ChainConfig), C.c_int64, _i32, _i32, _vp]),
+    "nz_band_chain_create_local": (C.c_int64, [C.POINTER(ChainConfig), _pi32, _i32, _i32]),
+    "nz_band_chain_run": (_i32, [C.c_int64, _i32]),
+    "nz_band_chain_sync": (_i32, [C.c_int64]),
+    "nz_band_chain_stage_ms": (_i32, [C.c_int64, _pf32]),
+    "nz_band_chain_local_bands": (_i32, [C.c_int64]),
+    "nz_band_chain_info": (_i32, [C.c_int64, _i32, C.POINTER(BandInfo)]),
+    "nz_band_chain_download": (_i32, [C.c_int64, _vp, _vp, _vp]),
+    "nz_band_chain_destroy": (_i32, [C.c_int64]),
     "nz_fractal_norm_value": (_f32, [_f32, _i32]),
     "nz_gauss_kernel": (_i32, [_i32, _i32, _pf32, _pi32]),
     "nz_limit_width": (_i32, [_i32]),

@@ -82,6 +82,8 @@ def _bind(lib):
     lib.nzref_normalize.restype = i32
     lib.nzref_normalize.argtypes = [_f32p, i64, _f32p]
     lib.nzref_num_threads.restype = i32
+    lib.nzref_set_num_threads.restype = i32
+    lib.nzref_set_num_threads.argtypes = [i32]
     lib.nzref_mod289_mismatches.restype = C.c_int64
     lib.nzref_mod289_mismatches.argtypes = [i32, i32, C.POINTER(i32)]
     lib.nzref_mod7_mismatches.restype = i32
@@ -254,6 +256,10 @@ class Oracle:
 
     def num_threads(self):
         return int(self.lib.nzref_num_threads())
+
+    def set_num_threads(self, n):
+        """OpenMP worker count for every later call (overrides OMP_NUM_THREADS); returns the count now in force."""
+        return int(self.lib.nzref_set_num_threads(int(n)))
 
 
 _cache = {}

@@ -932,6 +932,19 @@ NZREF_API int32_t nzref_num_threads(void) {
     return 1;
 #endif
 }
+/* bench.py's reference arm sets the worker count explicitly (Unity's JobsUtility.JobWorkerCount defaults to
+ * logical cores - 1): launchers such as torchrun export OMP_NUM_THREADS=1, which would otherwise decide it. */
+NZREF_API int32_t nzref_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n < 1) return -1;
+    omp_set_dynamic(0);
+    omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* Known-answer helper: counts integers v in [lo, hi] where the float mod289 differs from the
  * integer modulus (the float form is `x - floor(x*(1/289))*289`, which is NOT integer-mod in
