@@ -477,11 +477,13 @@ def e2e_small_config(env, name, steps=3):
         meshp = nz.BasePipeline([nz.MeshTileStage(nz.MeshType.OvershootSquareGridHeightMap)])
         d2h += mesh.vertices.nbytes + mesh.indices.nbytes
 
+    if name == "C2":
+        stages[-1].keepResident = True          # the mesh pipeline works on the same uuid and closes the scope
+
     def one():
-        with nz.host.pipeline():
-            gen.Run(nz.GeneratorData("bench", data, n, 0, 0))
-            if name == "C2":
-                meshp.Run(nz.MeshStageData("bench", data, R, n, 4, R * (500.0 / 256.0), 2000.0, mesh=mesh))
+        gen.Run(nz.GeneratorData("bench", data, n, 0, 0))
+        if name == "C2":
+            meshp.Run(nz.MeshStageData("bench", data, R, n, 4, R * (500.0 / 256.0), 2000.0, mesh=mesh))
     one()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -702,32 +704,32 @@ def run_e2e(args, env, chain, cfg):
         data = torch.empty(N * N, dtype=torch.float32, pin_memory=True).numpy()
         vtx = torch.empty((R + 1) * (R + 1), 12, dtype=torch.float32, pin_memory=True).numpy()
         idx = torch.empty(6 * R * R, dtype=torch.int32, pin_memory=True).numpy().view("uint32")
-        tail = [
-            nz.KernelFilterStage(nz.KernelFilterType.Gauss5_S1, iterations=cfg.filter_iterations),
-            nz.FlowMapStage(iterations=cfg.flow_iterations, normMin=cfg.norm_min, normMax=cfg.norm_max),
-            nz.ErosionFilterStage(iterations=cfg.erosion_iterations),
-        ]
-        gen = nz.BasePipeline([nz.NoiseStage(nz.FractalNoise.Simplex, hurst=cfg.hurst, octaves=cfg.octaves, noiseSize=cfg.noise_size)] + tail)
+        def tail():
+            st = [nz.KernelFilterStage(nz.KernelFilterType.Gauss5_S1, iterations=cfg.filter_iterations),
+                  nz.FlowMapStage(iterations=cfg.flow_iterations, normMin=cfg.norm_min, normMax=cfg.norm_max),
+                  nz.ErosionFilterStage(iterations=cfg.erosion_iterations)]
+            # residency is owned by the stage objects (GpuStage): the last generator stage brings the heightmap home but
+            # keeps the tile in HBM for the mesh pipeline, which works on the same uuid and closes the scope
+            st[-1].keepResident = True
+            return st
+        gen = nz.BasePipeline([nz.NoiseStage(nz.FractalNoise.Simplex, hurst=cfg.hurst, octaves=cfg.octaves, noiseSize=cfg.noise_size)] + tail())
         meshp = nz.BasePipeline([nz.MeshTileStage(nz.MeshType.OvershootSquareGridHeightMap)])
         mesh = nz.Mesh()
         mesh.vertices, mesh.indices = vtx, idx
 
         def one():
-            # one outer residency scope: the heightmap stays in HBM between the generator and the mesh pipeline
-            with nz.host.pipeline():
-                gen.Run(nz.GeneratorData("bench", data, N, 0, 0))
-                meshp.Run(nz.MeshStageData("bench", data, R, N, cfg.mesh_margin, cfg.tile_size, cfg.tile_height, mesh=mesh))
+            gen.Run(nz.GeneratorData("bench", data, N, 0, 0))
+            meshp.Run(nz.MeshStageData("bench", data, R, N, cfg.mesh_margin, cfg.tile_size, cfg.tile_height, mesh=mesh))
         d2h = data.nbytes + vtx.nbytes + idx.nbytes
 
         # second leg: the chain from a host-resident heightmap (what a Burst NoiseStage, a loaded .data file or a
         # texture hands to the first GPU stage).  The input is refreshed from a second pinned copy outside the timing.
         src = torch.empty(N * N, dtype=torch.float32, pin_memory=True).numpy()
-        filt = nz.BasePipeline(tail)
+        filt = nz.BasePipeline(tail())
 
         def one_in():
-            with nz.host.pipeline():
-                filt.Run(nz.GeneratorData("bench-in", data, N, 0, 0))
-                meshp.Run(nz.MeshStageData("bench-in", data, R, N, cfg.mesh_margin, cfg.tile_size, cfg.tile_height, mesh=mesh))
+            filt.Run(nz.GeneratorData("bench-in", data, N, 0, 0))
+            meshp.Run(nz.MeshStageData("bench-in", data, R, N, cfg.mesh_margin, cfg.tile_size, cfg.tile_height, mesh=mesh))
     else:
         own = torch.empty(chain.own, N, dtype=torch.float32, pin_memory=True)
         chain.run()

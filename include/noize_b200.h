@@ -334,7 +334,9 @@ NZ_API int32_t nz_comm_async_error(int64_t comm);
 NZ_API int32_t nz_comm_destroy(int64_t comm);
 
 /* One band of the chain in this process (rank/world/device of `comm`; comm == 0: a single band on `device`).  `stream` is
- * the cudaStream_t the band's work is enqueued on (NULL: a stream of the library's own). */
+ * the cudaStream_t the band's work is enqueued on (NULL = the legacy default stream, as in the device layer;
+ * NZ_STREAM_OWN = a non-blocking stream the library creates). */
+#define NZ_STREAM_OWN ((void*)(intptr_t)-1)
 NZ_API int64_t nz_band_chain_create(const nz_chain_config* cfg, int64_t comm, int32_t device, int32_t mode, void* stream);
 /* All n_bands bands in this process, band b on devices[b] (entries may repeat); ghost rows move by peer copies. */
 NZ_API int64_t nz_band_chain_create_local(const nz_chain_config* cfg, const int32_t* devices, int32_t n_bands, int32_t mode);

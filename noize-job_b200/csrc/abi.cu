@@ -436,7 +436,8 @@ static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out, 
         int32_t rc;
         if (banded) {
             std::unique_ptr<BandSet> bs;
-            rc = bandset_create(&bs, band_res, band_res, n_bands, 0, n_bands, devs.data(), BAND_GHOST_CAP, nullptr, nullptr);
+            rc = bandset_create(&bs, band_res, band_res, n_bands, 0, n_bands, devs.data(), BAND_GHOST_CAP, nullptr,
+                                (cudaStream_t)NZ_STREAM_OWN);
             if (rc != NZ_OK) return rc;
             m.bands = std::move(bs);
             if (need_contents && (rc = banded_copy_rows(m, /*to_host=*/false)) != NZ_OK) return rc;   // m frees its bands

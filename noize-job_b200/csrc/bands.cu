@@ -188,8 +188,8 @@ int32_t bandset_create(std::unique_ptr<BandSet>* out, int width, int rows, int w
             int32_t rc = dev_alloc((void**)&p, bytes);
             if (rc != NZ_OK) return rc;
         }
-        if (stream && n_local == 1) {
-            bd.s = stream;
+        if (stream != (cudaStream_t)NZ_STREAM_OWN && n_local == 1) {
+            bd.s = stream;              // the caller's stream (NULL: the legacy default stream)
         } else {
             NZ_CUDA(cudaStreamCreateWithFlags(&bd.s, cudaStreamNonBlocking));
             bd.own_stream = true;
@@ -727,7 +727,8 @@ NZ_API int64_t nz_band_chain_create_local(const nz_chain_config* cfg, const int3
     auto c = std::make_shared<Chain>();
     int32_t rc = chain_setup(*c, cfg, mode);
     if (rc != NZ_OK) return rc;
-    rc = bandset_create(&c->bs, cfg->resolution, cfg->resolution, n_bands, 0, n_bands, devices, chain_cap(*c), nullptr, nullptr);
+    rc = bandset_create(&c->bs, cfg->resolution, cfg->resolution, n_bands, 0, n_bands, devices, chain_cap(*c), nullptr,
+                        (cudaStream_t)NZ_STREAM_OWN);
     if (rc != NZ_OK) return rc;
     if ((rc = chain_check_fit(*c)) != NZ_OK) return rc;
     std::lock_guard<std::mutex> lk(g_handles_mu);

@@ -185,6 +185,11 @@ def normalize(src, tmp, args3, resolution):
 _scope = threading.local()
 
 
+def thread_in_scope():
+    """True while the calling thread is inside a residency scope it opened through this module."""
+    return getattr(_scope, "depth", 0) > 0 or getattr(_scope, "entered", 0) > 0
+
+
 def pipeline_begin():
     """Open a residency scope on this thread.  Scopes nest: only the outermost one talks to the library, so a
     caller can keep tiles resident across several pipelines (e.g. the generator pipeline and the mesh pipeline)."""
@@ -237,9 +242,11 @@ def scope_close(scope):
 def in_scope(scope):
     """Bracket one stage call made on the current thread inside `scope`."""
     scope_enter(scope)
+    _scope.entered = getattr(_scope, "entered", 0) + 1
     try:
         yield
     finally:
+        _scope.entered -= 1
         scope_leave()
 
 

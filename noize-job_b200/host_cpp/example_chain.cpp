@@ -27,6 +27,7 @@ int main(int argc, char** argv) {
         KernelFilterStage gauss; gauss.filter = KernelFilterType::Gauss5_S1; gauss.iterations = 17;
         FlowMapStage flow; flow.iterations = 5; flow.normMin = 0.f; flow.normMax = 0.005f;
         ErosionFilterStage erosion; erosion.iterations = 5;
+        erosion.keepResident = true;       // the mesh pipeline below works on the same uuid: the tile stays in HBM for it
         BasePipeline generator({&noise, &gauss, &flow, &erosion});
         int completed = 0;
         generator.Run(&gd, [&](StageIO*) { completed++; });
@@ -38,6 +39,7 @@ int main(int argc, char** argv) {
         MeshTileStage meshStage; meshStage.meshType = MeshType::OvershootSquareGridHeightMap;
         BasePipeline mesher({&meshStage});
         mesher.Run(&md);
+        if (GpuResidency::IsOpen("c2")) { printf("ERROR: the mesh stage must have closed the scope\n"); return 3; }
 
         printf("%s completed=%d launches=%lld height=%016llx vertices=%016llx indices=%016llx\n", nz_version(), completed,
                (long long)nz_kernel_launch_count(), fnv(tile.data(), tile.size() * 4),

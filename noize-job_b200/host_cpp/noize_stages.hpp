@@ -15,14 +15,16 @@
 //   BasePipeline (scheduling chain)   Pipeline/Executable/Pipeline.cs:104-181
 //   ErosionFilterStage                new: wraps ErosionKernelJob (Filter/Kernel/KernelJob.cs:317-350)
 //
-// A NativeSlice<float> is nz_slice_f32 {ptr, stride_bytes, length}.  JobHandle::Complete() returns when the
-// host buffers hold the results (the reference handle's contract); until then the device copies stay
-// resident (nz_pipeline_begin / nz_pipeline_end).  Header-only; link with -lnoize_b200.
+// A NativeSlice<float> is nz_slice_f32 {ptr, stride_bytes, length}.  Residency is owned by the stage objects: the first GPU
+// stage of a work item opens a scope keyed by StageIO.uuid, the last one before a host consumer closes it (one D2H per
+// dirty slice), exactly as the C# GpuStage does.  Header-only; link with -lnoize_b200.
 #pragma once
 #include <cstdint>
 #include <deque>
 #include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -49,34 +51,63 @@ enum class MeshType { SquareGridHeightMap, OvershootSquareGridHeightMap };
 enum class ConstantOperationType { MULTIPLY, BINARIZE };                          // Filter/ConstantStage.cs:15-18
 enum class ReductionType { SUBTRACT, MULTIPLY, ROOTSUMSQUARES, MAX, MIN };        // Filter/Reduce/ReduceStage.cs:12-18
 
-// ---- job handle: one residency scope shared by the stages of a scheduled chain ----------------------
+// ---- job handle + residency (same logic as unity/Interop/NoizeB200.cs: GpuResidency, CloseScopeJob, FlushScopeJob) ----
+// The native calls of this mirror run inline where Unity would run an IJob on a worker thread, so a handle is complete
+// when it is returned.
 class JobHandle {
-    struct Scope {
-        bool open = true;
-        Scope() { check(nz_pipeline_begin(), "nz_pipeline_begin"); }
-        void close() {
-            if (open) {
-                open = false;
-                check(nz_pipeline_end(), "nz_pipeline_end");
-            }
-        }
-        ~Scope() {
-            if (open) nz_pipeline_end();
-        }
-    };
-    std::shared_ptr<Scope> scope_;
+public:
+    bool IsCompleted() const { return true; }
+    void Complete() {}
+};
+
+// uuid -> residency scope (nz_scope_*) shared by the GPU stages that work on ONE work item (StageIO.uuid).
+class GpuResidency {
+    static std::map<std::string, int64_t>& scopes() {
+        static std::map<std::string, int64_t> m;
+        return m;
+    }
+    static std::mutex& mu() {
+        static std::mutex m;
+        return m;
+    }
 
 public:
-    JobHandle() = default;
-    static JobHandle Chain(const JobHandle& dependency) {
-        if (dependency.scope_ && dependency.scope_->open) return dependency;
-        JobHandle h;
-        h.scope_ = std::make_shared<Scope>();
-        return h;
+    static int64_t Enter(const std::string& uuid) {
+        std::lock_guard<std::mutex> lk(mu());
+        auto it = scopes().find(uuid);
+        if (it != scopes().end()) return it->second;
+        const int64_t scope = nz_scope_create();
+        if (scope < 0) check((int32_t)scope, "nz_scope_create");
+        scopes()[uuid] = scope;
+        return scope;
     }
-    bool IsCompleted() const { return !scope_ || !scope_->open; }
-    void Complete() {
-        if (scope_) scope_->close();
+    static void Close(const std::string& uuid) {              // CloseScopeJob
+        int64_t scope = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            auto it = scopes().find(uuid);
+            if (it == scopes().end()) return;
+            scope = it->second;
+            scopes().erase(it);
+        }
+        check(nz_scope_close(scope), "nz_scope_close");
+    }
+    static void Flush(const std::string& uuid, nz_slice_f32 data) {   // FlushScopeJob
+        int64_t scope = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu());
+            auto it = scopes().find(uuid);
+            if (it == scopes().end()) return;
+            scope = it->second;
+        }
+        check(nz_scope_enter(scope), "nz_scope_enter");
+        const int32_t rc = nz_flush_to_host(data.ptr);
+        nz_scope_leave();
+        check(rc, "nz_flush_to_host");
+    }
+    static bool IsOpen(const std::string& uuid) {
+        std::lock_guard<std::mutex> lk(mu());
+        return scopes().count(uuid) != 0;
     }
 };
 
@@ -123,6 +154,8 @@ protected:
 
 public:
     std::function<void(PipelineWorkItem&, JobHandle)> OnStageScheduledAction;
+    PipelineStage* nextStage = nullptr;   // receiver of OnStageScheduledAction when it is a stage (C#: Delegate.Target)
+    virtual bool IsGpuStage() const { return false; }
     virtual ~PipelineStage() = default;
     virtual void ResizeNativeContainers(int) {}
     virtual bool IsSchedulable(const PipelineWorkItem&) { return true; }
@@ -150,106 +183,130 @@ public:
     virtual void OnDestroy() {}
 };
 
-class NoiseStage : public PipelineStage {
+// Base of every stage that runs on the GPU: stage objects, not the pipeline, own residency (see NoizeB200.cs: GpuStage).
+class GpuStage : public PipelineStage {
+public:
+    bool keepResident = false;   // last GPU stage of a pipeline: flush the result home, keep the tile in HBM
+    bool IsGpuStage() const override { return true; }
+
+protected:
+    // NativeCallJob.Execute: enter the work item's scope, make the one blocking native call, leave
+    template <class F>
+    void Native(PipelineWorkItem& requirements, const char* what, F&& call) {
+        const std::string& uuid = requirements.data->uuid;
+        const int64_t scope = GpuResidency::Enter(uuid);
+        check(nz_scope_enter(scope), "nz_scope_enter");
+        const int32_t rc = call();
+        nz_scope_leave();
+        if (rc < 0) {
+            std::string msg = std::string(what) + ": " + nz_last_error();
+            try { GpuResidency::Close(uuid); } catch (...) {}
+            throw NzError(rc, msg);
+        }
+        jobHandle = JobHandle();
+    }
+
+public:
+    void OnStageScheduled(PipelineWorkItem& requirements, JobHandle dependency) override {
+        // hand-over to something that reads HOST memory: the scope's close (or flush) goes in front of the handle
+        if (!(nextStage && nextStage->IsGpuStage())) {
+            if (keepResident) GpuResidency::Flush(requirements.data->uuid, requirements.data->data);
+            else GpuResidency::Close(requirements.data->uuid);
+        }
+        PipelineStage::OnStageScheduled(requirements, dependency);
+    }
+};
+
+class NoiseStage : public GpuStage {
 public:
     FractalNoise noiseType = FractalNoise::Sin;
     float hurst = 0.f, startingAmplitude = 1.f, stepdown = 2.f, detuneRate = 0.f;
     int octaves = 1, noiseSize = 1000;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_fractal(d->data, d->resolution, (int)noiseType, hurst, startingAmplitude, stepdown, detuneRate, octaves,
-                         d->xpos, d->zpos, noiseSize), "nz_fractal");
+        Native(requirements, "nz_fractal", [&] { return nz_fractal(d->data, d->resolution, (int)noiseType, hurst, startingAmplitude, stepdown, detuneRate, octaves,
+                         d->xpos, d->zpos, noiseSize); });
     }
 };
 
-class KernelFilterStage : public PipelineStage {
+class KernelFilterStage : public GpuStage {
 public:
     KernelFilterType filter = KernelFilterType::Gauss9_S1;
     int iterations = 1;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
         // the reference chains `iterations` jobs; the GPU stage issues ONE fused call
-        check(nz_kernel_filter(d->data, nz_slice_f32{nullptr, 0, 0}, (int)filter, d->resolution, iterations), "nz_kernel_filter");
+        Native(requirements, "nz_kernel_filter", [&] { return nz_kernel_filter(d->data, nz_slice_f32{nullptr, 0, 0}, (int)filter, d->resolution, iterations); });
     }
 };
 
-class StageGaussianBlur : public PipelineStage {
+class StageGaussianBlur : public GpuStage {
 public:
     int iterations = 1, sigma = 0, width = 3;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_gauss_filter(d->data, nz_slice_f32{nullptr, 0, 0}, width, sigma, d->resolution, iterations), "nz_gauss_filter");
+        Native(requirements, "nz_gauss_filter", [&] { return nz_gauss_filter(d->data, nz_slice_f32{nullptr, 0, 0}, width, sigma, d->resolution, iterations); });
     }
 };
 
-class StageSmoothBlur : public PipelineStage {
+class StageSmoothBlur : public GpuStage {
 public:
     int iterations = 1, width = 1;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_smooth_filter(d->data, nz_slice_f32{nullptr, 0, 0}, width, d->resolution, iterations), "nz_smooth_filter");
+        Native(requirements, "nz_smooth_filter", [&] { return nz_smooth_filter(d->data, nz_slice_f32{nullptr, 0, 0}, width, d->resolution, iterations); });
     }
 };
 
-class ErosionFilterStage : public PipelineStage {
+class ErosionFilterStage : public GpuStage {
 public:
     int iterations = 5;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_min_erosion(d->data, d->resolution, iterations), "nz_min_erosion");
+        Native(requirements, "nz_min_erosion", [&] { return nz_min_erosion(d->data, d->resolution, iterations); });
     }
 };
 
 // ---- SURVEY section 8f rows ---------------------------------------------------------------------------------
-class StageThermalErosion : public PipelineStage {      // Filter/Kernel/Blur/StageThermalErosion.cs:13-29
+class StageThermalErosion : public GpuStage {      // Filter/Kernel/Blur/StageThermalErosion.cs:13-29
 public:
     int iterations = 1, talus = 45;
     float increment = 0.5f, meshHeightWidthRatio = 0.75f;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_thermal_erosion(d->data, (float)talus, increment, meshHeightWidthRatio, iterations, d->resolution), "nz_thermal_erosion");
+        Native(requirements, "nz_thermal_erosion", [&] { return nz_thermal_erosion(d->data, (float)talus, increment, meshHeightWidthRatio, iterations, d->resolution); });
     }
 };
 
-class ErosionStageSubtractiveFlow : public PipelineStage {   // Geologic/Stage/ErosionStageSubtractiveFlow.cs:17-247 (commented out upstream)
+class ErosionStageSubtractiveFlow : public GpuStage {   // Geologic/Stage/ErosionStageSubtractiveFlow.cs:17-247 (commented out upstream)
 public:
     int flowIterations = 5;                              // serialised upstream, read by nothing (:19-20, :226-228)
     float normMin = -0.1f, normMax = 0.1f, erosiveFactor = 0.1f;
     int erosiveIterations = 5;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_subtractive_flow_erosion(d->data, d->resolution, erosiveIterations, erosiveFactor, normMin, normMax),
-              "nz_subtractive_flow_erosion");
+        Native(requirements, "nz_subtractive_flow_erosion", [&] { return nz_subtractive_flow_erosion(d->data, d->resolution, erosiveIterations, erosiveFactor, normMin, normMax); });
     }
 };
 
-class ConstantStage : public PipelineStage {            // Filter/ConstantStage.cs:13-60
+class ConstantStage : public GpuStage {            // Filter/ConstantStage.cs:13-60
 public:
     ConstantOperationType operation = ConstantOperationType::MULTIPLY;
     float value = 0.5f;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_constant(d->data, nz_slice_f32{nullptr, 0, 0}, (int)operation, value, d->resolution), "nz_constant");
+        Native(requirements, "nz_constant", [&] { return nz_constant(d->data, nz_slice_f32{nullptr, 0, 0}, (int)operation, value, d->resolution); });
     }
 };
 
-class ReduceStage : public PipelineStage {              // Filter/Reduce/ReduceStage.cs:21-68
+class ReduceStage : public GpuStage {              // Filter/Reduce/ReduceStage.cs:21-68
     GeneratorData transformed;
 
 public:
     ReductionType operation = ReductionType::SUBTRACT;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         ReduceData* d = CheckRequirements<ReduceData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_reduce(d->data, d->rightData, nz_slice_f32{nullptr, 0, 0}, (int)operation, d->resolution), "nz_reduce");
+        Native(requirements, "nz_reduce", [&] { return nz_reduce(d->data, d->rightData, nz_slice_f32{nullptr, 0, 0}, (int)operation, d->resolution); });
     }
     void TransformData(PipelineWorkItem& inputData) override {   // downstream stages see a GeneratorData (:52-61)
         ReduceData* d = static_cast<ReduceData*>(inputData.data);
@@ -259,7 +316,7 @@ public:
     }
 };
 
-class CurveStage : public PipelineStage {               // Filter/Curve/CurveStage.cs:13-73
+class CurveStage : public GpuStage {               // Filter/Curve/CurveStage.cs:13-73
     std::vector<float> curve;
 
 public:
@@ -271,34 +328,31 @@ public:
     }
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_curve(d->data, nz_slice_f32{nullptr, 0, 0}, nz_slice_f32{curve.data(), 4, (int32_t)curve.size()}, d->resolution), "nz_curve");
+        Native(requirements, "nz_curve", [&] { return nz_curve(d->data, nz_slice_f32{nullptr, 0, 0}, nz_slice_f32{curve.data(), 4, (int32_t)curve.size()}, d->resolution); });
     }
 };
 
-class CropStage : public PipelineStage {                // Filter/Sample/CropStage.cs:13-19
+class CropStage : public GpuStage {                // Filter/Sample/CropStage.cs:13-19
 public:
     bool center = false;   // false: the reference's behaviour (CropJob.Offset is never assigned: top-left corner)
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         DownsampleData* d = dynamic_cast<DownsampleData*>(requirements.data);
         if (!d) throw std::runtime_error("Unhandled stageio");
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_crop(d->inputData, d->inputResolution, d->data, d->resolution, center ? (d->inputResolution - d->resolution) / 2 : 0), "nz_crop");
+        Native(requirements, "nz_crop", [&] { return nz_crop(d->inputData, d->inputResolution, d->data, d->resolution, center ? (d->inputResolution - d->resolution) / 2 : 0); });
     }
 };
 
-class FlowMapStage : public PipelineStage {
+class FlowMapStage : public GpuStage {
 public:
     int iterations = 5;
     float normMin = -.1f, normMax = .1f;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
         GeneratorData* d = CheckRequirements<GeneratorData>(requirements);
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_flowmap(d->data, d->resolution, iterations, normMin, normMax), "nz_flowmap");
+        Native(requirements, "nz_flowmap", [&] { return nz_flowmap(d->data, d->resolution, iterations, normMin, normMax); });
     }
 };
 
-class MeshTileStage : public PipelineStage {
+class MeshTileStage : public GpuStage {
 public:
     MeshType meshType = MeshType::SquareGridHeightMap;
     void Schedule(PipelineWorkItem& requirements, JobHandle dependency) override {
@@ -312,9 +366,8 @@ public:
             m.boundsCenter[k] = 0.5f * (k == 1 ? d->tileHeight : d->tileSize);
             m.boundsSize[k] = k == 1 ? d->tileHeight : d->tileSize;
         }
-        jobHandle = JobHandle::Chain(dependency);
-        check(nz_heightmap_mesh((int)meshType, m.vertices.data(), m.indices.data(), R, d->inputResolution, d->marginPix,
-                                d->tileHeight, d->tileSize, d->data), "nz_heightmap_mesh");
+        Native(requirements, "nz_heightmap_mesh", [&] { return nz_heightmap_mesh((int)meshType, m.vertices.data(), m.indices.data(), R, d->inputResolution, d->marginPix,
+                                d->tileHeight, d->tileSize, d->data); });
     }
 };
 
@@ -332,6 +385,7 @@ public:
         for (size_t i = 0; i < stages_.size(); i++) {
             if (i + 1 < stages_.size()) {
                 PipelineStage* next = stages_[i + 1];
+                stages_[i]->nextStage = next;
                 stages_[i]->OnStageScheduledAction = [next](PipelineWorkItem& w, JobHandle h) { next->ReceiveHandledInput(w, h); };
             } else {
                 stages_[i]->OnStageScheduledAction = [this](PipelineWorkItem& w, JobHandle h) { OnPipelineFullyScheduled(w, h); };

@@ -25,6 +25,7 @@ The C# production shim (unity/Interop/NoizeB200.cs) has the same structure with 
 A `NativeSlice<float>` is a 1-D numpy float32 view here (it may be strided).  `JobHandle.Complete()`
 returns when the host buffers hold the results, as the reference's handle does.
 """
+import threading
 from collections import deque
 from enum import IntEnum
 
@@ -85,31 +86,66 @@ class ReductionType(IntEnum):          # Filter/Reduce/ReduceStage.cs:12-18
     MIN = 4
 
 
-# ---- job handle -------------------------------------------------------------------------------------
+# ---- job handle + residency (unity/Interop/NoizeB200.cs: GpuResidency, NativeCallJob, CloseScopeJob, FlushScopeJob) ----
 class JobHandle:
-    """Completion token of scheduled GPU work.  Complete() brings every deferred result back to host."""
-
-    def __init__(self, pipeline_scope=None):
-        self._scope = pipeline_scope
-        self.IsCompleted = pipeline_scope is None
-
-    def Complete(self):
-        if not self.IsCompleted:
-            self._scope.close()
-            self.IsCompleted = True
-
-
-class _ResidencyScope:
-    """One nz_pipeline_begin/nz_pipeline_end bracket shared by the stages of a scheduled chain."""
+    """Completion token of scheduled work.  The native calls of this mirror run inline where Unity would run an IJob on a
+    worker thread, so a handle is complete when it is returned; `Complete()` is kept for the reference's call sites."""
 
     def __init__(self):
-        _h.pipeline_begin()
-        self.open = True
+        self.IsCompleted = True
 
-    def close(self):
-        if self.open:
-            self.open = False
-            _h.pipeline_end()
+    def Complete(self):
+        self.IsCompleted = True
+
+
+class GpuResidency:
+    """uuid -> residency scope (nz_scope_*) shared by the GPU stages that work on ONE work item (StageIO.uuid).
+
+    The FIRST GPU stage of a work item creates the scope, every GPU stage brackets its native call with
+    nz_scope_enter / nz_scope_leave (the call may run on any worker thread), and the LAST GPU stage before a non-GPU consumer
+    (a Burst stage, or the pipeline's fully-scheduled hook, Pipeline/Executable/Pipeline.cs:122-128) chains the scope's close
+    (one D2H per dirty slice) in front of the handle it hands on — or, with `keepResident`, only a flush, so that the next
+    pipeline working on the same uuid (the reference runs the generator pipeline and the mesh pipeline back to back,
+    Scripts/MeshTileGenerator.cs:94-138) finds the tile still in HBM."""
+    _scopes = {}
+    _lock = threading.Lock()
+
+    @classmethod
+    def Enter(cls, uuid):
+        with cls._lock:
+            scope = cls._scopes.get(uuid)
+            if scope is None:
+                scope = cls._scopes[uuid] = _h.scope_create()
+            return scope
+
+    @classmethod
+    def Close(cls, uuid):
+        with cls._lock:
+            scope = cls._scopes.pop(uuid, None)
+        if scope is not None:
+            _h.scope_close(scope)
+
+    @classmethod
+    def Flush(cls, uuid, slices):
+        with cls._lock:
+            scope = cls._scopes.get(uuid)
+        if scope is not None:
+            with _h.in_scope(scope):
+                for a in slices:
+                    if a is not None:
+                        _h.flush_to_host(a)
+
+    @classmethod
+    def IsOpen(cls, uuid):
+        with cls._lock:
+            return uuid in cls._scopes
+
+    @classmethod
+    def CloseAll(cls):
+        with cls._lock:
+            scopes, cls._scopes = list(cls._scopes.values()), {}
+        for scope in scopes:
+            _h.scope_close(scope)
 
 
 # ---- stage IO ---------------------------------------------------------------------------------------
@@ -209,14 +245,47 @@ class PipelineStage:
         pass
 
 
-def _chain(dependency):
-    """GPU stages of one chain share the upstream handle's residency scope (or open a new one)."""
-    if isinstance(dependency, JobHandle) and not dependency.IsCompleted:
-        return dependency
-    return JobHandle(_ResidencyScope())
+class GpuStage(PipelineStage):
+    """Base of every stage that runs on the GPU (C#: abstract class GpuStage : PipelineStage).  Stage objects, not the
+    pipeline, own the residency scope of the work item they are handed."""
+    keepResident = False      # last GPU stage of a pipeline: flush the result to the host but leave the tile in HBM
+
+    def _native(self, requirements, call):
+        """NativeCallJob.Execute: enter the work item's scope, make the one blocking native call, leave.  A caller that
+        already holds a scope on this thread (nz.host.pipeline()) keeps control of residency."""
+        uuid = requirements.data.uuid
+        if _h.thread_in_scope():
+            call()
+        else:
+            scope = GpuResidency.Enter(uuid)
+            try:
+                with _h.in_scope(scope):
+                    call()
+            except Exception:
+                GpuResidency.Close(uuid)      # CloseScopeJob still runs when a stage failed: nothing stays behind
+                raise
+        self.jobHandle = JobHandle()
+
+    def _next_is_gpu_stage(self):
+        nxt = getattr(self.OnStageScheduledAction, "__self__", None)
+        return isinstance(nxt, GpuStage)
+
+    def _slices(self, requirements):
+        d = requirements.data
+        return [getattr(d, "data", None)]
+
+    def OnStageScheduled(self, requirements, dependency):
+        # hand-over to something that reads HOST memory: the scope's close (or flush) goes in front of the handle
+        if not self._next_is_gpu_stage() and not _h.thread_in_scope():
+            uuid = requirements.data.uuid
+            if self.keepResident:
+                GpuResidency.Flush(uuid, self._slices(requirements))
+            else:
+                GpuResidency.Close(uuid)
+        super().OnStageScheduled(requirements, dependency)
 
 
-class NoiseStage(PipelineStage):
+class NoiseStage(GpuStage):
     def __init__(self, noiseType=FractalNoise.Sin, hurst=0.0, startingAmplitude=1.0, octaves=1, stepdown=2.0,
                  detuneRate=0.0, noiseSize=1000):
         super().__init__()
@@ -226,12 +295,11 @@ class NoiseStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.fractal(d.data, d.resolution, self.noiseType, self.hurst, self.startingAmplitude, self.stepdown,
-                   self.detuneRate, self.octaves, d.xpos, d.zpos, self.noiseSize)
+        self._native(requirements, lambda: _h.fractal(d.data, d.resolution, self.noiseType, self.hurst, self.startingAmplitude,
+                                                      self.stepdown, self.detuneRate, self.octaves, d.xpos, d.zpos, self.noiseSize))
 
 
-class KernelFilterStage(PipelineStage):
+class KernelFilterStage(GpuStage):
     def __init__(self, filter=KernelFilterType.Gauss9_S1, iterations=1):
         super().__init__()
         self.filter, self.iterations = filter, iterations
@@ -239,12 +307,11 @@ class KernelFilterStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
         # the reference schedules `iterations` dependent jobs; the GPU stage issues ONE fused call
-        _h.kernel_filter(d.data, None, self.filter, d.resolution, self.iterations)
+        self._native(requirements, lambda: _h.kernel_filter(d.data, None, self.filter, d.resolution, self.iterations))
 
 
-class StageGaussianBlur(PipelineStage):
+class StageGaussianBlur(GpuStage):
     def __init__(self, iterations=1, sigma=GaussSigma.s0d50, width=3):
         super().__init__()
         self.iterations, self.sigma, self.width = iterations, sigma, width
@@ -252,11 +319,10 @@ class StageGaussianBlur(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.gauss_filter(d.data, None, self.width, self.sigma, d.resolution, self.iterations)
+        self._native(requirements, lambda: _h.gauss_filter(d.data, None, self.width, self.sigma, d.resolution, self.iterations))
 
 
-class StageSmoothBlur(PipelineStage):
+class StageSmoothBlur(GpuStage):
     def __init__(self, iterations=1, width=1):
         super().__init__()
         self.iterations, self.width = iterations, width
@@ -264,11 +330,10 @@ class StageSmoothBlur(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.smooth_filter(d.data, None, self.width, d.resolution, self.iterations)
+        self._native(requirements, lambda: _h.smooth_filter(d.data, None, self.width, d.resolution, self.iterations))
 
 
-class ErosionFilterStage(PipelineStage):
+class ErosionFilterStage(GpuStage):
     def __init__(self, iterations=5):
         super().__init__()
         self.iterations = iterations
@@ -276,11 +341,10 @@ class ErosionFilterStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.min_erosion(d.data, d.resolution, self.iterations)
+        self._native(requirements, lambda: _h.min_erosion(d.data, d.resolution, self.iterations))
 
 
-class StageThermalErosion(PipelineStage):
+class StageThermalErosion(GpuStage):
     def __init__(self, iterations=1, talus=45, increment=0.5, meshHeightWidthRatio=0.75):
         super().__init__()
         self.iterations, self.talus, self.increment, self.meshHeightWidthRatio = iterations, talus, increment, meshHeightWidthRatio
@@ -288,11 +352,10 @@ class StageThermalErosion(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.thermal_erosion(d.data, float(self.talus), self.increment, self.meshHeightWidthRatio, self.iterations, d.resolution)
+        self._native(requirements, lambda: _h.thermal_erosion(d.data, float(self.talus), self.increment, self.meshHeightWidthRatio, self.iterations, d.resolution))
 
 
-class ErosionStageSubtractiveFlow(PipelineStage):
+class ErosionStageSubtractiveFlow(GpuStage):
     """Fields and defaults of ErosionStageSubtractiveFlow.cs:19-27.  `flowIterations` is kept as a field because the
     reference serialises it, but nothing reads it there either: cycle n runs n + 1 flow iterations (:226-228)."""
 
@@ -304,11 +367,10 @@ class ErosionStageSubtractiveFlow(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.subtractive_flow_erosion(d.data, d.resolution, self.erosiveIterations, self.erosiveFactor, self.normMin, self.normMax)
+        self._native(requirements, lambda: _h.subtractive_flow_erosion(d.data, d.resolution, self.erosiveIterations, self.erosiveFactor, self.normMin, self.normMax))
 
 
-class ConstantStage(PipelineStage):
+class ConstantStage(GpuStage):
     def __init__(self, operation=ConstantOperationType.MULTIPLY, value=0.5):
         super().__init__()
         self.operation, self.value = operation, value
@@ -316,11 +378,10 @@ class ConstantStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.constant(d.data, None, self.operation, self.value, d.resolution)
+        self._native(requirements, lambda: _h.constant(d.data, None, self.operation, self.value, d.resolution))
 
 
-class ReduceStage(PipelineStage):
+class ReduceStage(GpuStage):
     def __init__(self, operation=ReductionType.SUBTRACT):
         super().__init__()
         self.operation = operation
@@ -328,15 +389,17 @@ class ReduceStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(ReduceData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.reduce(d.data, d.rightData, None, self.operation, d.resolution)
+        self._native(requirements, lambda: _h.reduce(d.data, d.rightData, None, self.operation, d.resolution))
+
+    def _slices(self, requirements):
+        return [requirements.data.data]
 
     def TransformData(self, inputData):    # ReduceStage.cs:52-61: downstream stages see a GeneratorData
         d = inputData.data
         inputData.data = GeneratorData(d.uuid, d.data, d.resolution, d.xpos, d.zpos)
 
 
-class CurveStage(PipelineStage):
+class CurveStage(GpuStage):
     """`unityCurve` is any callable t -> value on [0,1] (AnimationCurve.Evaluate); it is discretised exactly as
     CurveStage.ExtractCurve does: curve[i] = Evaluate((float) i / samples), Filter/Curve/CurveStage.cs:27-35."""
 
@@ -355,11 +418,10 @@ class CurveStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.curve(d.data, None, self.curve, d.resolution)
+        self._native(requirements, lambda: _h.curve(d.data, None, self.curve, d.resolution))
 
 
-class CropStage(PipelineStage):
+class CropStage(GpuStage):
     """The reference never assigns CropJob.Offset, so its "CenterCropResolution" stage copies the top-left corner
     (Filter/Sample/CropJob.cs:25,36-43).  offset=None reproduces that; offset='center' is the evident intent."""
 
@@ -372,11 +434,10 @@ class CropStage(PipelineStage):
         if not isinstance(d, DownsampleData):
             raise Exception(f"Unhandled stageio {type(d).__name__}")
         off = 0 if self.offset is None else ((d.inputResolution - d.resolution) // 2 if self.offset == "center" else int(self.offset))
-        self.jobHandle = _chain(dependency)
-        _h.crop(d.inputData, d.inputResolution, d.data, d.resolution, off)
+        self._native(requirements, lambda: _h.crop(d.inputData, d.inputResolution, d.data, d.resolution, off))
 
 
-class FlowMapStage(PipelineStage):
+class FlowMapStage(GpuStage):
     def __init__(self, iterations=5, normMin=-0.1, normMax=0.1):
         super().__init__()
         self.iterations, self.normMin, self.normMax = iterations, normMin, normMax
@@ -384,11 +445,10 @@ class FlowMapStage(PipelineStage):
     def Schedule(self, requirements, dependency):
         self.CheckRequirements(GeneratorData, requirements)
         d = requirements.data
-        self.jobHandle = _chain(dependency)
-        _h.flowmap(d.data, d.resolution, self.iterations, self.normMin, self.normMax)
+        self._native(requirements, lambda: _h.flowmap(d.data, d.resolution, self.iterations, self.normMin, self.normMax))
 
 
-class MeshTileStage(PipelineStage):
+class MeshTileStage(GpuStage):
     def __init__(self, meshType=MeshType.SquareGridHeightMap):
         super().__init__()
         self.meshType = meshType
@@ -410,9 +470,8 @@ class MeshTileStage(PipelineStage):
             self.currentMesh.indices = np.empty(6 * R * R, np.uint32)
         self.currentMesh.bounds = ((0.5 * d.tileSize, 0.5 * d.tileHeight, 0.5 * d.tileSize),
                                    (d.tileSize, d.tileHeight, d.tileSize))
-        self.jobHandle = _chain(dependency)
-        _h.heightmap_mesh(self.meshType, self.currentMesh.vertices, self.currentMesh.indices, R, d.inputResolution,
-                          d.marginPix, d.tileHeight, d.tileSize, d.data)
+        self._native(requirements, lambda: _h.heightmap_mesh(self.meshType, self.currentMesh.vertices, self.currentMesh.indices, R,
+                                                             d.inputResolution, d.marginPix, d.tileHeight, d.tileSize, d.data))
 
 
 # ---- pipeline executor (the scheduling chain of BasePipeline) ------------------------------------------

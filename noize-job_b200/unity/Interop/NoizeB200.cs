@@ -10,6 +10,7 @@
 // Each GPU stage therefore schedules one IJob whose Execute() makes the blocking native call on a worker
 // thread, exactly where the Burst job body used to run.
 using System;
+using System.Collections.Generic;
 using System.Runtime.InteropServices;
 using Unity.Collections;
 using Unity.Collections.LowLevel.Unsafe;
@@ -19,6 +20,7 @@ using UnityEngine.Rendering;
 
 using xshazwar.noize.pipeline;
 using xshazwar.noize.filter;
+using xshazwar.noize.filter.blur;
 using xshazwar.noize.generate;
 using xshazwar.noize.mesh;
 
@@ -41,6 +43,9 @@ namespace xshazwar.noize.interop.b200 {
         const string LIB = "noize_b200";   // libnoize_b200.so in Assets/Plugins/x86_64
 
         [DllImport(LIB)] public static extern int nz_init(int* devices, int n);
+        // multi-GPU: large grids (>= 4096 rows) handed to the stage calls below are split into row bands over the first
+        // nBands devices of nz_init, inside the library; the stages do not change (include/noize_b200.h, "multi-GPU")
+        [DllImport(LIB)] public static extern int nz_set_bands(int nBands);
         [DllImport(LIB)] public static extern int nz_shutdown();
         [DllImport(LIB)] public static extern IntPtr nz_last_error();
         [DllImport(LIB)] public static extern IntPtr nz_version();
@@ -112,7 +117,7 @@ namespace xshazwar.noize.interop.b200 {
         public void Execute() {
             NzSlice s = NzSlice.From(data);
             int rc = 0;
-            if (scope != 0) Native.nz_scope_enter(scope);
+            if (scope != 0 && (rc = Native.nz_scope_enter(scope)) < 0) { status.Value = rc; return; }
             switch (op) {
                 case Op.Fractal:      rc = Native.nz_fractal(s, resolution, i0, f0, f1, f2, f3, i1, xpos, zpos, i2); break;
                 case Op.KernelFilter: rc = Native.nz_kernel_filter(s, NzSlice.Null, i0, resolution, i1); break;
@@ -134,17 +139,97 @@ namespace xshazwar.noize.interop.b200 {
     }
 
     /// Closes a residency scope when the chain's last job has run: flushes the device mirrors to the host slices.
-    /// Schedule it with the last stage's JobHandle as dependency and hand ITS handle to the pipeline.
+    /// Scheduled by the last GPU stage with its own job as dependency; ITS handle is what the stage hands on.
     public struct CloseScopeJob : IJob {
         public long scope;
         [NativeDisableContainerSafetyRestriction] public NativeReference<int> status;
-        public void Execute() { status.Value = Native.nz_scope_close(scope); }
+        public void Execute() {
+            int rc = Native.nz_scope_close(scope);
+            if (status.Value >= 0) status.Value = rc;      // keep the first failure of the chain
+        }
     }
 
+    /// keepResident: brings one slice home (the handle's contract: host memory holds the result) but leaves the scope,
+    /// and so the tile, in HBM for the next pipeline that works on the same uuid.
+    public unsafe struct FlushScopeJob : IJob {
+        public long scope;
+        [NativeDisableContainerSafetyRestriction] public NativeSlice<float> data;
+        [NativeDisableContainerSafetyRestriction] public NativeReference<int> status;
+        public void Execute() {
+            int rc = Native.nz_scope_enter(scope);
+            if (rc >= 0) {
+                rc = Native.nz_flush_to_host(data.GetUnsafePtr());
+                Native.nz_scope_leave();
+            }
+            if (status.Value >= 0) status.Value = rc;
+        }
+    }
+
+    /// uuid -> residency scope shared by the GPU stages that work on ONE work item (StageIO.uuid).  Main thread only:
+    /// Schedule() and OnStageScheduled() always run there (Pipeline/Stage/PipelineStage.cs:44-57).
+    public static class GpuResidency {
+        static readonly Dictionary<string, long> scopes = new Dictionary<string, long>();
+
+        public static long Enter(string uuid) {
+            if (!scopes.TryGetValue(uuid, out long scope)) {
+                scope = Native.nz_scope_create();
+                if (scope < 0) Native.Check((int) scope, "nz_scope_create");
+                scopes[uuid] = scope;
+            }
+            return scope;
+        }
+        /// the scope leaves the table now; it is closed by the job this returns (0: nothing open for uuid)
+        public static long Detach(string uuid) {
+            if (!scopes.TryGetValue(uuid, out long scope)) return 0;
+            scopes.Remove(uuid);
+            return scope;
+        }
+        public static long Peek(string uuid) => scopes.TryGetValue(uuid, out long scope) ? scope : 0;
+        /// e.g. from a MonoBehaviour's OnDestroy: nothing may stay resident when the pipeline objects go away
+        public static void CloseAll() {
+            foreach (long scope in scopes.Values) Native.nz_scope_close(scope);
+            scopes.Clear();
+        }
+    }
+
+    /// Base of every stage that runs on the GPU.  Stage objects, not the pipeline, own residency:
+    ///  * Schedule(): the first GPU stage of a work item creates the scope (GpuResidency.Enter), every stage passes it to
+    ///    its NativeCallJob, which brackets the native call with nz_scope_enter / nz_scope_leave on its worker thread;
+    ///  * OnStageScheduled(): when the next receiver is NOT a GPU stage — a Burst stage, or BasePipeline's
+    ///    OnPipelineFullyScheduled (Pipeline/Executable/Pipeline.cs:122-151) — the scope's close (or, with keepResident,
+    ///    a flush of this stage's slice) is chained behind this stage's job and ITS handle is handed on, so the handle
+    ///    still completes only when d.data (host memory) holds the result.
+    /// Chained GPU stages therefore pay one H2D (none after a generator) and one D2H per work item, not per stage.
     public abstract class GpuStage : PipelineStage {
+        [Tooltip("Last GPU stage of a pipeline: bring the result home but keep the tile in HBM for the next pipeline on the same uuid (e.g. generator pipeline -> mesh pipeline)")]
+        public bool keepResident = false;
         protected NativeReference<int> status;
         protected void EnsureStatus() {
             if (!status.IsCreated) status = new NativeReference<int>(Allocator.Persistent);
+            status.Value = 0;
+        }
+        protected long EnterScope(StageIO d) {
+            EnsureStatus();
+            return GpuResidency.Enter(d.uuid);
+        }
+        bool NextIsGpuStage() {
+            if (OnStageScheduledAction == null) return false;
+            foreach (Delegate next in OnStageScheduledAction.GetInvocationList())
+                if (next.Target is GpuStage) return true;
+            return false;
+        }
+        public override void OnStageScheduled(PipelineWorkItem requirements, JobHandle dependency) {
+            if (!NextIsGpuStage()) {
+                string uuid = requirements.data.uuid;
+                if (keepResident) {
+                    long scope = GpuResidency.Peek(uuid);
+                    if (scope != 0) jobHandle = new FlushScopeJob { scope = scope, data = requirements.data.data, status = status }.Schedule(jobHandle);
+                } else {
+                    long scope = GpuResidency.Detach(uuid);
+                    if (scope != 0) jobHandle = new CloseScopeJob { scope = scope, status = status }.Schedule(jobHandle);
+                }
+            }
+            OnStageScheduledAction?.Invoke(requirements, jobHandle);
         }
         public override void OnStageComplete() {
             if (status.IsCreated && status.Value < 0) Native.Check(status.Value, GetType().Name);
@@ -165,8 +250,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.Fractal, data = d.data, resolution = d.resolution, i0 = (int) noiseType, f0 = hurst,
                 f1 = startingAmplitude, f2 = stepdown, f3 = detuneRate, i1 = octaves, xpos = d.xpos, zpos = d.zpos,
                 i2 = noiseSize, status = status
@@ -181,10 +267,44 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             // the reference chains `iterations` jobs; the GPU stage issues ONE fused call
             jobHandle = new NativeCallJob {
-                op = NativeCallJob.Op.KernelFilter, data = d.data, resolution = d.resolution, i0 = (int) filter,
+                scope = scope, op = NativeCallJob.Op.KernelFilter, data = d.data, resolution = d.resolution, i0 = (int) filter,
+                i1 = iterations, status = status
+            }.Schedule(dependency);
+        }
+    }
+
+    // StageGaussianBlur, Filter/Kernel/Blur/StageGaussianBlur.cs:12-56 (same serialized fields; limitWidth is applied natively,
+    // BlurKernels.cs:30-36).  The reference chains `iterations` GaussFilter jobs (:33-46); this is one fused call.
+    [CreateAssetMenu(fileName = "GpuStageGaussianBlur", menuName = "Noize/B200/Blur/GaussianBlurFilter", order = 2)]
+    public class GpuStageGaussianBlur : GpuStage {
+        [Range(1, 32)] public int iterations = 1;
+        public GaussSigma sigma;
+        [Range(3, 25)] public int width = 3;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            long scope = EnterScope(d);
+            jobHandle = new NativeCallJob {
+                scope = scope, op = NativeCallJob.Op.GaussFilter, data = d.data, resolution = d.resolution, i0 = width,
+                i2 = (int) sigma, i1 = iterations, status = status
+            }.Schedule(dependency);
+        }
+    }
+
+    // StageSmoothBlur, Filter/Kernel/Blur/StageSmoothBlur.cs:12-54 (box blur of odd width, 1/width taps)
+    [CreateAssetMenu(fileName = "GpuStageSmoothBlur", menuName = "Noize/B200/Blur/SmoothBlurFilter", order = 2)]
+    public class GpuStageSmoothBlur : GpuStage {
+        [Range(1, 32)] public int iterations = 1;
+        [Range(3, 25)] public int width = 1;
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            long scope = EnterScope(d);
+            jobHandle = new NativeCallJob {
+                scope = scope, op = NativeCallJob.Op.SmoothFilter, data = d.data, resolution = d.resolution, i0 = width,
                 i1 = iterations, status = status
             }.Schedule(dependency);
         }
@@ -196,8 +316,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.MinErosion, data = d.data, resolution = d.resolution, i1 = iterations, status = status
             }.Schedule(dependency);
         }
@@ -213,8 +334,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.ThermalErosion, data = d.data, resolution = d.resolution, i1 = iterations,
                 f0 = (float) talus, f1 = increment, f2 = meshHeightWidthRatio, status = status
             }.Schedule(dependency);
@@ -232,8 +354,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.SubtractiveFlow, data = d.data, resolution = d.resolution, i1 = erosiveIterations,
                 f0 = normMin, f1 = normMax, f2 = erosiveFactor, status = status
             }.Schedule(dependency);
@@ -248,8 +371,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.Constant, data = d.data, resolution = d.resolution, i0 = (int) operation, f0 = value, status = status
             }.Schedule(dependency);
         }
@@ -262,8 +386,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<ReduceData>(requirements);
             ReduceData d = (ReduceData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.Reduce, data = d.data, data2 = d.rightData, resolution = d.resolution, i0 = (int) operation, status = status
             }.Schedule(dependency);
         }
@@ -287,8 +412,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.Curve, data = d.data, data2 = new NativeSlice<float>(curve), resolution = d.resolution, status = status
             }.Schedule(dependency);
         }
@@ -301,8 +427,9 @@ namespace xshazwar.noize.interop.b200 {
         public bool center = false;
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             DownsampleData d = (DownsampleData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.Crop, data = d.data, data2 = d.inputData, resolution = d.resolution,
                 inputResolution = d.inputResolution, i0 = center ? (d.inputResolution - d.resolution) / 2 : 0, status = status
             }.Schedule(dependency);
@@ -317,8 +444,9 @@ namespace xshazwar.noize.interop.b200 {
         public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
             CheckRequirements<GeneratorData>(requirements);
             GeneratorData d = (GeneratorData) requirements.data;
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.FlowMap, data = d.data, resolution = d.resolution, i1 = iterations, f0 = normMin,
                 f1 = normMax, status = status
             }.Schedule(dependency);
@@ -352,8 +480,9 @@ namespace xshazwar.noize.interop.b200 {
             md.subMeshCount = 1;
             md.SetSubMesh(0, new SubMeshDescriptor(0, icount) { bounds = bounds, vertexCount = vcount },
                           MeshUpdateFlags.DontRecalculateBounds | MeshUpdateFlags.DontValidateIndices);
-            EnsureStatus();
+            long scope = EnterScope(d);
             jobHandle = new NativeCallJob {
+                scope = scope,
                 op = NativeCallJob.Op.Mesh, data = d.data, vertices = md.GetVertexData<byte>().GetUnsafePtr(),
                 indices = (uint*) md.GetIndexData<uint>().GetUnsafePtr(), resolution = R, inputResolution = d.inputResolution,
                 marginPix = d.marginPix, i0 = (int) meshType, f0 = d.tileHeight, f1 = d.tileSize, status = status
