@@ -282,6 +282,25 @@ NZ_API int32_t nz_flush_to_host(const float* host_ptr);
 NZ_API int32_t nz_pin(void* host_ptr, size_t bytes);
 NZ_API int32_t nz_unpin(void* host_ptr);
 
+/* ---- named device-resident buffers (the GPU side of PipelineStateManager) ------------------------------------------ */
+/* The reference parks tiles between pipelines in named host buffers of its PipelineStateManager
+ * (Pipeline/PipelineState/PipelineStateManager.cs:39-127; name = "{xpos}_{zpos}__{resolution}__{contextAlias}",
+ * PipelineState/Stage/WriteGeneratorContextStage.cs:21-23) and copies them with FlushWriteSlice jobs
+ * (WriteGeneratorContextStage.cs:36-52, ReadGeneratorContextStage.cs:39-51).  Here the named buffer lives in HBM and
+ * outlives residency scopes, so a tile written by one pipeline is read by the next without touching the host:
+ *   nz_context_write: named := src   (device-to-device when src is resident in the caller's scope, one H2D otherwise)
+ *   nz_context_read : dst := named   (device-to-device into dst's mirror; the host slice follows at the scope's close)
+ * Names are process-wide.  Buffers hold `length` floats on the host layer's device. */
+NZ_API int32_t nz_context_write(const char* name, nz_slice_f32 src);
+NZ_API int32_t nz_context_read(const char* name, nz_slice_f32 dst);
+/* *length = element count, or -1 when no buffer of that name exists (PipelineStateManager.BufferExists) */
+NZ_API int32_t nz_context_exists(const char* name, int32_t* length);
+/* host copies for PipelineStateManager.SaveBufferToDisk / the saved-state load in GetBuffer (:64-72, :104-120) */
+NZ_API int32_t nz_context_download(const char* name, float* h_dst, int32_t length);
+NZ_API int32_t nz_context_upload(const char* name, const float* h_src, int32_t length);
+/* PipelineStateManager.ReleaseBuffer (:129-134); returns NZ_OK also when the name is unknown */
+NZ_API int32_t nz_context_release(const char* name);
+
 /* ---- multi-GPU: row bands of one large heightmap -------------------------------------- */
 /* The reference generates one tile at a time on the CPU (Scripts/MeshTileGenerator.cs:125-138,184-192); a heightmap too
  * large or too slow for one GPU is split into ROW BANDS: band b of g owns rows [b*n/g, (b+1)*n/g).  Noise needs no

@@ -15,4 +15,5 @@ from .stages import (FractalNoise, KernelFilterType, GaussSigma, MeshType, JobHa
                      MeshStageData, Mesh, PipelineWorkItem, PipelineStage, NoiseStage, KernelFilterStage,
                      StageGaussianBlur, StageSmoothBlur, ErosionFilterStage, FlowMapStage, MeshTileStage, BasePipeline,
                      ConstantOperationType, ReductionType, ReduceData, DownsampleData, StageThermalErosion, ErosionStageSubtractiveFlow,
-                     ConstantStage, ReduceStage, CurveStage, CropStage, GpuStage, GpuResidency)
+                     ConstantStage, ReduceStage, CurveStage, CropStage, GpuStage, GpuResidency,
+                     PipelineStateManager, WriteGeneratorContextStage, ReadGeneratorContextStage)

@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -1393,6 +1394,160 @@ NZ_API int32_t nz_crop(nz_slice_f32 input, int32_t input_resolution, nz_slice_f3
     if (rc == NZ_OK) out->dirty = true;
     int32_t rc2 = finish(out);
     return rc != NZ_OK ? rc : rc2;
+}
+
+// ---- named device-resident buffers (PipelineStateManager on the GPU) ------------------------------------------------
+}  // extern "C"
+
+namespace {
+struct NamedBuffer {
+    float* d = nullptr;
+    size_t n = 0;
+    int device = 0;
+    cudaEvent_t last = nullptr;     // recorded after every access: the next access, on whatever stream, waits for it
+};
+std::mutex g_named_mu;
+std::unordered_map<std::string, NamedBuffer> g_named;
+
+// called with g_named_mu held; (re)allocates the buffer for n floats on the current (primary) device
+int32_t named_prepare(NamedBuffer& b, size_t n) {
+    if (b.d && b.n != n) {
+        if (b.last) cudaEventSynchronize(b.last);
+        pool_free(b.d);
+        b.d = nullptr;
+    }
+    if (!b.d) {
+        int32_t rc = pool_alloc((void**)&b.d, n * sizeof(float));
+        if (rc != NZ_OK) return rc;
+        b.n = n;
+        b.device = t_state.device;
+    }
+    if (!b.last) NZ_CUDA(cudaEventCreateWithFlags(&b.last, cudaEventDisableTiming));
+    else NZ_CUDA(cudaStreamWaitEvent(t_state.stream, b.last, 0));
+    return NZ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+NZ_API int32_t nz_context_write(const char* name, nz_slice_f32 src) {
+    NZ_REQUIRE(name && name[0], "nz_context_write: empty buffer name");
+    NZ_REQUIRE(src.ptr && src.length > 0 && src.stride_bytes >= 4, "nz_context_write: empty slice");
+    UnscopedCleanup cleanup;
+    int32_t rc = begin_stage();
+    if (rc != NZ_OK) return rc;
+    Mirror* m = nullptr;
+    if ((rc = acquire(src, /*need_contents=*/true, &m)) != NZ_OK) return rc;     // resident: no copy; else one H2D
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_named_mu);
+        NamedBuffer& b = g_named[name];
+        rc = named_prepare(b, m->n);
+        if (rc == NZ_OK) {
+            cudaError_t e = cudaMemcpyAsync(b.d, m->d, m->n * sizeof(float), cudaMemcpyDeviceToDevice, t_state.stream);
+            if (e == cudaSuccess) e = cudaEventRecord(b.last, t_state.stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "nz_context_write");
+        } else if (!b.d) {
+            g_named.erase(name);
+        }
+    }
+    int32_t rc2 = finish(m);
+    return rc != NZ_OK ? rc : rc2;
+}
+
+NZ_API int32_t nz_context_read(const char* name, nz_slice_f32 dst) {
+    NZ_REQUIRE(name && name[0], "nz_context_read: empty buffer name");
+    NZ_REQUIRE(dst.ptr && dst.length > 0 && dst.stride_bytes >= 4, "nz_context_read: empty slice");
+    UnscopedCleanup cleanup;
+    int32_t rc = begin_stage();
+    if (rc != NZ_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_named_mu);
+        auto it = g_named.find(name);
+        if (it == g_named.end()) {
+            set_error("nz_context_read: no buffer named '%s'", name);
+            return NZ_E_STATE;
+        }
+        NZ_REQUIRE(it->second.n == (size_t)dst.length, "nz_context_read: buffer '%s' holds %zu floats, the slice %d", name,
+                   it->second.n, dst.length);
+    }
+    Mirror* m = nullptr;
+    if ((rc = acquire(dst, /*need_contents=*/false, &m)) != NZ_OK) return rc;
+    if ((rc = mark_uploaded()) != NZ_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_named_mu);
+        auto it = g_named.find(name);
+        if (it == g_named.end() || it->second.n != m->n) {
+            set_error("nz_context_read: buffer '%s' changed during the call", name);
+            rc = NZ_E_STATE;
+        } else {
+            NamedBuffer& b = it->second;
+            cudaError_t e = cudaStreamWaitEvent(t_state.stream, b.last, 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(m->d, b.d, m->n * sizeof(float), cudaMemcpyDeviceToDevice, t_state.stream);
+            if (e == cudaSuccess) e = cudaEventRecord(b.last, t_state.stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "nz_context_read");
+            else m->dirty = true;
+        }
+    }
+    int32_t rc2 = finish(m);
+    return rc != NZ_OK ? rc : rc2;
+}
+
+NZ_API int32_t nz_context_exists(const char* name, int32_t* length) {
+    NZ_REQUIRE(name && length, "nz_context_exists: null argument");
+    std::lock_guard<std::mutex> lk(g_named_mu);
+    auto it = g_named.find(name);
+    *length = it == g_named.end() ? -1 : (int32_t)it->second.n;
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_context_download(const char* name, float* h_dst, int32_t length) {
+    NZ_REQUIRE(name && h_dst && length > 0, "nz_context_download: bad arguments");
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_named_mu);
+    auto it = g_named.find(name);
+    if (it == g_named.end()) {
+        set_error("nz_context_download: no buffer named '%s'", name);
+        return NZ_E_STATE;
+    }
+    NZ_REQUIRE(it->second.n == (size_t)length, "nz_context_download: buffer '%s' holds %zu floats, not %d", name, it->second.n, length);
+    NZ_CUDA(cudaStreamWaitEvent(t_state.stream, it->second.last, 0));
+    NZ_CUDA(cudaMemcpyAsync(h_dst, it->second.d, (size_t)length * sizeof(float), cudaMemcpyDeviceToHost, t_state.stream));
+    NZ_CUDA(cudaEventRecord(it->second.last, t_state.stream));
+    NZ_CUDA(cudaStreamSynchronize(t_state.stream));
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_context_upload(const char* name, const float* h_src, int32_t length) {
+    NZ_REQUIRE(name && name[0] && h_src && length > 0, "nz_context_upload: bad arguments");
+    int32_t rc = thread_ready();
+    if (rc != NZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_named_mu);
+    NamedBuffer& b = g_named[name];
+    rc = named_prepare(b, (size_t)length);
+    if (rc != NZ_OK) {
+        if (!b.d) g_named.erase(name);
+        return rc;
+    }
+    NZ_CUDA(cudaMemcpyAsync(b.d, h_src, (size_t)length * sizeof(float), cudaMemcpyHostToDevice, t_state.stream));
+    NZ_CUDA(cudaEventRecord(b.last, t_state.stream));
+    NZ_CUDA(cudaStreamSynchronize(t_state.stream));      // h_src may be pageable and is the caller's to reuse
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_context_release(const char* name) {
+    NZ_REQUIRE(name, "nz_context_release: null name");
+    std::lock_guard<std::mutex> lk(g_named_mu);
+    auto it = g_named.find(name);
+    if (it == g_named.end()) return NZ_OK;
+    if (it->second.last) {
+        cudaEventSynchronize(it->second.last);
+        cudaEventDestroy(it->second.last);
+    }
+    pool_free(it->second.d);
+    g_named.erase(it);
+    return NZ_OK;
 }
 
 NZ_API int32_t nz_map_range(nz_slice_f32 map, float* res3, float lim_min, float lim_max) {

@@ -260,3 +260,39 @@ def pin(arr):
 
 def unpin(arr):
     _l.check(_l.load().nz_unpin(arr.ctypes.data))
+
+
+# ---- named device-resident buffers (PipelineStateManager on the GPU) -------------------------------------
+def context_write(name, src):
+    """named buffer := src (device-to-device when src is resident in the caller's scope)."""
+    _l.check(_l.load().nz_context_write(name.encode(), _l.as_slice(src)))
+
+
+def context_read(name, dst):
+    """dst := named buffer (device-to-device into dst's mirror)."""
+    _l.check(_l.load().nz_context_read(name.encode(), _l.as_slice(dst)))
+
+
+def context_exists(name):
+    """Element count of the named buffer, or -1."""
+    n = C.c_int32(-1)
+    _l.check(_l.load().nz_context_exists(name.encode(), C.byref(n)))
+    return int(n.value)
+
+
+def context_download(name):
+    n = context_exists(name)
+    if n < 0:
+        raise KeyError(name)
+    out = np.empty(n, np.float32)
+    _l.check(_l.load().nz_context_download(name.encode(), out.ctypes.data, n))
+    return out
+
+
+def context_upload(name, data):
+    a = np.ascontiguousarray(data, np.float32).reshape(-1)
+    _l.check(_l.load().nz_context_upload(name.encode(), a.ctypes.data, a.size))
+
+
+def context_release(name):
+    _l.check(_l.load().nz_context_release(name.encode()))

@@ -66,6 +66,12 @@ SIGNATURES = {
     "nz_last_timing": (_i32, [C.POINTER(Timing)]),
     "nz_test_fail_allocs": (_i32, [_i32, _i32]),
     "nz_set_bands": (_i32, [_i32]),
+    "nz_context_write": (_i32, [C.c_char_p, Slice]),
+    "nz_context_read": (_i32, [C.c_char_p, Slice]),
+    "nz_context_exists": (_i32, [C.c_char_p, _pi32]),
+    "nz_context_download": (_i32, [C.c_char_p, _vp, _i32]),
+    "nz_context_upload": (_i32, [C.c_char_p, _vp, _i32]),
+    "nz_context_release": (_i32, [C.c_char_p]),
     "nz_comm_unique_id": (_i32, [_vp, _i32]),
     "nz_comm_create": (C.c_int64, [_vp, _i32, _i32, _i32]),
     "nz_comm_async_error": (_i32, [C.c_int64]),

@@ -480,10 +480,12 @@ class BasePipeline:
     stage i+1's ReceiveHandledInput with the JobHandle as dependency (:130-151); Update() schedules the
     next queued item (:154-158,216-230), LateUpdate() completes it and fires completeAction (:160-181)."""
 
-    def __init__(self, stages, alias="pipeline"):
+    def __init__(self, stages, alias="pipeline", contextManager=None):
         if not stages:
             raise Exception("No stages in pipeline")
         self.alias = alias
+        self.contextManager = contextManager      # PipelineStateManager handed to every work item (Pipeline.cs:95-103)
+        self.dependencyHell = []
         self.stage_instances = list(stages)
         self.queue = deque()
         self.pipelineRunning = False
@@ -497,7 +499,24 @@ class BasePipeline:
                 st.OnStageScheduledAction = self.OnPipelineFullyScheduled
 
     def Enqueue(self, input, scheduleAction=None, completeAction=None, dependency=None):
-        self.queue.append(PipelineWorkItem(input, completeAction, scheduleAction, dependency))
+        self.queue.append(PipelineWorkItem(input, completeAction, scheduleAction, dependency, self.contextManager))
+
+    def WorkIsSchedulable(self, item):         # Pipeline.cs:256-265
+        return all([st.IsSchedulable(item) for st in self.stage_instances])
+
+    def GetNextJob(self):
+        """Pipeline.cs:183-215: items whose stages are not schedulable yet (a context buffer that does not exist, a locked
+        one) wait in `dependencyHell` and are retried before the queue on every Update."""
+        for i, item in enumerate(list(self.dependencyHell)):
+            if self.WorkIsSchedulable(item):
+                self.dependencyHell.remove(item)
+                return item
+        while self.queue:
+            item = self.queue.popleft()
+            if self.WorkIsSchedulable(item):
+                return item
+            self.dependencyHell.append(item)
+        return None
 
     def Schedule(self, workItem):
         if self.pipelineRunning:
@@ -514,8 +533,10 @@ class BasePipeline:
             requirements.scheduledAction(requirements.data, dependency)
 
     def Update(self):
-        if not self.pipelineRunning and not self.pipelineQueued and self.queue:
-            self.Schedule(self.queue.popleft())
+        if not self.pipelineRunning and not self.pipelineQueued:
+            job = self.GetNextJob()
+            if job is not None:
+                self.Schedule(job)
 
     def LateUpdate(self):
         if self.pipelineRunning:
@@ -537,3 +558,100 @@ class BasePipeline:
     def Destroy(self):
         for st in self.stage_instances:
             st.Destroy()
+
+
+# ---- PipelineState: named buffers that outlive a pipeline run, on the GPU -------------------------------------------------
+class PipelineStateManager:
+    """Mirror of the float-buffer part of PipelineStateManager (Pipeline/PipelineState/PipelineStateManager.cs:39-160) with the
+    buffers living in HBM (nz_context_*): GetBuffer / BufferExists / ReleaseBuffer / IsLocked / TrySetLock /
+    SaveBufferToDisk, and the saved-state load of GetBuffer (:64-72) through the reference's own on-disk format (serde.py).
+    A buffer is referred to by its NAME; there is no host array behind it until someone downloads it."""
+
+    def __init__(self):
+        self.savedState = None
+        self._locks = {}
+
+    def SetSavePath(self, path, saveName, saveVersion):
+        from . import serde
+        self.savedState = serde.PipelineSerdeManager(path, saveName, saveVersion)
+
+    def GetBuffer(self, name, size=-1, ignoreSaved=False):
+        """Returns the buffer's name once it exists on the device; a saved copy on disk is uploaded the first time."""
+        if _h.context_exists(name) < 0 and self.savedState is not None and not ignoreSaved:
+            n = self.savedState.CachedSize(name)
+            if n > 0:
+                _h.context_upload(name, self.savedState.ReadData(name, np.float32, n))
+        return name
+
+    def BufferExists(self, name):
+        return _h.context_exists(name) >= 0
+
+    def ReleaseBuffer(self, name):
+        existed = self.BufferExists(name)
+        _h.context_release(name)
+        self._locks.pop(name, None)
+        return existed
+
+    def IsLocked(self, key):
+        h = self._locks.get(key)
+        return h is not None and not h.IsCompleted
+
+    def TrySetLock(self, key, handle, spyHandle=None):
+        if self.IsLocked(key):
+            return False
+        self._locks[key] = handle
+        return True
+
+    def SaveBufferToDisk(self, name, size=-1):
+        if self.savedState is None:
+            raise ValueError("No serde manager is active")
+        self.savedState.WriteData(_h.context_download(name), name)
+
+
+def _context_buffer_name(d, alias):
+    return f"{d.xpos}_{d.zpos}__{d.resolution}__{alias}"          # WriteGeneratorContextStage.getBufferName, :21-23
+
+
+class WriteGeneratorContextStage(GpuStage):
+    """PipelineState/Stage/WriteGeneratorContextStage.cs:13-55: parks the work item's tile in the state manager under
+    "{xpos}_{zpos}__{resolution}__{contextAlias}".  On the GPU that is one device-to-device copy out of the resident tile."""
+
+    def __init__(self, contextAlias=""):
+        super().__init__()
+        self.contextAlias = contextAlias
+
+    def IsSchedulable(self, job):
+        if job.stageManager is None:
+            return False
+        return not job.stageManager.IsLocked(_context_buffer_name(job.data, self.contextAlias))
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        gd = requirements.data
+        name = requirements.stageManager.GetBuffer(_context_buffer_name(gd, self.contextAlias), gd.resolution * gd.resolution,
+                                                   ignoreSaved=True)
+        self._native(requirements, lambda: _h.context_write(name, gd.data))
+        requirements.stageManager.TrySetLock(name, self.jobHandle, self.jobHandle)
+
+
+class ReadGeneratorContextStage(GpuStage):
+    """PipelineState/Stage/ReadGeneratorContextStage.cs:13-53: the work item's tile := the named buffer."""
+
+    def __init__(self, contextAlias=""):
+        super().__init__()
+        self.contextAlias = contextAlias
+
+    def IsSchedulable(self, job):
+        if job.stageManager is None:
+            return False
+        name = _context_buffer_name(job.data, self.contextAlias)
+        job.stageManager.GetBuffer(name)          # a saved copy on disk counts as existing
+        if not job.stageManager.BufferExists(name):
+            return False
+        return not job.stageManager.IsLocked(name)
+
+    def Schedule(self, requirements, dependency):
+        self.CheckRequirements(GeneratorData, requirements)
+        gd = requirements.data
+        name = requirements.stageManager.GetBuffer(_context_buffer_name(gd, self.contextAlias), gd.resolution * gd.resolution)
+        self._native(requirements, lambda: _h.context_read(name, gd.data))

@@ -84,6 +84,14 @@ namespace xshazwar.noize.interop.b200 {
         [DllImport(LIB)] public static extern int nz_map_range(NzSlice map, float* res3, float limMin, float limMax);
         [DllImport(LIB)] public static extern int nz_normalize(NzSlice src, NzSlice tmp, float* args3, int resolution);
 
+        // named device-resident buffers: the GPU side of PipelineStateManager (Pipeline/PipelineState/PipelineStateManager.cs:39-127)
+        [DllImport(LIB)] public static extern int nz_context_write([MarshalAs(UnmanagedType.LPStr)] string name, NzSlice src);
+        [DllImport(LIB)] public static extern int nz_context_read([MarshalAs(UnmanagedType.LPStr)] string name, NzSlice dst);
+        [DllImport(LIB)] public static extern int nz_context_exists([MarshalAs(UnmanagedType.LPStr)] string name, int* length);
+        [DllImport(LIB)] public static extern int nz_context_download([MarshalAs(UnmanagedType.LPStr)] string name, float* dst, int length);
+        [DllImport(LIB)] public static extern int nz_context_upload([MarshalAs(UnmanagedType.LPStr)] string name, float* src, int length);
+        [DllImport(LIB)] public static extern int nz_context_release([MarshalAs(UnmanagedType.LPStr)] string name);
+
         // process-wide residency scope: the stages of one chain run on different worker threads
         [DllImport(LIB)] public static extern long nz_scope_create();
         [DllImport(LIB)] public static extern int nz_scope_enter(long scope);
@@ -433,6 +441,60 @@ namespace xshazwar.noize.interop.b200 {
                 op = NativeCallJob.Op.Crop, data = d.data, data2 = d.inputData, resolution = d.resolution,
                 inputResolution = d.inputResolution, i0 = center ? (d.inputResolution - d.resolution) / 2 : 0, status = status
             }.Schedule(dependency);
+        }
+    }
+
+    /// Write/ReadGeneratorContextStage on the GPU: the tile is parked in (or fetched from) a NAMED buffer in HBM that outlives
+    /// residency scopes — one device-to-device copy where the reference runs a FlushWriteSlice memcpy job between two host
+    /// arrays (PipelineState/Stage/WriteGeneratorContextStage.cs:36-52, ReadGeneratorContextStage.cs:39-51).  The job is
+    /// managed (a string cannot cross into Burst); the name is pinned in a GCHandle for the job's lifetime.
+    public unsafe struct ContextCopyJob : IJob {
+        public bool write;
+        public GCHandle name;
+        [NativeDisableContainerSafetyRestriction] public NativeSlice<float> data;
+        [NativeDisableContainerSafetyRestriction] public NativeReference<int> status;
+        public long scope;
+        public void Execute() {
+            string n = (string) name.Target;
+            int rc = scope != 0 ? Native.nz_scope_enter(scope) : 0;
+            if (rc >= 0) {
+                rc = write ? Native.nz_context_write(n, NzSlice.From(data)) : Native.nz_context_read(n, NzSlice.From(data));
+                if (scope != 0) Native.nz_scope_leave();
+            }
+            name.Free();
+            status.Value = rc;
+        }
+    }
+
+    public abstract class GpuContextStage : GpuStage {
+        public string contextAlias;
+        protected string BufferName(GeneratorData d) => $"{d.xpos}_{d.zpos}__{d.resolution}__{contextAlias}";   // getBufferName, :21-23
+        protected static bool Exists(string name) { int n = -1; Native.nz_context_exists(name, &n); return n >= 0; }
+        protected void ScheduleCopy(PipelineWorkItem requirements, JobHandle dependency, bool write) {
+            CheckRequirements<GeneratorData>(requirements);
+            GeneratorData d = (GeneratorData) requirements.data;
+            long scope = EnterScope(d);
+            jobHandle = new ContextCopyJob {
+                write = write, name = GCHandle.Alloc(BufferName(d)), data = d.data, status = status, scope = scope
+            }.Schedule(dependency);
+        }
+    }
+
+    [CreateAssetMenu(fileName = "GpuWriteGeneratorContextStage", menuName = "Noize/B200/State/WriteContext", order = 2)]
+    public unsafe class GpuWriteGeneratorContextStage : GpuContextStage {
+        JobHandle pending;
+        public override bool IsSchedulable(PipelineWorkItem job) => pending.IsCompleted;          // the LockJob of the reference (:43-52)
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            ScheduleCopy(requirements, dependency, true);
+            pending = jobHandle;
+        }
+    }
+
+    [CreateAssetMenu(fileName = "GpuReadGeneratorContextStage", menuName = "Noize/B200/State/ReadContext", order = 2)]
+    public unsafe class GpuReadGeneratorContextStage : GpuContextStage {
+        public override bool IsSchedulable(PipelineWorkItem job) => Exists(BufferName((GeneratorData) job.data));   // :24-37
+        public override void Schedule(PipelineWorkItem requirements, JobHandle dependency) {
+            ScheduleCopy(requirements, dependency, false);
         }
     }
 

@@ -130,3 +130,48 @@ def test_blur_stages_match_oracle(nz, oracle):
     d = src.copy().reshape(-1)
     nz.BasePipeline([nz.StageSmoothBlur(iterations=2, width=5)]).Run(nz.GeneratorData("blur", d, N))
     assert np.abs(d.reshape(N, N) - oracle.smooth_filter(src, 5, 2)).max() <= 1e-6
+
+
+def test_context_stages_keep_tiles_on_the_device_between_pipelines(nz, tmp_path):
+    """Write/ReadGeneratorContextStage + PipelineStateManager (PipelineState/Stage/*.cs, PipelineStateManager.cs:39-160) with
+    the named buffers in HBM: a generator pipeline parks its tile, a second pipeline picks it up; the buffer round-trips
+    through the reference's on-disk format."""
+    mgr = nz.PipelineStateManager()
+    gen = nz.BasePipeline(_gen_stages(nz)[:2] + [nz.WriteGeneratorContextStage("terrain")], contextManager=mgr)
+    use = nz.BasePipeline([nz.ReadGeneratorContextStage("terrain"), nz.FlowMapStage(iterations=3, normMin=0.0, normMax=0.005)],
+                          contextManager=mgr)
+    name = f"0_424__{N}__terrain"
+    out = np.zeros(N * N, np.float32)
+    done = []
+    # the consumer is enqueued FIRST: its buffer does not exist yet, so the item waits (Pipeline.cs:200-214)
+    use.Enqueue(nz.GeneratorData("consumer", out, N, 0, 424), completeAction=lambda d: done.append(d.uuid))
+    use.Update()
+    assert not use.pipelineRunning and len(use.dependencyHell) == 1 and not mgr.BufferExists(name)
+    tile = np.zeros(N * N, np.float32)
+    gen.Run(nz.GeneratorData("producer", tile, N, 0, 424))
+    assert mgr.BufferExists(name) and nz.host.context_exists(name) == N * N
+    want = np.zeros(N * N, np.float32)
+    nz.host.fractal(want, N, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 424, 1700)
+    nz.host.kernel_filter(want, None, 2, N, 4)
+    assert np.array_equal(tile, want) and np.array_equal(nz.host.context_download(name), want)
+    use.Update()
+    use.LateUpdate()
+    assert done == ["consumer"] and not use.dependencyHell
+    nz.host.flowmap(want, N, 3, 0.0, 0.005)
+    assert np.array_equal(out, want)
+    # SaveBufferToDisk -> a fresh manager finds the saved copy and uploads it on first use (PipelineStateManager.cs:64-72)
+    mgr.SetSavePath(str(tmp_path), "world", "1")
+    mgr.SaveBufferToDisk(name)
+    assert mgr.ReleaseBuffer(name) and not mgr.BufferExists(name)
+    mgr2 = nz.PipelineStateManager()
+    mgr2.SetSavePath(str(tmp_path), "world", "1")
+    out2 = np.zeros(N * N, np.float32)
+    nz.BasePipeline([nz.ReadGeneratorContextStage("terrain")], contextManager=mgr2).Run(nz.GeneratorData("reload", out2, N, 0, 424))
+    tile_only = np.zeros(N * N, np.float32)
+    nz.host.fractal(tile_only, N, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 424, 1700)
+    nz.host.kernel_filter(tile_only, None, 2, N, 4)
+    assert np.array_equal(out2, tile_only)
+    mgr2.ReleaseBuffer(name)
+    with pytest.raises(nz.NzError) as e:
+        nz.host.context_read("no-such-buffer", out2)
+    assert e.value.code == nz.lib.NZ_E_STATE
