@@ -564,6 +564,16 @@ int32_t fractal_params(FractalParams* p, int width, int rows, int z_first, int n
     // bound on the simplex lattice index |floor(v + (vx+vy)*0.366)| <= 1.74*max|v| over the tile and all octaves
     {
         double f = 1.0, fmax = 1.0, det = 0.0;
+        bool positive = noise_size > 0 && xpos >= 0 && (long long)zpos + z_first >= 0;
+        {   // the kernels' own float recurrence decides the sign of every octave frequency
+            float ff = 1.0f, dd = 0.0f;
+            for (int i = 0; i < octaves; i++) {
+                dd += detune;
+                ff *= (stepdown - dd);
+                if (!(ff > 0.0f) && i + 1 < octaves) positive = false;
+            }
+        }
+        p->nonneg = positive;
         for (int i = 0; i < octaves; i++) {
             det += detune;
             f *= ((double)stepdown - det);

@@ -536,11 +536,8 @@ int32_t chain_setup(Chain& c, const nz_chain_config* cfg, int mode) {
 int chain_cap(const Chain& c) {
     const int above = c.h_filter + c.h_flow + c.h_erosion + c.h_mesh;
     if (c.mode == NZ_BANDS_RECOMPUTE) return above;
-    int m = c.h_filter;
-    if (c.h_flow > m) m = c.h_flow;
-    if (c.h_erosion > m) m = c.h_erosion;
-    if (c.h_mesh > m) m = c.h_mesh;
-    return m;
+    const int merged = c.h_flow + c.h_erosion + c.h_mesh;     // the second exchange of a pass (see chain_run)
+    return c.h_filter > merged ? c.h_filter : merged;
 }
 
 int32_t chain_check_fit(const Chain& c) {
@@ -569,8 +566,6 @@ int32_t chain_run(Chain& c, bool timed) {
     c.timed = timed;
     // recompute mode: ghost rows still needed AFTER each stage (the window shrinks stage by stage)
     const int rem_filter_a = exch ? 0 : c.h_flow + c.h_erosion + c.h_mesh, rem_filter_b = exch ? 0 : c.h_flow + c.h_mesh;
-    const int rem_flow_a = exch ? 0 : c.h_erosion + c.h_mesh, rem_flow_b = exch ? 0 : c.h_mesh;
-    const int rem_ero_a = exch ? 0 : c.h_mesh, rem_ero_b = exch ? 0 : c.h_mesh;
     int32_t rc;
     if ((rc = chain_mark(c, 0)) != NZ_OK) return rc;
     {
@@ -586,19 +581,28 @@ int32_t chain_run(Chain& c, bool timed) {
         if (rc != NZ_OK) return rc;
     }
     if ((rc = chain_mark(c, 2)) != NZ_OK) return rc;
+    if (exch) {
+        // Exchange mode moves ghost rows TWICE per pass: before the filter (r * iterations rows) and here, once, for
+        // everything downstream — the flow map's 2I+1 rows plus the rows the value erosion (above only) and the mesh (1)
+        // will still need from what the flow map and the erosion produce on those ghost rows.  Per-stage exchanges would
+        // cost two more NCCL round trips for a few rows of extra stencil work (17 above / 12 below at the C5 parameters).
+        const int a2 = c.h_flow + c.h_erosion + c.h_mesh, b2 = c.h_flow + c.h_mesh;
+        if ((rc = bandset_exchange(bs, a2, b2)) != NZ_OK) return rc;
+    }
+    // after the merged exchange both modes run the rest of the chain on shrinking windows
+    const int xfa = c.h_erosion + c.h_mesh, xfb = c.h_mesh, xea = c.h_mesh, xeb = c.h_mesh;
     if (f.flow_iterations > 0) {
-        rc = bandset_flowmap(bs, f.flow_iterations, f.norm_min, f.norm_max, rem_flow_a, rem_flow_b, exch);
+        rc = bandset_flowmap(bs, f.flow_iterations, f.norm_min, f.norm_max, xfa, xfb, false);
         if (rc != NZ_OK) return rc;
     }
     if ((rc = chain_mark(c, 3)) != NZ_OK) return rc;
     if (f.erosion_iterations > 0) {
-        rc = bandset_min_erosion(bs, f.erosion_iterations, rem_ero_a, rem_ero_b, exch);
+        rc = bandset_min_erosion(bs, f.erosion_iterations, xea, xeb, false);
         if (rc != NZ_OK) return rc;
     }
     if ((rc = chain_mark(c, 4)) != NZ_OK) return rc;
     if (f.mesh_resolution > 0) {
         Range rg("nz.mesh");
-        if (exch && (rc = bandset_exchange(bs, 1, 1)) != NZ_OK) return rc;
         rc = bandset_mesh(bs, f.mesh_type, f.mesh_resolution, f.tile_height, f.tile_size);
         if (rc != NZ_OK) return rc;
     }

@@ -442,11 +442,182 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_perlin_pair_kernel(float*
     }
 }
 
+// =====================================================================================================================
+// psrnoise (periodic simplex with rotated gradients): PeriodicPerlin (rot 0) and RotatedSimplex (rot 0.62), the basis of
+// BASELINE config C4.  Same function as psrnoise2<TYPE, true> in noise_kernels.cu, bit for bit (tests compare the two).
+//
+// The hash chain is  g = G[ permute( permute(xw + yw/2) + yw ) ]  per simplex corner, with (xw, yw) the corner wrapped into
+// the period (1010, 102).  The INNER hash argument is a half-integer, so it is not a residue class and stays arithmetic
+// (five f32x2 instructions per corner and pair); its result h1 is an exact integer in [-145, 145] and yw an exact integer
+// in [0, 102), so the OUTER hash and the (cos, sin) of its value are one bank-private LDS.64:
+//     T[(h1 + yw + 145) mod 289] = rotated_gradient(permute_int(h1 + yw), rot)        (289 rows x 256 B = 74 KB)
+// The period wrap of the first corner uses a round-to-nearest quotient (two packed adds) instead of the scalar kernel's
+// truncation (an XU instruction): the remainder is exact either way, and one conditional add of the period brings both to
+// the same value.  The other two corners are the first one plus a half-integer offset with ONE wrap.
+// Preconditions (host-checked, psr_pair_ok): FAST hash domain and non-negative noise coordinates, which make every wrapped
+// coordinate >= -1.5 and every yw >= 0.  A cell whose first corner is not >= (1, 0) (the first lattice column) recomputes
+// its six wrapped coordinates with the scalar kernel's own code.
+constexpr int PSR_ROWS = 289;
+constexpr int PSR_SMEM = PSR_ROWS * 256;
+constexpr float PSR_PERX = 1010.0f, PSR_PERY = 102.0f;
+
+__device__ __forceinline__ float2 psr_rotated_gradient(float p, float rot) {     // rotated_gradient() of noise_kernels.cu
+    float u = fmaf(p, 0.0243902439f, rot);
+    u = (u - floorf(u)) * 6.28318530718f;
+    return make_float2(cosf(u), sinf(u));
+}
+
+__device__ void build_psr_table(float rot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < PSR_ROWS; r += nwarps)
+        *reinterpret_cast<float2*>(sm + r * 256 + lane * 8) = psr_rotated_gradient((float)permute_int(r - 145), rot);
+    __syncthreads();
+}
+__device__ __forceinline__ float2 lds_psr(uint32_t off) { return *reinterpret_cast<const float2*>(sm + off); }
+
+// fmod_period<true>() of noise_kernels.cu (the slow path keeps the scalar kernel's exact code)
+__device__ __forceinline__ float psr_fmod_scalar(float p, float per, float inv_per) {
+    const float a = fabsf(p);
+    const float q = truncf(a * inv_per);
+    float r = fmaf(-per, q, a);
+    r = r < 0.0f ? r + per : r;
+    r = r >= per ? r - per : r;
+    return copysignf(r, p);
+}
+// p mod per for p >= 0 (exact): round-to-nearest quotient, remainder in (-per, per), one conditional add
+__device__ __forceinline__ P psr_fmod_pos(P p, float per, float inv_per) {
+    const P q = psub(pfma(p, bc(inv_per), bc(MAGIC)), bc(MAGIC));
+    const P r = pfma(bc(-per), q, p);
+    return padd(r, make_float2(r.x < 0.0f ? per : 0.0f, r.y < 0.0f ? per : 0.0f));
+}
+// v >= per ? v - per : v   (v < 2 per)
+__device__ __forceinline__ P psr_wrap_hi(P v, float per) {
+    return padd(v, make_float2(v.x >= per ? -per : 0.0f, v.y >= per ? -per : 0.0f));
+}
+// permute_centered() of noise_kernels.cu on a pair
+__device__ __forceinline__ P ppermute_centered(P x) {
+    const P u = pmul(pfma(bc(34.0f), x, bc(1.0f)), x);
+    const P q = psub(pfma(u, bc(1.0f / 289.0f), bc(MAGIC)), bc(MAGIC));
+    return pfma(bc(-289.0f), q, u);
+}
+// gradients of one corner of both cells: (gx.x, gy.x) for cell A, (gx.y, gy.y) for cell B
+__device__ __forceinline__ void psr_grad(P xw, P yw, uint32_t c2, P& gx, P& gy) {
+    const P h1 = ppermute_centered(pfma(bc(0.5f), yw, xw));
+    const P b = padd(padd(h1, yw), bc(MAGIC));                      // (h1 + yw) as address bits
+    uint32_t uA = (__float_as_uint(b.x) << 8) + c2, uB = (__float_as_uint(b.y) << 8) + c2;
+    uA = min(uA, uA - WRAP8);
+    uB = min(uB, uB - WRAP8);
+    const float2 gA = lds_psr(uA), gB = lds_psr(uB);
+    gx = make_float2(gA.x, gB.x);
+    gy = make_float2(gA.y, gB.y);
+}
+
+// psrnoise2(posx, posy) for two cells that share posx; returns the basis value Rectify(psrnoise) of both
+__device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
+    posy = padd(posy, bc(0.001f));
+    const P ux = pfma(posy, bc(0.5f), bc(posx));
+    const P i0x = pfloor(ux), i0y = pfloor(posy);
+    const P f0x = psub(ux, i0x), f0y = psub(posy, i0y);
+    const bool cA = f0x.x > f0y.x, cB = f0x.y > f0y.y;
+    const P i1x = make_float2(cA ? 1.0f : 0.0f, cB ? 1.0f : 0.0f);
+    const P i1y = make_float2(cA ? 0.0f : 1.0f, cB ? 0.0f : 1.0f);
+    const P h1y = make_float2(cA ? 0.0f : 0.5f, cB ? 0.0f : 0.5f);            // i1y * 0.5 (exact)
+    const P p0x = pfma(neg(i0y), bc(0.5f), i0x), p0y = i0y;
+    const P p1x = psub(padd(p0x, i1x), h1y), p1y = padd(p0y, i1y);
+    const P p2x = padd(p0x, bc(0.5f)), p2y = padd(p0y, bc(1.0f));
+    const P d0x = psub(bc(posx), p0x), d0y = psub(posy, p0y);
+    const P d1x = psub(bc(posx), p1x), d1y = psub(posy, p1y);
+    const P d2x = psub(bc(posx), p2x), d2y = psub(posy, p2y);
+    // period wrap: first corner by exact remainder, the other two by offset and one wrap
+    P xw0 = psr_fmod_pos(p0x, PSR_PERX, 1.0f / PSR_PERX), yw0 = psr_fmod_pos(p0y, PSR_PERY, 1.0f / PSR_PERY);
+    P yw2 = psr_wrap_hi(padd(yw0, bc(1.0f)), PSR_PERY);
+    P yw1 = make_float2(cA ? yw0.x : yw2.x, cB ? yw0.y : yw2.y);
+    P xw2 = psr_wrap_hi(padd(xw0, bc(0.5f)), PSR_PERX);
+    P xw1 = psr_wrap_hi(padd(xw0, make_float2(cA ? 1.0f : -0.5f, cB ? 1.0f : -0.5f)), PSR_PERX);
+    xw1 = padd(xw1, make_float2(xw1.x < 0.0f ? PSR_PERX : 0.0f, xw1.y < 0.0f ? PSR_PERX : 0.0f));
+    // first lattice column / row: the scalar kernel's general path, per cell (rare)
+    const bool slowA = !(p0x.x >= 1.0f && p0y.x >= 0.0f), slowB = !(p0x.y >= 1.0f && p0y.y >= 0.0f);
+    if (slowA || slowB) {
+        const float ipx = 1.0f / PSR_PERX, ipy = 1.0f / PSR_PERY;
+        if (slowA) {
+            xw0.x = psr_fmod_scalar(p0x.x, PSR_PERX, ipx); yw0.x = psr_fmod_scalar(p0y.x, PSR_PERY, ipy);
+            xw1.x = psr_fmod_scalar(p1x.x, PSR_PERX, ipx); yw1.x = psr_fmod_scalar(p1y.x, PSR_PERY, ipy);
+            xw2.x = psr_fmod_scalar(p2x.x, PSR_PERX, ipx); yw2.x = psr_fmod_scalar(p2y.x, PSR_PERY, ipy);
+        }
+        if (slowB) {
+            xw0.y = psr_fmod_scalar(p0x.y, PSR_PERX, ipx); yw0.y = psr_fmod_scalar(p0y.y, PSR_PERY, ipy);
+            xw1.y = psr_fmod_scalar(p1x.y, PSR_PERX, ipx); yw1.y = psr_fmod_scalar(p1y.y, PSR_PERY, ipy);
+            xw2.y = psr_fmod_scalar(p2x.y, PSR_PERX, ipx); yw2.y = psr_fmod_scalar(p2y.y, PSR_PERY, ipy);
+        }
+    }
+    P g0x, g0y, g1x, g1y, g2x, g2y;
+    psr_grad(xw0, yw0, c2, g0x, g0y);
+    psr_grad(xw1, yw1, c2, g1x, g1y);
+    psr_grad(xw2, yw2, c2, g2x, g2y);
+    const P w0 = pfma(g0y, d0y, pmul(g0x, d0x)), w1 = pfma(g1y, d1y, pmul(g1x, d1x)), w2 = pfma(g2y, d2y, pmul(g2x, d2x));
+    P t0 = pmax0(psub(bc(0.8f), pfma(d0y, d0y, pmul(d0x, d0x))));
+    P t1 = pmax0(psub(bc(0.8f), pfma(d1y, d1y, pmul(d1x, d1x))));
+    P t2 = pmax0(psub(bc(0.8f), pfma(d2y, d2y, pmul(d2x, d2x))));
+    t0 = pmul(t0, t0); t0 = pmul(t0, t0);
+    t1 = pmul(t1, t1); t1 = pmul(t1, t1);
+    t2 = pmul(t2, t2); t2 = pmul(t2, t2);
+    const P n = pmul(bc(11.0f), pfma(t2, w2, pfma(t1, w1, pmul(t0, w0))));     // 11 * dot3(t, w)
+    return pmul(padd(n, bc(1.0f)), bc(0.5f));                                 // Rectify: (1 + v) * 0.5
+}
+
+__global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_psr_pair_kernel(float* __restrict__ dst, FractalParams p, float rot, int wshift,
+                                                                      int col_blocks, int n_items) {
+    build_psr_table(rot);
+    const int lane = threadIdx.x & 31;
+    uint32_t c2 = 145 * 256 + lane * 8 - MAGIC_SHL8;
+    asm volatile("" : "+r"(c2));
+    const int tx = threadIdx.x & ((1 << wshift) - 1), ty = threadIdx.x >> wshift;
+    const int rows_per_item = 4 * (PAIR_THREADS >> wshift);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cb = item % col_blocks, rg = item / col_blocks;
+        const int x = (cb << wshift) + tx;
+        const int r0 = rg * rows_per_item + 4 * ty;
+        const float xi = ((float)x + p.posx) / p.noise_size;
+        P zi[2], t[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            zi[q].x = ((float)(p.z_first + r0 + 2 * q) + p.posz) / p.noise_size;
+            zi[q].y = ((float)(p.z_first + r0 + 2 * q + 1) + p.posz) / p.noise_size;
+            t[q] = bc(0.0f);
+        }
+        float detune = 0.0f, f = 1.0f, a = p.start_amp;
+        for (int i = 0; i < p.octaves; i++) {
+            const float posx = f * xi;
+#pragma unroll
+            for (int q = 0; q < 2; q++) t[q] = pfma(bc(a), psr_pair(posx, pmul(bc(f), zi[q]), c2), t[q]);
+            detune += p.detune_rate;
+            f *= (p.stepdown - detune);
+            a *= p.G;
+        }
+        if (x < p.width) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int r = r0 + 2 * q;
+                if (r < p.rows) dst[(size_t)r * p.width + x] = t[q].x / p.norm;
+                if (r + 1 < p.rows) dst[(size_t)(r + 1) * p.width + x] = t[q].y / p.norm;
+            }
+        }
+    }
+}
+
 }  // namespace
 
+static bool is_psr(int noise_type) { return noise_type == NZ_NOISE_PERIODIC_PERLIN || noise_type == NZ_NOISE_ROTATED_SIMPLEX; }
+
+// the psrnoise pair kernel additionally needs non-negative noise coordinates (see its header)
+bool fractal_pair_possible(int noise_type, const FractalParams& p) {
+    if (!p.fast_hash || p.width < 32) return false;
+    if (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR || noise_type == NZ_NOISE_PERLIN) return true;
+    return is_psr(noise_type) && p.nonneg;
+}
+
 bool fractal_pair_supported(int noise_type, const FractalParams& p) {
-    return (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR || noise_type == NZ_NOISE_PERLIN) && p.fast_hash &&
-           p.width >= 32 && (long long)p.width * p.rows >= (1 << 19);
+    return fractal_pair_possible(noise_type, p) && (long long)p.width * p.rows >= (1 << 19);
 }
 
 int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s) {
@@ -457,6 +628,7 @@ int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p
         NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_cellular_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELL_SMEM));
         NZ_CUDA(cudaFuncSetAttribute(fbm_perlin_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PERLIN_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(fbm_psr_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSR_SMEM));
         configured.mark();
     }
     int wshift = 5;
@@ -472,7 +644,10 @@ int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p
     const long long n_items = (long long)col_blocks * cdiv(p.rows, rows_per_item);
     NZ_REQUIRE(n_items < (1ll << 31), "nz_fractal: window too large");
     const int grid = n_items < sms ? (int)n_items : sms;
-    if (noise_type == NZ_NOISE_PERLIN) {
+    if (is_psr(noise_type)) {
+        const float rot = noise_type == NZ_NOISE_ROTATED_SIMPLEX ? 0.62f : 0.0f;     // Fractal.cs:184,201
+        fbm_psr_pair_kernel<<<grid, PAIR_THREADS, PSR_SMEM, s>>>(d_dst, p, rot, wshift, col_blocks, (int)n_items);
+    } else if (noise_type == NZ_NOISE_PERLIN) {
         fbm_perlin_pair_kernel<2><<<grid, PAIR_THREADS, PERLIN_SMEM, s>>>(d_dst, p, wshift, col_blocks, (int)n_items);
     } else if (noise_type == NZ_NOISE_CELLULAR) {
         if (cells == 2)

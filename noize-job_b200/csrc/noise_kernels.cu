@@ -486,9 +486,7 @@ int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cud
     {
         const char* force = getenv("NZ_FBM_PATH");
         const bool scalar = force && force[0] == 's', pair = force && force[0] == 'p';
-        if (!scalar && (noise_type == NZ_NOISE_SIMPLEX || noise_type == NZ_NOISE_CELLULAR || noise_type == NZ_NOISE_PERLIN) &&
-            p.fast_hash && p.width >= 32 &&
-            (pair || fractal_pair_supported(noise_type, p)))
+        if (!scalar && fractal_pair_possible(noise_type, p) && (pair || fractal_pair_supported(noise_type, p)))
             return launch_fractal_pair(d_dst, noise_type, p, s);
     }
     if (p.rows > 65535) {

@@ -53,11 +53,13 @@ struct FractalParams {
     float norm;  // CalcFractalNormValue
     int fast_hash;  // every lattice index of this launch is below 2^21 (simplex may use the magic-number residue)
     int fast_hash3d;  // the same for the domain-rotated 3-D bases (their rotated / skewed coordinates are up to 3x larger)
+    int nonneg;       // every noise coordinate of this launch is >= 0 (tile origin, row offset, noise size and all octave frequencies)
 };
 int32_t fractal_params(FractalParams* p, int width, int rows, int z_first, int noise_type, float hurst, float start_amp,
                        float stepdown, float detune, int octaves, int xpos, int zpos, int noise_size);   // abi.cu
 int32_t launch_fractal(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
-bool fractal_pair_supported(int noise_type, const FractalParams& p);
+bool fractal_pair_possible(int noise_type, const FractalParams& p);    // the packed-pair kernel computes this launch correctly
+bool fractal_pair_supported(int noise_type, const FractalParams& p);   // ... and the window is large enough to prefer it
 int32_t launch_fractal_pair(float* d_dst, int noise_type, const FractalParams& p, cudaStream_t s);
 
 int32_t launch_separable(float* d_data, float* d_tmp, int width, int rows, int ksize, const float* kx,

@@ -682,3 +682,31 @@ def test_concurrent_host_threads_with_side_streams(nz, oracle):
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
     assert len({w.tobytes()[:4096] for w in want}) == 4      # the four inputs really differ
+
+
+@pytest.mark.parametrize("res,pos", [(96, (0, 0)), (300, (0, 424)), (1031, (100000, 3)), (1024, (15000, 15000)), (2048, (14336, 14336))])
+@pytest.mark.parametrize("noise_type", [2, 4])
+def test_packed_pair_psrnoise_kernel_is_bit_identical_to_the_scalar_kernel(nz, oracle, fbm_path, res, pos, noise_type):
+    """fbm_psr_pair_kernel (periodic perlin / rotated simplex, the basis of BASELINE config C4) vs fbm_kernel<...> in
+    noise_kernels.cu.  (0, 0) exercises the first lattice column, where a cell falls back to the scalar wrap code."""
+    fbm_path("scalar")
+    a = gpu_fractal(nz, res, noise_type, *pos)
+    fbm_path("pair")
+    b = gpu_fractal(nz, res, noise_type, *pos)
+    fbm_path(None)
+    assert np.isfinite(a).all()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if res <= 300:
+        assert np.abs(b - ref_fractal(oracle, res, noise_type, *pos)).max() <= TOL_NOISE
+
+
+def test_packed_pair_psrnoise_kernel_odd_parameters_and_negative_origins(nz, fbm_path):
+    kw = dict(hurst=0.9001, octaves=6, noise_size=7475, stepdown=2.17, detune_rate=0.013, starting_amplitude=0.7)
+    for noise_type in (2, 4):
+        for pos in ((12345, 999), (12345, -999), (-7, 5)):          # negative origins are not eligible: both runs take the scalar kernel
+            fbm_path("scalar")
+            a = gpu_fractal(nz, 777, noise_type, *pos, **kw)
+            fbm_path("pair")
+            b = gpu_fractal(nz, 777, noise_type, *pos, **kw)
+            fbm_path(None)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (noise_type, pos)
