@@ -484,15 +484,28 @@ __device__ __forceinline__ float psr_fmod_scalar(float p, float per, float inv_p
     r = r >= per ? r - per : r;
     return copysignf(r, p);
 }
-// p mod per for p >= 0 (exact): round-to-nearest quotient, remainder in (-per, per), one conditional add
-__device__ __forceinline__ P psr_fmod_pos(P p, float per, float inv_per) {
-    const P q = psub(pfma(p, bc(inv_per), bc(MAGIC)), bc(MAGIC));
-    const P r = pfma(bc(-per), q, p);
-    return padd(r, make_float2(r.x < 0.0f ? per : 0.0f, r.y < 0.0f ? per : 0.0f));
+// Exact selects without predicates.  For floats a, b of which at most one is negative and the wanted one is the smaller
+// NON-NEGATIVE one, the unsigned minimum of the bit patterns picks it (a negative float has the sign bit set, i.e. is huge
+// as an unsigned): one integer min per element instead of a compare and a select.
+__device__ __forceinline__ P umin_bits(P a, P b) {
+    return make_float2(__uint_as_float(min(__float_as_uint(a.x), __float_as_uint(b.x))),
+                       __uint_as_float(min(__float_as_uint(a.y), __float_as_uint(b.y))));
 }
-// v >= per ? v - per : v   (v < 2 per)
-__device__ __forceinline__ P psr_wrap_hi(P v, float per) {
-    return padd(v, make_float2(v.x >= per ? -per : 0.0f, v.y >= per ? -per : 0.0f));
+// a - b without a sign flip of b (fma(b, -1, a) is the same IEEE difference)
+__device__ __forceinline__ P psubm(P a, P b) { return __ffma2_rn(b, bc(-1.0f), a); }
+// r < 0 ? r + per : r   for r in (-per, per)
+__device__ __forceinline__ P psr_wrap_lo(P r, float per) { return umin_bits(r, padd(r, bc(per))); }
+// v >= per ? v - per : v   for v in [0, 2 per)
+__device__ __forceinline__ P psr_wrap_hi(P v, float per) { return umin_bits(v, padd(v, bc(-per))); }
+// v >= per ? v - per : v   for v in (-per, 2 per): a negative v stays (v - per is negative too: compare, do not bit-min)
+__device__ __forceinline__ P psr_wrap_hi_signed(P v, float per) {
+    const P w = padd(v, bc(-per));
+    return make_float2(w.x >= 0.0f ? w.x : v.x, w.y >= 0.0f ? w.y : v.y);
+}
+// p mod per for p >= 0 (exact): round-to-nearest quotient, remainder in (-per, per), one wrap
+__device__ __forceinline__ P psr_fmod_pos(P p, float per, float inv_per) {
+    const P q = padd(pfma(p, bc(inv_per), bc(MAGIC)), bc(-MAGIC));
+    return psr_wrap_lo(pfma(bc(-per), q, p), per);
 }
 // permute_centered() of noise_kernels.cu on a pair
 __device__ __forceinline__ P ppermute_centered(P x) {
@@ -512,40 +525,43 @@ __device__ __forceinline__ void psr_grad(P xw, P yw, uint32_t c2, P& gx, P& gy) 
     gy = make_float2(gA.y, gB.y);
 }
 
-// psrnoise2(posx, posy) for two cells that share posx; returns the basis value Rectify(psrnoise) of both
+// psrnoise2(posx, posy) for two cells that share posx; returns the basis value Rectify(psrnoise) of both.
+// Differences and selects are written in the forms that cost the fewest issue slots; each is the same exact value or the
+// same single IEEE rounding as the scalar kernel's expression (commented where it is not literal).
 __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
     posy = padd(posy, bc(0.001f));
     const P ux = pfma(posy, bc(0.5f), bc(posx));
     const P i0x = pfloor(ux), i0y = pfloor(posy);
-    const P f0x = psub(ux, i0x), f0y = psub(posy, i0y);
-    const bool cA = f0x.x > f0y.x, cB = f0x.y > f0y.y;
-    const P i1x = make_float2(cA ? 1.0f : 0.0f, cB ? 1.0f : 0.0f);
-    const P i1y = make_float2(cA ? 0.0f : 1.0f, cB ? 0.0f : 1.0f);
-    const P h1y = make_float2(cA ? 0.0f : 0.5f, cB ? 0.0f : 0.5f);            // i1y * 0.5 (exact)
-    const P p0x = pfma(neg(i0y), bc(0.5f), i0x), p0y = i0y;
-    const P p1x = psub(padd(p0x, i1x), h1y), p1y = padd(p0y, i1y);
-    const P p2x = padd(p0x, bc(0.5f)), p2y = padd(p0y, bc(1.0f));
-    const P d0x = psub(bc(posx), p0x), d0y = psub(posy, p0y);
-    const P d1x = psub(bc(posx), p1x), d1y = psub(posy, p1y);
-    const P d2x = psub(bc(posx), p2x), d2y = psub(posy, p2y);
-    // period wrap: first corner by exact remainder, the other two by offset and one wrap
-    P xw0 = psr_fmod_pos(p0x, PSR_PERX, 1.0f / PSR_PERX), yw0 = psr_fmod_pos(p0y, PSR_PERY, 1.0f / PSR_PERY);
+    const P f0x = psubm(ux, i0x), f0y = psubm(posy, i0y);
+    // c = f0x > f0y as 1.0 / 0.0; (i1x, i1y) = (c, 1 - c), i1y / 2 = 0.5 - c / 2, all exact
+    const P c = make_float2(f0x.x > f0y.x ? 1.0f : 0.0f, f0x.y > f0y.y ? 1.0f : 0.0f);
+    const P i1y = psubm(bc(1.0f), c);
+    const P p0x = pfma(i0y, bc(-0.5f), i0x);                                   // fma(-i0y, 0.5, i0x)
+    const P p1x = psubm(padd(p0x, c), pfma(c, bc(-0.5f), bc(0.5f))), p1y = padd(i0y, i1y);
+    const P p2x = padd(p0x, bc(0.5f)), p2y = padd(i0y, bc(1.0f));
+    const P d0x = psubm(bc(posx), p0x), d0y = psubm(posy, i0y);
+    const P d1x = psubm(bc(posx), p1x), d1y = psubm(posy, p1y);
+    const P d2x = psubm(bc(posx), p2x), d2y = psubm(posy, p2y);
+    // period wrap: first corner by exact remainder, the other two by offset and one wrap (all values are exact multiples
+    // of 0.5, so any exact route to the remainder gives the scalar kernel's bits)
+    P xw0 = psr_fmod_pos(p0x, PSR_PERX, 1.0f / PSR_PERX), yw0 = psr_fmod_pos(i0y, PSR_PERY, 1.0f / PSR_PERY);
     P yw2 = psr_wrap_hi(padd(yw0, bc(1.0f)), PSR_PERY);
-    P yw1 = make_float2(cA ? yw0.x : yw2.x, cB ? yw0.y : yw2.y);
+    P yw1 = pfma(c, psubm(yw0, yw2), yw2);                                    // c ? yw0 : yw2  (exact: small integers)
     P xw2 = psr_wrap_hi(padd(xw0, bc(0.5f)), PSR_PERX);
-    P xw1 = psr_wrap_hi(padd(xw0, make_float2(cA ? 1.0f : -0.5f, cB ? 1.0f : -0.5f)), PSR_PERX);
-    xw1 = padd(xw1, make_float2(xw1.x < 0.0f ? PSR_PERX : 0.0f, xw1.y < 0.0f ? PSR_PERX : 0.0f));
-    // first lattice column / row: the scalar kernel's general path, per cell (rare)
-    const bool slowA = !(p0x.x >= 1.0f && p0y.x >= 0.0f), slowB = !(p0x.y >= 1.0f && p0y.y >= 0.0f);
+    // xw0 + (c ? 1 : -0.5) lies in [-0.5, per + 1): wrap down, then up (at most one of them changes the value)
+    P xw1 = psr_wrap_lo(psr_wrap_hi_signed(padd(xw0, pfma(c, bc(1.5f), bc(-0.5f))), PSR_PERX), PSR_PERX);
+    // first lattice column (p0x < 1; p0y >= 0 always: the host proved the coordinates non-negative): the scalar
+    // kernel's general path, per cell (rare)
+    const bool slowA = !(p0x.x >= 1.0f), slowB = !(p0x.y >= 1.0f);
     if (slowA || slowB) {
         const float ipx = 1.0f / PSR_PERX, ipy = 1.0f / PSR_PERY;
         if (slowA) {
-            xw0.x = psr_fmod_scalar(p0x.x, PSR_PERX, ipx); yw0.x = psr_fmod_scalar(p0y.x, PSR_PERY, ipy);
+            xw0.x = psr_fmod_scalar(p0x.x, PSR_PERX, ipx); yw0.x = psr_fmod_scalar(i0y.x, PSR_PERY, ipy);
             xw1.x = psr_fmod_scalar(p1x.x, PSR_PERX, ipx); yw1.x = psr_fmod_scalar(p1y.x, PSR_PERY, ipy);
             xw2.x = psr_fmod_scalar(p2x.x, PSR_PERX, ipx); yw2.x = psr_fmod_scalar(p2y.x, PSR_PERY, ipy);
         }
         if (slowB) {
-            xw0.y = psr_fmod_scalar(p0x.y, PSR_PERX, ipx); yw0.y = psr_fmod_scalar(p0y.y, PSR_PERY, ipy);
+            xw0.y = psr_fmod_scalar(p0x.y, PSR_PERX, ipx); yw0.y = psr_fmod_scalar(i0y.y, PSR_PERY, ipy);
             xw1.y = psr_fmod_scalar(p1x.y, PSR_PERX, ipx); yw1.y = psr_fmod_scalar(p1y.y, PSR_PERY, ipy);
             xw2.y = psr_fmod_scalar(p2x.y, PSR_PERX, ipx); yw2.y = psr_fmod_scalar(p2y.y, PSR_PERY, ipy);
         }
@@ -555,9 +571,9 @@ __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
     psr_grad(xw1, yw1, c2, g1x, g1y);
     psr_grad(xw2, yw2, c2, g2x, g2y);
     const P w0 = pfma(g0y, d0y, pmul(g0x, d0x)), w1 = pfma(g1y, d1y, pmul(g1x, d1x)), w2 = pfma(g2y, d2y, pmul(g2x, d2x));
-    P t0 = pmax0(psub(bc(0.8f), pfma(d0y, d0y, pmul(d0x, d0x))));
-    P t1 = pmax0(psub(bc(0.8f), pfma(d1y, d1y, pmul(d1x, d1x))));
-    P t2 = pmax0(psub(bc(0.8f), pfma(d2y, d2y, pmul(d2x, d2x))));
+    P t0 = pmax0(psubm(bc(0.8f), pfma(d0y, d0y, pmul(d0x, d0x))));
+    P t1 = pmax0(psubm(bc(0.8f), pfma(d1y, d1y, pmul(d1x, d1x))));
+    P t2 = pmax0(psubm(bc(0.8f), pfma(d2y, d2y, pmul(d2x, d2x))));
     t0 = pmul(t0, t0); t0 = pmul(t0, t0);
     t1 = pmul(t1, t1); t1 = pmul(t1, t1);
     t2 = pmul(t2, t2); t2 = pmul(t2, t2);

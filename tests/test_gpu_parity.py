@@ -710,3 +710,21 @@ def test_packed_pair_psrnoise_kernel_odd_parameters_and_negative_origins(nz, fbm
             b = gpu_fractal(nz, 777, noise_type, *pos, **kw)
             fbm_path(None)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (noise_type, pos)
+
+
+@pytest.mark.parametrize("group", ["0", "4", "6"])
+@pytest.mark.parametrize("rows,width,iters", [(1100, 4100, 5), (1400, 3000, 4), (1500, 2872, 3), (2100, 2048, 5), (700, 6144, 5)])
+def test_flow_group_strips_equal_wavefront_kernel_bitwise(nz, oracle, torch_cuda, monkeypatch, rows, width, iters, group):
+    """flow_group_kernel: the warps of a CTA share one wide strip and trade their seam values through shared memory once
+    per step (NZ_FLOW_GROUP = 4 or 6 warps; 0 = the independent 64-column strips).  Grids above 2^22 cells engage it."""
+    torch = torch_cuda
+    h = torch.rand(rows, width, device="cuda") * 0.05 + torch.linspace(0, 1, width, device="cuda")[None, :] * 0.2
+    monkeypatch.setenv("NZ_FLOW_PATH", "wave")
+    wave = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    before = nz.device.flow_walk_reruns()
+    monkeypatch.setenv("NZ_FLOW_PATH", "reg")
+    monkeypatch.setenv("NZ_FLOW_GROUP", group)
+    reg = nz.device.flowmap(h.clone(), torch.empty_like(h), None, iters, 0.0, 0.005).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(reg, wave)
+    assert nz.device.flow_walk_reruns() == before
