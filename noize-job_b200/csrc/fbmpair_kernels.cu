@@ -525,7 +525,7 @@ __device__ __forceinline__ void psr_grad(P xw, P yw, uint32_t c2, P& gx, P& gy) 
     gy = make_float2(gA.y, gB.y);
 }
 
-// psrnoise2(posx, posy) for two cells that share posx; returns the basis value Rectify(psrnoise) of both.
+// psrnoise2(posx, posy) for two cells that share posx; returns TWICE the basis value Rectify(psrnoise) of both.
 // Differences and selects are written in the forms that cost the fewest issue slots; each is the same exact value or the
 // same single IEEE rounding as the scalar kernel's expression (commented where it is not literal).
 __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
@@ -533,11 +533,12 @@ __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
     const P ux = pfma(posy, bc(0.5f), bc(posx));
     const P i0x = pfloor(ux), i0y = pfloor(posy);
     const P f0x = psubm(ux, i0x), f0y = psubm(posy, i0y);
-    // c = f0x > f0y as 1.0 / 0.0; (i1x, i1y) = (c, 1 - c), i1y / 2 = 0.5 - c / 2, all exact
-    const P c = make_float2(f0x.x > f0y.x ? 1.0f : 0.0f, f0x.y > f0y.y ? 1.0f : 0.0f);
-    const P i1y = psubm(bc(1.0f), c);
+    // The kernel is bound by the FP32 pipe (88 f32x2 instructions per pair and octave, measured 11.7 ms at 16384^2), so
+    // everything that depends on the simplex half c = f0x > f0y is a SELECT (ALU pipe), not arithmetic
+    const bool cA = f0x.x > f0y.x, cB = f0x.y > f0y.y;
+    const P i1x = make_float2(cA ? 1.0f : 0.0f, cB ? 1.0f : 0.0f), i1y = make_float2(cA ? 0.0f : 1.0f, cB ? 0.0f : 1.0f);
     const P p0x = pfma(i0y, bc(-0.5f), i0x);                                   // fma(-i0y, 0.5, i0x)
-    const P p1x = psubm(padd(p0x, c), pfma(c, bc(-0.5f), bc(0.5f))), p1y = padd(i0y, i1y);
+    const P p1x = psubm(padd(p0x, i1x), make_float2(cA ? 0.0f : 0.5f, cB ? 0.0f : 0.5f)), p1y = padd(i0y, i1y);
     const P p2x = padd(p0x, bc(0.5f)), p2y = padd(i0y, bc(1.0f));
     const P d0x = psubm(bc(posx), p0x), d0y = psubm(posy, i0y);
     const P d1x = psubm(bc(posx), p1x), d1y = psubm(posy, p1y);
@@ -546,10 +547,10 @@ __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
     // of 0.5, so any exact route to the remainder gives the scalar kernel's bits)
     P xw0 = psr_fmod_pos(p0x, PSR_PERX, 1.0f / PSR_PERX), yw0 = psr_fmod_pos(i0y, PSR_PERY, 1.0f / PSR_PERY);
     P yw2 = psr_wrap_hi(padd(yw0, bc(1.0f)), PSR_PERY);
-    P yw1 = pfma(c, psubm(yw0, yw2), yw2);                                    // c ? yw0 : yw2  (exact: small integers)
+    P yw1 = make_float2(cA ? yw0.x : yw2.x, cB ? yw0.y : yw2.y);
     P xw2 = psr_wrap_hi(padd(xw0, bc(0.5f)), PSR_PERX);
     // xw0 + (c ? 1 : -0.5) lies in [-0.5, per + 1): wrap down, then up (at most one of them changes the value)
-    P xw1 = psr_wrap_lo(psr_wrap_hi_signed(padd(xw0, pfma(c, bc(1.5f), bc(-0.5f))), PSR_PERX), PSR_PERX);
+    P xw1 = psr_wrap_lo(psr_wrap_hi_signed(padd(xw0, make_float2(cA ? 1.0f : -0.5f, cB ? 1.0f : -0.5f)), PSR_PERX), PSR_PERX);
     // first lattice column (p0x < 1; p0y >= 0 always: the host proved the coordinates non-negative): the scalar
     // kernel's general path, per cell (rare)
     const bool slowA = !(p0x.x >= 1.0f), slowB = !(p0x.y >= 1.0f);
@@ -578,7 +579,8 @@ __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
     t1 = pmul(t1, t1); t1 = pmul(t1, t1);
     t2 = pmul(t2, t2); t2 = pmul(t2, t2);
     const P n = pmul(bc(11.0f), pfma(t2, w2, pfma(t1, w1, pmul(t0, w0))));     // 11 * dot3(t, w)
-    return pmul(padd(n, bc(1.0f)), bc(0.5f));                                 // Rectify: (1 + v) * 0.5
+    // Rectify is (1 + v) * 0.5; the exact halving is folded into the caller's amplitude: fma(a, 0.5 x, t) == fma(0.5 a, x, t)
+    return padd(n, bc(1.0f));
 }
 
 __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_psr_pair_kernel(float* __restrict__ dst, FractalParams p, float rot, int wshift,
@@ -605,7 +607,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_psr_pair_kernel(float* __
         for (int i = 0; i < p.octaves; i++) {
             const float posx = f * xi;
 #pragma unroll
-            for (int q = 0; q < 2; q++) t[q] = pfma(bc(a), psr_pair(posx, pmul(bc(f), zi[q]), c2), t[q]);
+            const float ah = a * 0.5f;            // exact (power of two): see psr_pair
+#pragma unroll
+            for (int q = 0; q < 2; q++) t[q] = pfma(bc(ah), psr_pair(posx, pmul(bc(f), zi[q]), c2), t[q]);
             detune += p.detune_rate;
             f *= (p.stepdown - detune);
             a *= p.G;

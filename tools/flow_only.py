@@ -13,6 +13,8 @@ for _ in range(2):
         nz.device.kernel_filter(a, b, 2, 17)
     elif what == "noise":
         nz.device.fractal(a, 3, 0.4, octaves=13, noise_size=1700)
+    elif what == "psr":
+        nz.device.fractal(a, 4, 0.4, octaves=13, noise_size=1700)
     elif what == "erosion":
         nz.device.min_erosion(a, b, 5)
 torch.cuda.synchronize()
