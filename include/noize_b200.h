@@ -344,6 +344,10 @@ typedef struct {
     int64_t halo_bytes_per_run;     /* ghost-row bytes this band received per run */
 } nz_band_info;
 
+/* Host logic of the partition, no GPU needed: rows [z0, z1) and vertex rows [vz0, vz1) band `rank` of `world` owns of a
+ * resolution^2 grid meshed at mesh_resolution (0: no mesh).  Fills rank, world, z0, z1, vz0, vz1 of *out; the rest is zero. */
+NZ_API int32_t nz_band_geometry(int32_t resolution, int32_t world, int32_t rank, int32_t mesh_resolution, nz_band_info* out);
+
 /* NCCL communicator over the band processes (one rank per GPU).  Rank 0 calls nz_comm_unique_id and hands the 128 bytes
  * to the others through whatever channel the host has; every rank then calls nz_comm_create.  > 0: handle; < 0: NZ_E*. */
 NZ_API int32_t nz_comm_unique_id(void* id_bytes, int32_t capacity);

@@ -435,3 +435,12 @@ class LibBandChain:
             self.release()
         except Exception:
             pass
+
+
+def lib_band_geometry(N, world, rank, mesh_resolution=0):
+    """nz_band_geometry: (z0, z1, vz0, vz1) of band `rank` of `world` as the LIBRARY partitions the grid (no GPU needed)."""
+    import ctypes as C
+    from . import lib as _l
+    i = _l.BandInfo()
+    _l.check(_l.load().nz_band_geometry(N, world, rank, mesh_resolution, C.byref(i)))
+    return i.z0, i.z1, i.vz0, i.vz1

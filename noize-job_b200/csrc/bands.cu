@@ -629,6 +629,22 @@ using namespace nz;
 
 extern "C" {
 
+NZ_API int32_t nz_band_geometry(int32_t resolution, int32_t world, int32_t rank, int32_t mesh_resolution, nz_band_info* out) {
+    NZ_REQUIRE(out, "nz_band_geometry: null output");
+    NZ_REQUIRE(resolution > 0 && world >= 1 && world <= resolution && rank >= 0 && rank < world && mesh_resolution >= 0,
+               "nz_band_geometry: bad partition (resolution %d, world %d, rank %d)", resolution, world, rank);
+    memset(out, 0, sizeof(*out));
+    Band bd;
+    bd.rank = rank;
+    band_rows(resolution, world, rank, &bd.z0, &bd.z1);
+    out->rank = rank;
+    out->world = world;
+    out->z0 = bd.z0;
+    out->z1 = bd.z1;
+    if (mesh_resolution > 0) band_vertex_rows(bd, world, resolution, mesh_resolution, &out->vz0, &out->vz1);
+    return NZ_OK;
+}
+
 NZ_API int32_t nz_comm_unique_id(void* id_bytes, int32_t capacity) {
     NZ_REQUIRE(id_bytes && capacity >= NZ_COMM_ID_BYTES, "nz_comm_unique_id: the buffer must hold %d bytes", NZ_COMM_ID_BYTES);
     Nccl* api;

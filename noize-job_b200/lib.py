@@ -72,6 +72,7 @@ SIGNATURES = {
     "nz_context_download": (_i32, [C.c_char_p, _vp, _i32]),
     "nz_context_upload": (_i32, [C.c_char_p, _vp, _i32]),
     "nz_context_release": (_i32, [C.c_char_p]),
+    "nz_band_geometry": (_i32, [_i32, _i32, _i32, _i32, C.POINTER(BandInfo)]),
     "nz_comm_unique_id": (_i32, [_vp, _i32]),
     "nz_comm_create": (C.c_int64, [_vp, _i32, _i32, _i32]),
     "nz_comm_async_error": (_i32, [C.c_int64]),

@@ -150,3 +150,32 @@ def test_cuda_engine_fails_loudly_without_a_gpu():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU path"):
         bands.CudaEngine()
+
+
+def test_library_partition_equals_python_partition():
+    """The in-library band chain (nz_band_chain_*) and bands.BandChain must cut the grid identically: owned heightmap rows
+    and owned vertex rows, for every rank, including uneven splits and the margin rows of the first / last band."""
+    from noize_job_b200 import bands
+
+    class NoEngine:
+        name = "none"
+
+        def empty(self, rows, width):
+            return None
+
+    for N, margin in ((16384, 4), (1024, 4), (1000, 12), (257, 1)):
+        cfg = bands.ChainConfig(N=N, mesh_margin=margin, filter_iterations=1, flow_iterations=1, erosion_iterations=1)
+        for world in (1, 2, 3, 7, 8):
+            covered, vcovered = [], []
+            for rank in range(world):
+                z0, z1, vz0, vz1 = bands.lib_band_geometry(N, world, rank, cfg.R)
+                py = bands.BandChain(cfg, NoEngine(), rank, world, None, mode="recompute")
+                assert (z0, z1, vz0, vz1) == (py.z0, py.z1, py.vz0, py.vz1), (N, world, rank)
+                covered.append((z0, z1))
+                vcovered.append((vz0, vz1))
+            assert covered[0][0] == 0 and covered[-1][1] == N and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+            assert vcovered[0][0] == 0 and vcovered[-1][1] == cfg.R + 1 and all(a[1] == b[0] for a, b in zip(vcovered, vcovered[1:]))
+    import noize_job_b200 as nz
+    import pytest
+    with pytest.raises(nz.NzError):
+        bands.lib_band_geometry(16, 32, 0)

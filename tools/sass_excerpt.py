@@ -22,7 +22,7 @@ KERNELS = [
     ("sep_walk_kernel_R2_T3", r"sep_walk_kernel<2, 3, false, 16>"),
     ("sep_ring_kernel_R2", r"sep_ring_kernel<2,"),
     ("flow_walk_kernel_I5", r"flow_walk_kernel<5,"),
-    ("flow_quad_kernel_I5", r"flow_quad_kernel<5"),
+    ("flow_group_kernel_I5_NW4", r"flow_group_kernel<5, 4,"),
     ("min_walk_kernel_5", r"min_walk_kernel<5>"),
     ("mesh_kernel_overshoot", r"mesh_kernel<1>"),
     ("thermal_tile_kernel", r"thermal_tile_kernel"),
