@@ -458,8 +458,16 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_perlin_pair_kernel(float*
 // coordinate >= -1.5 and every yw >= 0.  A cell whose first corner is not >= (1, 0) (the first lattice column) recomputes
 // its six wrapped coordinates with the scalar kernel's own code.
 constexpr int PSR_ROWS = 289;
-constexpr int PSR_SMEM = PSR_ROWS * 256;
 constexpr float PSR_PERX = 1010.0f, PSR_PERY = 102.0f;
+// The INNER hash h1 = permute(xw + yw/2) is a function of the half-integer k/2 = xw + yw/2 alone, k in [-3, 2122): a second
+// table, T1[k + 3] = (h1 + 145) * 256 (the T2 row offset), takes five f32x2 instructions per corner off the FP32 pipe, which
+// bounds this kernel.  Lookups are random, so the table is stored 8 times, word (k + 3) * 8 + (lane & 7): lanes of different
+// residue never share a bank, the four lanes of one residue collide only when their k agree modulo 4.
+constexpr int PSR_T1_ENTRIES = 2128, PSR_T1_COPIES = 8;
+constexpr int PSR_OFF_T1 = PSR_ROWS * 256;
+constexpr int PSR_SMEM = PSR_OFF_T1 + PSR_T1_ENTRIES * PSR_T1_COPIES * 4;
+constexpr float MAGIC_HALF = 6291456.0f;                                 // 1.5 * 2^22: ulp 0.5, so k = 2 (xw + yw/2) sits in the mantissa
+constexpr uint32_t MAGIC_HALF_SHL5 = (uint32_t)(0x4AC00000ull << 5);
 
 __device__ __forceinline__ float2 psr_rotated_gradient(float p, float rot) {     // rotated_gradient() of noise_kernels.cu
     float u = fmaf(p, 0.0243902439f, rot);
@@ -471,6 +479,14 @@ __device__ void build_psr_table(float rot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int r = warp; r < PSR_ROWS; r += nwarps)
         *reinterpret_cast<float2*>(sm + r * 256 + lane * 8) = psr_rotated_gradient((float)permute_int(r - 145), rot);
+    for (int i = threadIdx.x; i < PSR_T1_ENTRIES * PSR_T1_COPIES; i += blockDim.x) {
+        // permute_centered() of noise_kernels.cu on the half-integer (k - 3) / 2, operation for operation
+        const float x = (float)((i / PSR_T1_COPIES) - 3) * 0.5f;
+        const float u = fmaf(34.0f, x, 1.0f) * x;
+        const float q = fmaf(u, 1.0f / 289.0f, MAGIC) - MAGIC;
+        const float h1 = fmaf(-289.0f, q, u);
+        *reinterpret_cast<uint32_t*>(sm + PSR_OFF_T1 + i * 4) = (uint32_t)(((int)h1 + 145) * 256);
+    }
     __syncthreads();
 }
 __device__ __forceinline__ float2 lds_psr(uint32_t off) { return *reinterpret_cast<const float2*>(sm + off); }
@@ -507,17 +523,13 @@ __device__ __forceinline__ P psr_fmod_pos(P p, float per, float inv_per) {
     const P q = padd(pfma(p, bc(inv_per), bc(MAGIC)), bc(-MAGIC));
     return psr_wrap_lo(pfma(bc(-per), q, p), per);
 }
-// permute_centered() of noise_kernels.cu on a pair
-__device__ __forceinline__ P ppermute_centered(P x) {
-    const P u = pmul(pfma(bc(34.0f), x, bc(1.0f)), x);
-    const P q = psub(pfma(u, bc(1.0f / 289.0f), bc(MAGIC)), bc(MAGIC));
-    return pfma(bc(-289.0f), q, u);
-}
-// gradients of one corner of both cells: (gx.x, gy.x) for cell A, (gx.y, gy.y) for cell B
-__device__ __forceinline__ void psr_grad(P xw, P yw, uint32_t c2, P& gx, P& gy) {
-    const P h1 = ppermute_centered(pfma(bc(0.5f), yw, xw));
-    const P b = padd(padd(h1, yw), bc(MAGIC));                      // (h1 + yw) as address bits
-    uint32_t uA = (__float_as_uint(b.x) << 8) + c2, uB = (__float_as_uint(b.y) << 8) + c2;
+// gradients of one corner of both cells: (gx.x, gy.x) for cell A, (gx.y, gy.y) for cell B.
+//   c1 = PSR_OFF_T1 + 3 * 32 + (lane & 7) * 4 - MAGIC_HALF_SHL5,  c2 = lane * 8 - MAGIC_SHL8
+__device__ __forceinline__ void psr_grad(P xw, P yw, uint32_t c1, uint32_t c2, P& gx, P& gy) {
+    const P kb = pfma(bc(0.5f), yw, padd(xw, bc(MAGIC_HALF)));     // (xw + yw/2) + MAGIC_HALF, exact: k in the mantissa
+    const P yb = padd(yw, bc(MAGIC));                               // yw as address bits
+    const uint32_t tA = lds_u32((__float_as_uint(kb.x) << 5) + c1), tB = lds_u32((__float_as_uint(kb.y) << 5) + c1);
+    uint32_t uA = (__float_as_uint(yb.x) << 8) + tA + c2, uB = (__float_as_uint(yb.y) << 8) + tB + c2;   // T2 row h1 + yw + 145
     uA = min(uA, uA - WRAP8);
     uB = min(uB, uB - WRAP8);
     const float2 gA = lds_psr(uA), gB = lds_psr(uB);
@@ -528,7 +540,7 @@ __device__ __forceinline__ void psr_grad(P xw, P yw, uint32_t c2, P& gx, P& gy) 
 // psrnoise2(posx, posy) for two cells that share posx; returns TWICE the basis value Rectify(psrnoise) of both.
 // Differences and selects are written in the forms that cost the fewest issue slots; each is the same exact value or the
 // same single IEEE rounding as the scalar kernel's expression (commented where it is not literal).
-__device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
+__device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c1, uint32_t c2) {
     posy = padd(posy, bc(0.001f));
     const P ux = pfma(posy, bc(0.5f), bc(posx));
     const P i0x = pfloor(ux), i0y = pfloor(posy);
@@ -568,9 +580,9 @@ __device__ __forceinline__ P psr_pair(float posx, P posy, uint32_t c2) {
         }
     }
     P g0x, g0y, g1x, g1y, g2x, g2y;
-    psr_grad(xw0, yw0, c2, g0x, g0y);
-    psr_grad(xw1, yw1, c2, g1x, g1y);
-    psr_grad(xw2, yw2, c2, g2x, g2y);
+    psr_grad(xw0, yw0, c1, c2, g0x, g0y);
+    psr_grad(xw1, yw1, c1, c2, g1x, g1y);
+    psr_grad(xw2, yw2, c1, c2, g2x, g2y);
     const P w0 = pfma(g0y, d0y, pmul(g0x, d0x)), w1 = pfma(g1y, d1y, pmul(g1x, d1x)), w2 = pfma(g2y, d2y, pmul(g2x, d2x));
     P t0 = pmax0(psubm(bc(0.8f), pfma(d0y, d0y, pmul(d0x, d0x))));
     P t1 = pmax0(psubm(bc(0.8f), pfma(d1y, d1y, pmul(d1x, d1x))));
@@ -587,8 +599,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_psr_pair_kernel(float* __
                                                                       int col_blocks, int n_items) {
     build_psr_table(rot);
     const int lane = threadIdx.x & 31;
-    uint32_t c2 = 145 * 256 + lane * 8 - MAGIC_SHL8;
-    asm volatile("" : "+r"(c2));
+    uint32_t c1 = PSR_OFF_T1 + 3 * 32 + (lane & 7) * 4 - MAGIC_HALF_SHL5, c2 = lane * 8 - MAGIC_SHL8;
+    asm volatile("" : "+r"(c1), "+r"(c2));
     const int tx = threadIdx.x & ((1 << wshift) - 1), ty = threadIdx.x >> wshift;
     const int rows_per_item = 4 * (PAIR_THREADS >> wshift);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -609,7 +621,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) fbm_psr_pair_kernel(float* __
 #pragma unroll
             const float ah = a * 0.5f;            // exact (power of two): see psr_pair
 #pragma unroll
-            for (int q = 0; q < 2; q++) t[q] = pfma(bc(ah), psr_pair(posx, pmul(bc(f), zi[q]), c2), t[q]);
+            for (int q = 0; q < 2; q++) t[q] = pfma(bc(ah), psr_pair(posx, pmul(bc(f), zi[q]), c1, c2), t[q]);
             detune += p.detune_rate;
             f *= (p.stepdown - detune);
             a *= p.G;
