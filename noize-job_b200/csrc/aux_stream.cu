@@ -41,6 +41,11 @@ bool aux_disabled() {
 
 }  // namespace
 
+static thread_local int t_grid_edges = 3;
+int grid_edges() { return t_grid_edges; }
+GridEdgesScope::GridEdgesScope(int edges) : prev(t_grid_edges) { t_grid_edges = edges; }
+GridEdgesScope::~GridEdgesScope() { t_grid_edges = prev; }
+
 int sm_count() {
     static std::atomic<int> cache[64] = {};
     int dev = 0;

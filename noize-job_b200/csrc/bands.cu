@@ -307,7 +307,9 @@ int32_t bandset_stage(BandSet& bs, int above, int below, const BandStageFn& fn) 
         float* cur = bd.buf[bd.cur] + (size_t)row0 * W;
         float* other = bd.buf[bd.cur ^ 1] + (size_t)row0 * W;
         float* result = cur;
-        rc = fn(bd, cur, other, nrows, bd.z0 - a, &result);
+        const int first = bd.z0 - a;
+        GridEdgesScope edges((first == 0 ? 1 : 0) | (first + nrows == bs.rows ? 2 : 0));
+        rc = fn(bd, cur, other, nrows, first, &result);
         if (rc != NZ_OK) return rc;
         if (result == other) bd.cur ^= 1;
         NZ_CUDA(cudaEventRecord(bd.done, bd.s));

@@ -137,4 +137,16 @@ struct DeviceOnce {
 // multiprocessor count of the CURRENT device (cached per device)
 int sm_count();
 
+// Which edges of the window a stencil launch works on are edges of the GRID (bit 0: first row, bit 1: last row).  The
+// default is both: reads beyond them clamp to the edge row (Pipeline/Tiles/TileData.cs:72-77).  A row band in the middle
+// of a larger grid (bands.cu) has neither: its first and last rows are ghost rows whose results nobody keeps, so the
+// register-walk kernels let their clamp-free interior launch run over them instead of handing 2 x 32 (filter) or 2 x 64
+// (flow map) rows of every strip to the slower border launch.  A thread-local hint, set around one stage call.
+int grid_edges();
+struct GridEdgesScope {
+    int prev;
+    explicit GridEdgesScope(int edges);
+    ~GridEdgesScope();
+};
+
 }  // namespace nz

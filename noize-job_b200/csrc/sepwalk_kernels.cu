@@ -66,7 +66,9 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     const int L1 = has_right ? (W - 1 - wx0) / VW : 31;        // lane whose element 3 is grid column W-1
     int rs = max(zc0 - R * T, 0);
     rs -= rs % KS;                                             // first input row, phase 0
-    const int r_end = min(zc1 - 1 + R * T, H - 1 + R * T);     // last (virtual) input row
+    // last (virtual) input row.  The clamp-free body never reads past the window: a chunk that ends at a window edge which
+    // is not a grid edge (row bands, grid_edges()) simply stops there, leaving the last R*T rows unwritten — they are ghost rows
+    const int r_end = min(zc1 - 1 + R * T, BORDER ? H - 1 + R * T : H - 1);
 
     auto load_row = [&](int r, float (&v)[VW]) {
         const float* g = src + (size_t)(BORDER ? min(r, H - 1) : r) * W;
@@ -270,7 +272,12 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     g.s_lo = 1; g.s_hi = 0;
     for (int k = g.ns - 1; k >= 1; k--)
         if (k * USE - HALO + STRIP <= width) { g.s_hi = k + 1; break; }
-    g.r_lo = WB; g.r_hi = rows - WB;
+    // a window edge that is not a grid edge (a row band of a larger grid: grid_edges()) needs no clamp: the interior
+    // launch runs over it (what it computes within R*T rows of that edge is garbage, as the clamped values would be for the
+    // band: those are ghost rows)
+    const int edges = grid_edges();
+    g.r_lo = (edges & 1) ? WB : 0;
+    g.r_hi = (edges & 2) ? rows - WB : rows;
     if (g.s_hi <= g.s_lo || g.r_hi - g.r_lo < 32) { g.s_lo = g.s_hi = 0; g.r_lo = g.r_hi = rows; }
     g.zcb = WB;
     g.n_top = g.ns * cdiv(g.r_lo, g.zcb);

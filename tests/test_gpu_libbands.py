@@ -253,3 +253,16 @@ def test_library_nccl_halo_exchange_equals_single_band_bitwise(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_nccl_worker, args=(world, port, 1024, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok_{r}").exists() for r in range(world))
+
+
+def test_large_bands_with_edge_free_interior_launches_equal_single_band_bitwise(nz):
+    """Bands large enough for the register-walk kernels (filter >= 8M cells, flow map > 4M cells per window): a band whose
+    window edge is not a grid edge lets the clamp-free interior launch run over it (grid_edges() hint in nz_common.cuh).
+    Three bands of a 6144^2 grid at the C5 iteration counts: the middle band has no grid edge at all."""
+    kw = dict(N=6144, noise_size=1700, filter_iterations=17, flow_iterations=5, erosion_iterations=5)
+    (h1, v1, i1), _ = _run(None, **kw)
+    (h, v, i), halo = _run(_devices(3), **kw)
+    assert np.array_equal(h, h1), "heightmap differs from the single band"
+    assert np.array_equal(v.view(np.uint32), v1.view(np.uint32)) and np.array_equal(i, i1)
+    (h, v, i), _ = _run(_devices(2), "recompute", **kw)
+    assert np.array_equal(h, h1) and np.array_equal(v.view(np.uint32), v1.view(np.uint32)) and np.array_equal(i, i1)
