@@ -51,10 +51,37 @@ __device__ __forceinline__ float4 ld_shared_f4(unsigned smem_addr) {
     return v;
 }
 
+// ---- bulk-copy (TMA engine) row feed, measured alternative to the per-lane cp.async feed (NZ_WALK_FEED=bulk) ----
+// One elected lane issues cp.async.bulk (SASS: UBLKCP) of the warp's 512-byte row segment into the ring slot and the copy
+// completes on an mbarrier of that slot; every lane then waits for the slot's phase before it reads its 16 bytes.  The
+// ring becomes warp-shared, so the lanes must have finished reading a slot (__syncwarp) before lane 0 refills it.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 // BORDER = false is the steady-state body for warps whose strip and chunk touch no grid border: no clamp logic.
-template <int R, int T, bool SCALE, bool BORDER, int PFR>
+// BULK (interior body only): rows arrive by cp.async.bulk + mbarrier instead of per-lane cp.async (see above).
+template <int R, int T, bool SCALE, bool BORDER, int PFR, bool BULK = false>
 __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor,
-                                          const TapsW<R>& kx, const TapsW<R>& kz, int wx0, int zc0, int zc1, unsigned ring_base) {
+                                          const TapsW<R>& kx, const TapsW<R>& kz, int wx0, int zc0, int zc1, unsigned ring_base,
+                                          unsigned bar_base = 0) {
     constexpr int KS = 2 * R + 1;
     constexpr int HALO = (R * T + 3) & ~3;       // multiple of 4: strips and their useful part start on a lane boundary
     constexpr int USE = STRIP - 2 * HALO;
@@ -91,6 +118,22 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     const unsigned ring_lane = ring_base + (unsigned)(lane * VW * sizeof(float));   // shared-space byte address
     if (BORDER) {
         load_row(rs, nxt);
+    } else if (BULK) {
+        if (lane == 0) {
+#pragma unroll 1
+            for (int j = 0; j < PFR; j++) mbar_init(bar_base + j * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll 1
+            for (int j = 0; j < PFR - 1; j++)
+                if (rs + j <= r_end) {
+                    const unsigned slot = (rs + j) & (PFR - 1);
+                    mbar_expect_tx(bar_base + slot * 8, STRIP * 4);
+                    bulk_load(ring_base + slot * (STRIP * 4), src + (size_t)(rs + j) * W + wx0, STRIP * 4, bar_base + slot * 8);
+                }
+        }
     } else {
 #pragma unroll 1
         for (int j = 0; j < PFR - 1; j++) {
@@ -111,6 +154,17 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
 #pragma unroll
                     for (int q = 0; q < VW; q++) v[q] = nxt[q];
                     if (r0 < r_end) load_row(r0 + 1, nxt);
+                } else if (BULK) {
+                    const int ra = r0 + PFR - 1;                     // row requested now; its slot held row r0 - 1, read last step
+                    __syncwarp();
+                    if (lane == 0 && ra <= r_end) {
+                        const unsigned slot = ra & (PFR - 1);
+                        mbar_expect_tx(bar_base + slot * 8, STRIP * 4);
+                        bulk_load(ring_base + slot * (STRIP * 4), src + (size_t)ra * W + wx0, STRIP * 4, bar_base + slot * 8);
+                    }
+                    mbar_wait(bar_base + (r0 & (PFR - 1)) * 8, (unsigned)(((r0 - rs) / PFR) & 1));
+                    const float4 t4 = ld_shared_f4(ring_lane + (r0 & (PFR - 1)) * (STRIP * 4));
+                    v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
                 } else {
                     const int ra = r0 + PFR - 1;                     // row requested now, consumed PFR-1 steps later
                     if (ra <= r_end) cp_async16(ring_lane + (ra & (PFR - 1)) * (STRIP * 4), src + (size_t)ra * W + gx);
@@ -205,7 +259,7 @@ struct WalkRanges {
     int n_top, n_bot, n_items;    //   all strips x [0, r_lo), all strips x [r_hi, H), border strips x [r_lo, r_hi)
 };
 
-template <int R, int T, bool SCALE, int PFR>
+template <int R, int T, bool SCALE, int PFR, bool BULK = false>
 __global__ void __launch_bounds__(WALK_WARPS * 32, 5)
 sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz,
                 int zc, WalkRanges g) {
@@ -216,9 +270,10 @@ sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, i
     const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
     const int zc0 = g.r_lo + blockIdx.y * zc, zc1 = min(zc0 + zc, g.r_hi);
     // the host chose the ranges so that the strip lies inside the grid and so does the chunk with its warm-up and drain rows
-    extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP]
+    extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP] (+ [WALK_WARPS][PFR] mbarriers for the bulk feed)
     const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (PFR * STRIP));
-    walk_body<R, T, SCALE, false, PFR>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+    const unsigned bar_base = (unsigned)__cvta_generic_to_shared(ring + WALK_WARPS * PFR * STRIP) + (threadIdx.x >> 5) * (PFR * 8);
+    walk_body<R, T, SCALE, false, PFR, BULK>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base, bar_base);
 }
 
 template <int R, int T, bool SCALE>
@@ -329,7 +384,13 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
             NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, SC, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         sep_walk_kernel<R, T, SC, PF><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);  \
     } while (0)
-    if (factor == 1.0f) {
+    // NZ_WALK_FEED=bulk: the bulk-copy (TMA engine) row feed, kept as a MEASURED alternative (profiles/r2_walk_feed_scan.txt)
+    const char* ef = getenv("NZ_WALK_FEED");
+    if (ef && ef[0] == 'b' && factor == 1.0f) {
+        const size_t sm = (size_t)WALK_WARPS * 16 * STRIP * sizeof(float) + (size_t)WALK_WARPS * 16 * 8;
+        NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        sep_walk_kernel<R, T, false, 16, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+    } else if (factor == 1.0f) {
         if (pfr == 8) NZ_WALK_LAUNCH(false, 8);
         else if (pfr == 32) NZ_WALK_LAUNCH(false, 32);
         else NZ_WALK_LAUNCH(false, 16);

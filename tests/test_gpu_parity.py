@@ -728,3 +728,17 @@ def test_flow_group_strips_equal_wavefront_kernel_bitwise(nz, oracle, torch_cuda
     torch.cuda.synchronize()
     assert torch.equal(reg, wave)
     assert nz.device.flow_walk_reruns() == before
+
+
+@pytest.mark.parametrize("rows,width,ftype,iters", [(700, 600, 2, 17), (1300, 1000, 3, 7), (513, 472, 6, 4), (2200, 4096, 2, 17)])
+def test_bulk_copy_row_feed_equals_cp_async_feed_bitwise(nz, torch_cuda, monkeypatch, rows, width, ftype, iters):
+    """NZ_WALK_FEED=bulk: the separable walk fed by cp.async.bulk + mbarrier (the TMA engine, SASS UBLKCP) instead of per-lane
+    cp.async — a measured alternative (profiles/r2_walk_feed_scan.txt); same arithmetic, so the same bits."""
+    torch = torch_cuda
+    a = torch.from_numpy(rand_grid(rows, width)).cuda()
+    monkeypatch.setenv("NZ_SEP_PATH", "walk")
+    ref = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    monkeypatch.setenv("NZ_WALK_FEED", "bulk")
+    bulk = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(bulk, ref)
