@@ -162,7 +162,8 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
                         mbar_expect_tx(bar_base + slot * 8, STRIP * 4);
                         bulk_load(ring_base + slot * (STRIP * 4), src + (size_t)ra * W + wx0, STRIP * 4, bar_base + slot * 8);
                     }
-                    mbar_wait(bar_base + (r0 & (PFR - 1)) * 8, (unsigned)(((r0 - rs) / PFR) & 1));
+                    // (the up to KS-1 surplus steps past r_end have no row in flight: nothing to wait for)
+                    if (r0 <= r_end) mbar_wait(bar_base + (r0 & (PFR - 1)) * 8, (unsigned)(((r0 - rs) / PFR) & 1));
                     const float4 t4 = ld_shared_f4(ring_lane + (r0 & (PFR - 1)) * (STRIP * 4));
                     v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
                 } else {
