@@ -201,7 +201,11 @@ int32_t launch_flowmap(float* d_height, float* d_tmp, void* d_scratch, int width
 // PERSISTING flow fields, then erodes the heights by erosive_factor x the normalised velocity magnitude.  The heights
 // change between cycles and the flows carry over, so the cycles run on the per-iteration kernels with water + 4 flows in
 // d_scratch (5 fields).  The erosion of cycle n reads only the flows, so it may update the heights in place.
-size_t subtractive_flow_scratch_bytes(int width, int rows) { return (size_t)width * rows * sizeof(float) * 5; }
+// Fused form (NZ_SUBFLOW_PATH=unfused turns it off): up to 5 cycles on widths that are a multiple of 4 run ONE launch per
+// cycle (launch_flow_tile_cycle, flowtile_kernels.cu): the cycle's n + 1 iterations stay in an SM-resident tile, the flow
+// fields are read once and written once per cycle (two sets of 4 planes, ping-pong) and the erosion is the tile's epilogue
+// into a second height buffer: 9 fields of scratch, 40 B/cell/CYCLE of HBM traffic instead of ~44 B/cell/ITERATION.
+size_t subtractive_flow_scratch_bytes(int width, int rows) { return (size_t)width * rows * sizeof(float) * ((width & 3) == 0 ? 9 : 5); }
 
 int32_t launch_subtractive_flow_erosion(float* d_height, void* d_scratch, int width, int rows, int erosive_iterations,
                                         float erosive_factor, float norm_min, float norm_max, cudaStream_t s) {
@@ -212,6 +216,28 @@ int32_t launch_subtractive_flow_erosion(float* d_height, void* d_scratch, int wi
     const size_t n = (size_t)width * rows;
     const float norm_range = norm_max - norm_min;
     float* sc = (float*)d_scratch;
+    {
+        const char* e = getenv("NZ_SUBFLOW_PATH");
+        const bool fused = !(e && e[0] == 'u') && erosive_iterations <= 5 && (width & 3) == 0 &&
+                           (((uintptr_t)d_height | (uintptr_t)d_scratch) & 15) == 0;
+        if (fused) {
+            float* fA = sc;              // 4 planes
+            float* fB = sc + 4 * n;      // 4 planes
+            float* hcur = d_height;
+            float* hnext = sc + 8 * n;
+            const float* fin = nullptr;  // zero before the first cycle
+            float* fout = fA;
+            for (int c = 0; c < erosive_iterations; c++) {
+                int32_t rc = launch_flow_tile_cycle(hcur, hnext, fin, fout, n, width, rows, c + 1, norm_min, norm_max, erosive_factor, s);
+                if (rc != NZ_OK) return rc;
+                float* t = hcur; hcur = hnext; hnext = t;
+                fin = fout;
+                fout = fout == fA ? fB : fA;
+            }
+            if (hcur != d_height) NZ_CUDA(cudaMemcpyAsync(d_height, hcur, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            return NZ_OK;
+        }
+    }
     FlowFields f = {sc, sc + n, sc + 2 * n, sc + 3 * n, sc + 4 * n};
     dim3 grid(cdiv(width, TX), rows);
     for (int c = 0; c < erosive_iterations; c++) {

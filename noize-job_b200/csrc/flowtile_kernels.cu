@@ -38,6 +38,12 @@ struct TileParams {
     int hx, hz;        // halo columns (2I rounded up to 4) and rows (2I)
     float nmin, nrange, nsign;
     int zero_ok;
+    // CYCLE form (one cycle of the subtractive-flow erosion, launch_flow_tile_cycle): the outflows come from fin (null: all
+    // zero, the first cycle) instead of starting at zero, the final outflows of the tile's interior go to fout, and the
+    // output is the eroded height  h - factor * normalised velocity  instead of the normalised velocity
+    const float* fin[4];
+    float* fout[4];
+    float factor;
 };
 
 struct F4 {
@@ -74,7 +80,7 @@ __device__ __forceinline__ void flow_cell(float H0, float HW, float HE, float HS
 
 // One tile.  BORDER = false is the body for tiles that contain no grid border (the great majority): no clamp selects,
 // no load guards.
-template <int I, bool BORDER>
+template <int I, bool BORDER, bool CYCLE = false>
 __device__ __forceinline__ void flow_tile_body(const TileParams& p, float* const pW, float* const pE, float* const pS,
                                                float* const pN, float* const pH, int warp, int col, int x0, int z0) {
         const int gx = x0 + col;
@@ -111,7 +117,22 @@ __device__ __forceinline__ void flow_tile_body(const TileParams& p, float* const
                 HN = lds4(pH + min(r + 1, TH - 1) * TW + col);
                 if (BORDER && gz == 0) HS = H0;
                 if (BORDER && gz == p.H - 1) HN = H0;
-                if (t == 0) {
+                if (t == 0 && CYCLE && p.fin[0]) {
+                    // the flow fields persist across the cycles of the subtractive-flow erosion: this cycle starts from them
+                    const bool in = !BORDER || (gz >= 0 && gz < p.H && gx >= 0 && gx + 3 < p.W);
+                    float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a, c = a, d = a;
+                    if (in) {
+                        const size_t gi = (size_t)gz * p.W + gx;
+                        a = __ldg(reinterpret_cast<const float4*>(p.fin[0] + gi));
+                        b = __ldg(reinterpret_cast<const float4*>(p.fin[1] + gi));
+                        c = __ldg(reinterpret_cast<const float4*>(p.fin[2] + gi));
+                        d = __ldg(reinterpret_cast<const float4*>(p.fin[3] + gi));
+                    }
+                    fW.v[0] = a.x; fW.v[1] = a.y; fW.v[2] = a.z; fW.v[3] = a.w;
+                    fE.v[0] = b.x; fE.v[1] = b.y; fE.v[2] = b.z; fE.v[3] = b.w;
+                    fS.v[0] = c.x; fS.v[1] = c.y; fS.v[2] = c.z; fS.v[3] = c.w;
+                    fN.v[0] = d.x; fN.v[1] = d.y; fN.v[2] = d.z; fN.v[3] = d.w;
+                } else if (t == 0) {
 #pragma unroll
                     for (int q = 0; q < 4; q++) fW.v[q] = fE.v[q] = fS.v[q] = fN.v[q] = 0.0f;
                 } else {
@@ -178,13 +199,23 @@ __device__ __forceinline__ void flow_tile_body(const TileParams& p, float* const
                 if (p.nrange < 1e-12f) v = 0.0f;
                 const float tt = v - p.nmin;
                 res.v[q] = (tt == 0.0f && p.zero_ok) ? tt * p.nsign : tt / p.nrange;
+                // ConstantMultiply then SubtractTiles (ErosionStageSubtractiveFlow.cs:196-222): one rounding each
+                if (CYCLE) res.v[q] = h[g][q] - res.v[q] * p.factor;
             }
-            if (col >= p.hx && col < TW - p.hx && (!BORDER || (gx >= 0 && gx + 3 < p.W)))
-                *reinterpret_cast<float4*>(p.out + (size_t)gz * p.W + gx) = make_float4(res.v[0], res.v[1], res.v[2], res.v[3]);
+            if (col >= p.hx && col < TW - p.hx && (!BORDER || (gx >= 0 && gx + 3 < p.W))) {
+                const size_t gi = (size_t)gz * p.W + gx;
+                *reinterpret_cast<float4*>(p.out + gi) = make_float4(res.v[0], res.v[1], res.v[2], res.v[3]);
+                if (CYCLE) {
+                    *reinterpret_cast<float4*>(p.fout[0] + gi) = make_float4(fW.v[0], fW.v[1], fW.v[2], fW.v[3]);
+                    *reinterpret_cast<float4*>(p.fout[1] + gi) = make_float4(fE.v[0], fE.v[1], fE.v[2], fE.v[3]);
+                    *reinterpret_cast<float4*>(p.fout[2] + gi) = make_float4(fS.v[0], fS.v[1], fS.v[2], fS.v[3]);
+                    *reinterpret_cast<float4*>(p.fout[3] + gi) = make_float4(fN.v[0], fN.v[1], fN.v[2], fN.v[3]);
+                }
+            }
         }
 }
 
-template <int I>
+template <int I, bool CYCLE = false>
 __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) {
     extern __shared__ __align__(16) float sm[];
     float* const pW = sm;
@@ -202,9 +233,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) 
         // the tile's cells lie strictly inside the grid: no cell has a missing neighbour
         const bool inside = x0 > 0 && z0 > 0 && x0 + TW < p.W && z0 + TH < p.H;
         if (inside)
-            flow_tile_body<I, false>(p, pW, pE, pS, pN, pH, warp, col, x0, z0);
+            flow_tile_body<I, false, CYCLE>(p, pW, pE, pS, pN, pH, warp, col, x0, z0);
         else
-            flow_tile_body<I, true>(p, pW, pE, pS, pN, pH, warp, col, x0, z0);
+            flow_tile_body<I, true, CYCLE>(p, pW, pE, pS, pN, pH, warp, col, x0, z0);
     }
 }
 
@@ -212,6 +243,56 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flow_tile_kernel(TileParams p) 
 
 bool flow_tile_supported(int width, int rows, int iterations, const void* a, const void* b) {
     return iterations >= 1 && iterations <= 5 && (width & 3) == 0 && rows >= 1 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
+static TileParams tile_params(const float* d_height, float* d_out, int width, int rows, int I, float norm_min, float norm_max) {
+    TileParams p;
+    p.h = d_height; p.out = d_out; p.W = width; p.H = rows;
+    p.hz = 2 * I;
+    p.hx = (2 * I + 3) & ~3;
+    p.tiles_x = cdiv(width, TW - 2 * p.hx);
+    p.n_tiles = p.tiles_x * cdiv(rows, TH - 2 * p.hz);
+    p.nmin = norm_min;
+    p.nrange = norm_max - norm_min;
+    p.nsign = copysignf(1.0f, p.nrange);
+    p.zero_ok = (p.nrange != 0.0f) && isfinite(p.nrange);
+    for (int k = 0; k < 4; k++) { p.fin[k] = nullptr; p.fout[k] = nullptr; }
+    p.factor = 0.0f;
+    return p;
+}
+
+// One cycle of the subtractive-flow erosion, fused (ErosionStageSubtractiveFlow.ScheduleCycle, :138-222): water := 1e-4,
+// `iterations` x (outflow, water) starting from the outflow fields d_fin (4 planes; null: all zero), the final outflows to
+// d_fout (4 planes), and d_out = d_height - factor * normalised |velocity|.  Nothing may alias: neighbouring tiles read the
+// halo of the inputs while others write their interiors.  1 <= iterations <= 5.
+int32_t launch_flow_tile_cycle(const float* d_height, float* d_out, const float* d_fin, float* d_fout, size_t plane, int width, int rows,
+                               int iterations, float norm_min, float norm_max, float factor, cudaStream_t s) {
+    static DeviceOnce attr_set;
+    if (attr_set.need()) {
+        NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+        NZ_CUDA(cudaFuncSetAttribute(flow_tile_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+        attr_set.mark();
+    }
+    TileParams p = tile_params(d_height, d_out, width, rows, iterations, norm_min, norm_max);
+    for (int k = 0; k < 4; k++) {
+        p.fin[k] = d_fin ? d_fin + k * plane : nullptr;
+        p.fout[k] = d_fout + k * plane;
+    }
+    p.factor = factor;
+    const int sms = sm_count();
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    switch (iterations) {
+        case 1: flow_tile_kernel<1, true><<<grid, FT_THREADS, FT_SMEM, s>>>(p); break;
+        case 2: flow_tile_kernel<2, true><<<grid, FT_THREADS, FT_SMEM, s>>>(p); break;
+        case 3: flow_tile_kernel<3, true><<<grid, FT_THREADS, FT_SMEM, s>>>(p); break;
+        case 4: flow_tile_kernel<4, true><<<grid, FT_THREADS, FT_SMEM, s>>>(p); break;
+        default: flow_tile_kernel<5, true><<<grid, FT_THREADS, FT_SMEM, s>>>(p); break;
+    }
+    NZ_LAUNCHED();
+    return NZ_OK;
 }
 
 // d_out must not alias d_height
@@ -227,16 +308,7 @@ int32_t launch_flow_tile(const float* d_height, float* d_out, int width, int row
         attr_set.mark();
     }
     const int I = iterations;
-    TileParams p;
-    p.h = d_height; p.out = d_out; p.W = width; p.H = rows;
-    p.hz = 2 * I;
-    p.hx = (2 * I + 3) & ~3;
-    p.tiles_x = cdiv(width, TW - 2 * p.hx);
-    p.n_tiles = p.tiles_x * cdiv(rows, TH - 2 * p.hz);
-    p.nmin = norm_min;
-    p.nrange = norm_max - norm_min;
-    p.nsign = copysignf(1.0f, p.nrange);
-    p.zero_ok = (p.nrange != 0.0f) && isfinite(p.nrange);
+    TileParams p = tile_params(d_height, d_out, width, rows, I, norm_min, norm_max);
     const int sms = sm_count();
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     switch (I) {

@@ -92,6 +92,8 @@ int32_t launch_flow_walk(const float* d_height, float* d_out, int width, int row
 bool flow_tile_supported(int width, int rows, int iterations, const void* a, const void* b);
 int32_t launch_flow_tile(const float* d_height, float* d_out, int width, int rows, int iterations, float norm_min,
                          float norm_max, cudaStream_t s);
+int32_t launch_flow_tile_cycle(const float* d_height, float* d_out, const float* d_fin, float* d_fout, size_t plane, int width, int rows,
+                               int iterations, float norm_min, float norm_max, float factor, cudaStream_t s);
 int32_t launch_mesh(int mesh_type, void* d_vtx, uint32_t* d_idx, int R, int inRes, float tile_height,
                     float tile_size, const float* d_heights, int h_row_first, int h_rows, int vz_begin, int vz_end,
                     cudaStream_t s);

@@ -167,3 +167,22 @@ def test_subtractive_flow_erosion_stage_and_device_layer(nz, oracle):
     assert np.array_equal(bits(t.cpu().numpy()), bits(oracle.subtractive_flow_erosion(r, 3, 0.1, 0.0, 0.5)))
     with pytest.raises(nz.NzError):
         nz.host.subtractive_flow_erosion(data, res, -1, 0.1, 0.0, 0.005)
+
+
+@pytest.mark.parametrize("rows,width,cycles", [(700, 1000, 3), (300, 2048, 5), (257, 132, 2), (600, 600, 6)])
+def test_subtractive_flow_fused_cycles_equal_per_iteration_kernels_bitwise(nz, oracle, monkeypatch, rows, width, cycles):
+    """One launch per cycle on the SM-resident tile kernel (flows read and written once per cycle, erosion as the tile's
+    epilogue) against the per-iteration HBM kernels, over many tiles, tile seams and grid borders; 6 cycles exceed the fused
+    form's 5 iterations and take the per-iteration path either way."""
+    import torch
+    r = np.random.default_rng(11).random((rows, width), dtype=np.float32) * np.float32(0.2)
+    monkeypatch.setenv("NZ_SUBFLOW_PATH", "unfused")
+    a = torch.from_numpy(r).cuda()
+    nz.device.subtractive_flow_erosion(a, cycles, 0.1, 0.0, 0.05)
+    monkeypatch.delenv("NZ_SUBFLOW_PATH")
+    b = torch.from_numpy(r).cuda()
+    nz.device.subtractive_flow_erosion(b, cycles, 0.1, 0.0, 0.05)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    if rows * width <= 300000:
+        assert np.array_equal(bits(b.cpu().numpy()), bits(oracle.subtractive_flow_erosion(r, cycles, 0.1, 0.0, 0.05)))
