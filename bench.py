@@ -408,6 +408,7 @@ def time_small(env, fn, steps, warmup, sync_all=False):
     tot = 0.0
     for _ in range(steps):
         env.flush_l2()
+        torch.cuda.synchronize()          # the timed work may run on streams of its own: the flush must be over
         if sync_all:
             env.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -428,20 +429,15 @@ def run_small_config(env, name, steps, warmup):
         from noize_job_b200 import tiles
         cfg = tiles.TileWorldConfig()
         slots = 4
-        tw = tiles.TileWorld(cfg, tiles.TileCudaEngine(slots), env.rank, env.world, slots=slots)
-        cur = torch.cuda.current_stream()
-
-        def fn():
-            for s in tw.eng.streams:
-                s.wait_stream(cur)
-            tw.run()
-            for s in tw.eng.streams:
-                cur.wait_stream(s)
+        # the tile loop runs inside the library (nz_tile_world_*): one C call per pass, `slots` tiles in flight
+        tw = tiles.LibTileWorld(cfg, env.rank, env.world, slots=slots)
+        fn = tw.run
         ms = time_small(env, fn, steps, warmup, sync_all=env.world > 1)
         ms = env.max_over_ranks([ms])[0]
         cells = cfg.tiles_x * cfg.tiles_z * cfg.resolution ** 2
-        extra = {"tiles": cfg.tiles_x * cfg.tiles_z, "tiles_per_gpu": len(tw.mine), "streams_per_gpu": slots}
-        del tw
+        extra = {"tiles": cfg.tiles_x * cfg.tiles_z, "tiles_per_gpu": len(tw.mine), "streams_per_gpu": slots,
+                 "engine": "nz_tile_world (C ABI)"}
+        tw.release()
     else:
         ms, cells, extra = 0.0, 0, {}
         if env.rank == 0:

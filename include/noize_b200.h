@@ -375,6 +375,33 @@ NZ_API int32_t nz_band_chain_info(int64_t chain, int32_t local_band, nz_band_inf
 NZ_API int32_t nz_band_chain_download(int64_t chain, float* h_heights, void* h_vertices, uint32_t* h_indices);
 NZ_API int32_t nz_band_chain_destroy(int64_t chain);
 
+/* ---- tiled worlds: several tiles in flight on one GPU ------------------------------------------------------------------- */
+/* The reference generates a world tile by tile, ONE tile in flight: MeshTileGenerator hands tile (tx, tz) to the generator
+ * pipeline with xpos = tileResolution * tx, zpos = tileResolution * tz (Scripts/MeshTileGenerator.cs:125-138,184-192).  A
+ * 1024^2 tile cannot fill 148 SMs, so a tile world keeps `slots` tiles in flight on separate streams and runs, per tile,
+ * the chain of BASELINE.json configs[3]: fBm noise -> separable filter x iterations -> [edge filter (e.g. Sobel3_2D) on a
+ * COPY] -> mesh.  Tiles are independent (noise is a pure function of position, every filter clamps at the tile's own border),
+ * so sharding a world over GPUs needs no communication: each process runs its own tiles. */
+typedef struct {
+    int32_t resolution;             /* generator resolution of one tile (e.g. 1024) */
+    int32_t tile_resolution;        /* world cells between tile origins (e.g. 1000: tiles overlap by resolution - tile_resolution) */
+    int32_t noise_type; float hurst, starting_amplitude, stepdown, detune_rate; int32_t octaves, noise_size;
+    int32_t filter_type, filter_iterations;
+    int32_t edge_filter_type, edge_filter_iterations;   /* on a copy of the filtered tile; 0 iterations: none */
+    int32_t mesh_type, mesh_resolution, mesh_margin_pix; float tile_height, tile_size;   /* mesh_resolution 0: no mesh */
+} nz_tile_config;
+
+NZ_API int64_t nz_tile_world_create(const nz_tile_config* cfg, int32_t device, int32_t slots);
+/* Runs the chain for n tiles, tiles_xz = {tx0, tz0, tx1, tz1, ...}.  Host outputs are per-tile arrays laid out tile after
+ * tile (resolution^2 floats of heights / edges, (R+1)^2 * 48 bytes of vertices, 6 R^2 indices); any of them may be NULL, in
+ * which case that output stays in the slot's device buffers and is overwritten by the slot's next tile.  Synchronises. */
+NZ_API int32_t nz_tile_world_run(int64_t world, const int32_t* tiles_xz, int32_t n, float* h_heights, float* h_edges,
+                                 void* h_vertices, uint32_t* h_indices);
+/* DEVICE pointers of the last tile a slot ran (heights, edges, vertices, indices), for tests and device-resident consumers */
+NZ_API int32_t nz_tile_world_slot(int64_t world, int32_t slot, float** d_heights, float** d_edges, void** d_vertices,
+                                  uint32_t** d_indices);
+NZ_API int32_t nz_tile_world_destroy(int64_t world);
+
 /* ---- device layer ------------------------------------------------------------------- */
 /* All pointers are DEVICE pointers unless named h_*. `stream` is a cudaStream_t (NULL = legacy
  * default stream).  Grids are width x rows, contiguous.  Calls only enqueue work.           */

@@ -868,3 +868,179 @@ NZ_API int32_t nz_band_chain_destroy(int64_t chain) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// tiled worlds: several tiles in flight on one GPU (BASELINE config C4)
+// =====================================================================================================================
+namespace nz {
+namespace {
+
+struct TileSlot {
+    cudaStream_t s = nullptr;
+    float *a = nullptr, *b = nullptr, *edge = nullptr;
+    void* vtx = nullptr;
+    uint32_t* idx = nullptr;
+    float* heights = nullptr;      // which of a / b holds the last tile's filtered heights
+};
+struct TileWorld {
+    nz_tile_config cfg{};
+    int device = 0;
+    float kx[NZ_MAX_KERNEL_WIDTH], kz[NZ_MAX_KERNEL_WIDTH], factor = 1.0f;
+    int ksize = 0;
+    std::vector<TileSlot> slots;
+    std::mutex mu;
+    ~TileWorld() {
+        DeviceGuard g(device);
+        for (TileSlot& t : slots) {
+            if (t.s) cudaStreamSynchronize(t.s);
+            dev_free(t.a); dev_free(t.b); dev_free(t.edge); dev_free(t.vtx); dev_free(t.idx);
+            if (t.s) cudaStreamDestroy(t.s);
+        }
+    }
+};
+std::unordered_map<long long, std::shared_ptr<TileWorld>> g_tile_worlds;
+
+int32_t find_tile_world(long long h, std::shared_ptr<TileWorld>* out) {
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    auto it = g_tile_worlds.find(h);
+    if (it == g_tile_worlds.end()) {
+        set_error("unknown tile world handle %lld", h);
+        return NZ_E_INVALID;
+    }
+    *out = it->second;
+    return NZ_OK;
+}
+
+}  // namespace
+}  // namespace nz
+
+extern "C" {
+
+NZ_API int64_t nz_tile_world_create(const nz_tile_config* cfg, int32_t device, int32_t slots) {
+    NZ_REQUIRE(cfg, "nz_tile_world_create: null config");
+    NZ_REQUIRE(cfg->resolution > 0 && cfg->resolution <= 16384 && cfg->tile_resolution > 0, "nz_tile_world_create: bad tile resolution");
+    NZ_REQUIRE(slots >= 1 && slots <= 64, "nz_tile_world_create: slots %d out of range [1,64]", slots);
+    NZ_REQUIRE(cfg->filter_iterations >= 0 && cfg->edge_filter_iterations >= 0, "nz_tile_world_create: negative iteration count");
+    int ndev = 0;
+    NZ_CUDA(cudaGetDeviceCount(&ndev));
+    NZ_REQUIRE(device >= 0 && device < ndev, "nz_tile_world_create: device %d not visible (%d devices)", device, ndev);
+    auto w = std::make_shared<TileWorld>();
+    w->cfg = *cfg;
+    w->device = device;
+    if (cfg->filter_iterations > 0) {
+        NZ_REQUIRE(cfg->filter_type >= 0 && cfg->filter_type < NZ_FILTER__COUNT, "nz_tile_world_create: filter_type %d out of range", cfg->filter_type);
+        if (cfg->filter_type != NZ_FILTER_SOBEL3_2D) {
+            int32_t rc = kernel_filter_table(cfg->filter_type, w->kx, w->kz, &w->ksize, &w->factor);
+            if (rc != NZ_OK) return rc;
+        }
+    }
+    if (cfg->edge_filter_iterations > 0)
+        NZ_REQUIRE(cfg->edge_filter_type >= 0 && cfg->edge_filter_type < NZ_FILTER__COUNT, "nz_tile_world_create: edge_filter_type %d out of range",
+                   cfg->edge_filter_type);
+    if (cfg->mesh_resolution > 0)
+        NZ_REQUIRE(cfg->mesh_type >= 0 && cfg->mesh_type < NZ_MESH__COUNT, "nz_tile_world_create: mesh_type %d out of range", cfg->mesh_type);
+    DeviceGuard g(device);
+    const size_t n = (size_t)cfg->resolution * cfg->resolution, R = (size_t)cfg->mesh_resolution;
+    w->slots.resize(slots);
+    for (TileSlot& t : w->slots) {
+        NZ_CUDA(cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking));
+        int32_t rc = dev_alloc((void**)&t.a, n * sizeof(float));
+        if (rc == NZ_OK) rc = dev_alloc((void**)&t.b, n * sizeof(float));
+        if (rc == NZ_OK && cfg->edge_filter_iterations > 0) rc = dev_alloc((void**)&t.edge, n * sizeof(float));
+        if (rc == NZ_OK && R > 0) rc = dev_alloc(&t.vtx, (R + 1) * (R + 1) * NZ_MESH_VERTEX_BYTES);
+        if (rc == NZ_OK && R > 0) rc = dev_alloc((void**)&t.idx, 6 * R * R * sizeof(uint32_t));
+        if (rc != NZ_OK) return rc;          // ~TileWorld frees what was allocated
+    }
+    std::lock_guard<std::mutex> lk(g_handles_mu);
+    const long long h = g_next_handle++;
+    g_tile_worlds[h] = w;
+    return h;
+}
+
+NZ_API int32_t nz_tile_world_run(int64_t world, const int32_t* tiles_xz, int32_t n, float* h_heights, float* h_edges,
+                                 void* h_vertices, uint32_t* h_indices) {
+    NZ_REQUIRE(n >= 0 && (tiles_xz || n == 0), "nz_tile_world_run: bad tile list");
+    std::shared_ptr<TileWorld> w;
+    int32_t rc = find_tile_world(world, &w);
+    if (rc != NZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(w->mu);
+    const nz_tile_config& c = w->cfg;
+    NZ_REQUIRE(!h_edges || c.edge_filter_iterations > 0, "nz_tile_world_run: this world has no edge filter");
+    NZ_REQUIRE((!h_vertices && !h_indices) || c.mesh_resolution > 0, "nz_tile_world_run: this world has no mesh");
+    DeviceGuard g(w->device);
+    Range rg("nz.tile_world");
+    const int res = c.resolution, R = c.mesh_resolution;
+    const size_t cells = (size_t)res * res;
+    const size_t vbytes = (size_t)(R + 1) * (R + 1) * NZ_MESH_VERTEX_BYTES, icount = (size_t)6 * R * R;
+    for (int k = 0; k < n; k++) {
+        TileSlot& t = w->slots[k % w->slots.size()];       // stream order makes the slot's reuse safe
+        const int tx = tiles_xz[2 * k], tz = tiles_xz[2 * k + 1];
+        FractalParams p;
+        // tile -> noise domain: xpos = tileResolution * tx, zpos = tileResolution * tz (MeshTileGenerator.cs:188-189)
+        rc = fractal_params(&p, res, res, 0, c.noise_type, c.hurst, c.starting_amplitude, c.stepdown, c.detune_rate, c.octaves,
+                            c.tile_resolution * tx, c.tile_resolution * tz, c.noise_size);
+        if (rc == NZ_OK) rc = launch_fractal(t.a, c.noise_type, p, t.s);
+        float* cur = t.a;
+        if (rc == NZ_OK && c.filter_iterations > 0)
+            rc = c.filter_type == NZ_FILTER_SOBEL3_2D ? launch_sobel2d(t.a, t.b, res, res, c.filter_iterations, &cur, t.s)
+                                                      : launch_separable(t.a, t.b, res, res, w->ksize, w->kx, w->kz, w->factor, c.filter_iterations, &cur, t.s);
+        if (rc != NZ_OK) return rc;
+        float* other = cur == t.a ? t.b : t.a;
+        float* edges = nullptr;
+        if (c.edge_filter_iterations > 0) {
+            NZ_CUDA(cudaMemcpyAsync(t.edge, cur, cells * sizeof(float), cudaMemcpyDeviceToDevice, t.s));
+            if (c.edge_filter_type == NZ_FILTER_SOBEL3_2D) {
+                rc = launch_sobel2d(t.edge, other, res, res, c.edge_filter_iterations, &edges, t.s);
+            } else {
+                float ekx[9], ekz[9], ef;
+                int eks;
+                rc = kernel_filter_table(c.edge_filter_type, ekx, ekz, &eks, &ef);
+                if (rc == NZ_OK) rc = launch_separable(t.edge, other, res, res, eks, ekx, ekz, ef, c.edge_filter_iterations, &edges, t.s);
+            }
+            if (rc != NZ_OK) return rc;
+            if (edges != t.edge) {      // keep the slot's roles fixed: edges live in t.edge
+                NZ_CUDA(cudaMemcpyAsync(t.edge, edges, cells * sizeof(float), cudaMemcpyDeviceToDevice, t.s));
+                edges = t.edge;
+            }
+        }
+        if (R > 0) {
+            rc = launch_mesh(c.mesh_type, t.vtx, t.idx, R, res, c.tile_height, c.tile_size, cur, 0, res, 0, R + 1, t.s);
+            if (rc != NZ_OK) return rc;
+        }
+        t.heights = cur;
+        if (h_heights) NZ_CUDA(cudaMemcpyAsync(h_heights + (size_t)k * cells, cur, cells * sizeof(float), cudaMemcpyDeviceToHost, t.s));
+        if (h_edges) NZ_CUDA(cudaMemcpyAsync(h_edges + (size_t)k * cells, edges, cells * sizeof(float), cudaMemcpyDeviceToHost, t.s));
+        if (h_vertices) NZ_CUDA(cudaMemcpyAsync((char*)h_vertices + (size_t)k * vbytes, t.vtx, vbytes, cudaMemcpyDeviceToHost, t.s));
+        if (h_indices) NZ_CUDA(cudaMemcpyAsync(h_indices + (size_t)k * icount, t.idx, icount * sizeof(uint32_t), cudaMemcpyDeviceToHost, t.s));
+    }
+    for (TileSlot& t : w->slots) NZ_CUDA(cudaStreamSynchronize(t.s));
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_tile_world_slot(int64_t world, int32_t slot, float** d_heights, float** d_edges, void** d_vertices, uint32_t** d_indices) {
+    std::shared_ptr<TileWorld> w;
+    int32_t rc = find_tile_world(world, &w);
+    if (rc != NZ_OK) return rc;
+    std::lock_guard<std::mutex> lk(w->mu);
+    NZ_REQUIRE(slot >= 0 && slot < (int)w->slots.size(), "nz_tile_world_slot: slot %d out of range", slot);
+    const TileSlot& t = w->slots[slot];
+    if (d_heights) *d_heights = t.heights;
+    if (d_edges) *d_edges = t.edge;
+    if (d_vertices) *d_vertices = t.vtx;
+    if (d_indices) *d_indices = t.idx;
+    return NZ_OK;
+}
+
+NZ_API int32_t nz_tile_world_destroy(int64_t world) {
+    std::shared_ptr<TileWorld> w;
+    {
+        std::lock_guard<std::mutex> lk(g_handles_mu);
+        auto it = g_tile_worlds.find(world);
+        NZ_REQUIRE(it != g_tile_worlds.end(), "nz_tile_world_destroy: unknown tile world handle %lld", (long long)world);
+        w = it->second;
+        g_tile_worlds.erase(it);
+    }
+    return NZ_OK;      // the last reference frees the slots
+}
+
+}  // extern "C"

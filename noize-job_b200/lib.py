@@ -50,6 +50,17 @@ class BandInfo(C.Structure):
                 ("d_indices", C.c_void_p), ("halo_bytes_per_run", C.c_int64)]
 
 
+class TileConfig(C.Structure):
+    """nz_tile_config: the per-tile chain of a tiled world (BASELINE config C4)."""
+    _fields_ = [("resolution", C.c_int32), ("tile_resolution", C.c_int32),
+                ("noise_type", C.c_int32), ("hurst", C.c_float), ("starting_amplitude", C.c_float), ("stepdown", C.c_float),
+                ("detune_rate", C.c_float), ("octaves", C.c_int32), ("noise_size", C.c_int32),
+                ("filter_type", C.c_int32), ("filter_iterations", C.c_int32),
+                ("edge_filter_type", C.c_int32), ("edge_filter_iterations", C.c_int32),
+                ("mesh_type", C.c_int32), ("mesh_resolution", C.c_int32), ("mesh_margin_pix", C.c_int32),
+                ("tile_height", C.c_float), ("tile_size", C.c_float)]
+
+
 class Timing(C.Structure):
     _fields_ = [("ms_h2d", C.c_float), ("ms_kernel", C.c_float), ("ms_d2h", C.c_float), ("kernel_launches", C.c_int32)]
 
@@ -86,6 +97,10 @@ SIGNATURES = {
     "nz_band_chain_info": (_i32, [C.c_int64, _i32, C.POINTER(BandInfo)]),
     "nz_band_chain_download": (_i32, [C.c_int64, _vp, _vp, _vp]),
     "nz_band_chain_destroy": (_i32, [C.c_int64]),
+    "nz_tile_world_create": (C.c_int64, [C.POINTER(TileConfig), _i32, _i32]),
+    "nz_tile_world_run": (_i32, [C.c_int64, _pi32, _i32, _vp, _vp, _vp, _vp]),
+    "nz_tile_world_slot": (_i32, [C.c_int64, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "nz_tile_world_destroy": (_i32, [C.c_int64]),
     "nz_fractal_norm_value": (_f32, [_f32, _i32]),
     "nz_gauss_kernel": (_i32, [_i32, _i32, _pf32, _pi32]),
     "nz_limit_width": (_i32, [_i32]),

@@ -114,3 +114,42 @@ class TileWorld:
         if consume is not None:
             tx, tz, h, e = item
             consume(tx, tz, h, e, self.bufs[slot]["vtx"], self.bufs[slot]["idx"])
+
+
+class LibTileWorld:
+    """The same sharding with the tile loop INSIDE the library (nz_tile_world_*): one C call runs this rank's tiles, `slots`
+    of them in flight on separate streams.  The Python loop of TileWorld costs ~80 us of host time per tile (five ctypes
+    calls and a torch copy), which is what a 1024^2 tile takes on the GPU: on 8 GPUs the Python form is host-bound."""
+
+    def __init__(self, cfg, rank=0, world=1, slots=4, device=None):
+        import ctypes as C
+        import torch
+        from . import lib as _l
+        self._l, self._C, self.cfg, self.rank, self.world, self.slots = _l, C, cfg, rank, world, slots
+        self.mine = [(tx, tz) for tx, tz in cfg.tiles() if tile_owner(tx, tz, cfg, world) == rank]
+        c = _l.TileConfig(cfg.resolution, cfg.tile_resolution, cfg.noise_type, cfg.hurst, 1.0, 2.0, 0.0, cfg.octaves, cfg.noise_size,
+                          cfg.filter_type, cfg.filter_iterations, cfg.edge_filter_type, 1, cfg.mesh_type, cfg.R, cfg.mesh_margin,
+                          cfg.tile_height, cfg.tile_size)
+        dev = torch.cuda.current_device() if device is None else device
+        self.handle = int(_l.load().nz_tile_world_create(C.byref(c), dev, slots))
+        if self.handle < 0:
+            _l.check(self.handle)
+        flat = [v for t in self.mine for v in t]
+        self._tiles = (C.c_int32 * max(1, len(flat)))(*flat)
+
+    def run(self, heights=None, edges=None, vertices=None, indices=None):
+        """Runs this rank's tiles; optional HOST arrays (numpy, C-contiguous, one entry per owned tile) receive the outputs."""
+        p = lambda a: None if a is None else a.ctypes.data
+        self._l.check(self._l.load().nz_tile_world_run(self.handle, self._tiles, len(self.mine), p(heights), p(edges), p(vertices), p(indices)))
+        return len(self.mine)
+
+    def release(self):
+        if self.handle:
+            self._l.check(self._l.load().nz_tile_world_destroy(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -110,3 +110,26 @@ def test_tile_world_on_gpu_matches_oracle_tile_by_tile(nz, oracle):
         assert np.abs(e - oracle.kernel_filter(ref, 11, 1)).max() <= 2e-6
         rv, ri = oracle.heightmap_mesh(1, h, cfg.R, 4, cfg.tile_height, cfg.tile_size)
         assert np.array_equal(i, ri) and np.abs(v - rv).max() <= 1e-5 * cfg.tile_height
+
+
+def test_library_tile_world_matches_oracle_tile_by_tile(nz, oracle):
+    """nz_tile_world_*: the C4 tile loop inside the library (3 tiles in flight), outputs downloaded per tile."""
+    from noize_job_b200 import tiles
+    cfg = tiles.TileWorldConfig(tiles_x=3, tiles_z=2, resolution=256, tile_resolution=250, octaves=6, noise_size=400)
+    R = cfg.R
+    for rank in range(2):
+        tw = tiles.LibTileWorld(cfg, rank, 2, slots=3)
+        n = len(tw.mine)
+        h = np.zeros((n, 256, 256), np.float32)
+        e = np.zeros((n, 256, 256), np.float32)
+        v = np.zeros((n, (R + 1) * (R + 1), 12), np.float32)
+        i = np.zeros((n, 6 * R * R), np.uint32)
+        assert tw.run(h, e, v, i) == n
+        for k, (tx, tz) in enumerate(tw.mine):
+            ref = oracle.kernel_filter(oracle.fractal(256, 256, 4, 0.4, octaves=6, xpos=250 * tx, zpos=250 * tz, noise_size=400), 3, 3)
+            assert np.abs(h[k] - ref).max() <= 1e-6
+            assert np.abs(e[k] - oracle.kernel_filter(ref, 11, 1)).max() <= 2e-6
+            rv, ri = oracle.heightmap_mesh(1, h[k], R, 4, cfg.tile_height, cfg.tile_size)
+            assert np.array_equal(i[k], ri) and np.abs(v[k] - rv).max() <= 1e-5 * cfg.tile_height
+        tw.run()                                   # device-resident form (what the bench times)
+        tw.release()
