@@ -881,6 +881,7 @@ struct TileSlot {
     void* vtx = nullptr;
     uint32_t* idx = nullptr;
     float* heights = nullptr;      // which of a / b holds the last tile's filtered heights
+    float* edges = nullptr;        // which of edge / (the other of a, b) holds its edge map
 };
 struct TileWorld {
     nz_tile_config cfg{};
@@ -998,16 +999,13 @@ NZ_API int32_t nz_tile_world_run(int64_t world, const int32_t* tiles_xz, int32_t
                 if (rc == NZ_OK) rc = launch_separable(t.edge, other, res, res, eks, ekx, ekz, ef, c.edge_filter_iterations, &edges, t.s);
             }
             if (rc != NZ_OK) return rc;
-            if (edges != t.edge) {      // keep the slot's roles fixed: edges live in t.edge
-                NZ_CUDA(cudaMemcpyAsync(t.edge, edges, cells * sizeof(float), cudaMemcpyDeviceToDevice, t.s));
-                edges = t.edge;
-            }
         }
         if (R > 0) {
             rc = launch_mesh(c.mesh_type, t.vtx, t.idx, R, res, c.tile_height, c.tile_size, cur, 0, res, 0, R + 1, t.s);
             if (rc != NZ_OK) return rc;
         }
         t.heights = cur;
+        t.edges = edges;
         if (h_heights) NZ_CUDA(cudaMemcpyAsync(h_heights + (size_t)k * cells, cur, cells * sizeof(float), cudaMemcpyDeviceToHost, t.s));
         if (h_edges) NZ_CUDA(cudaMemcpyAsync(h_edges + (size_t)k * cells, edges, cells * sizeof(float), cudaMemcpyDeviceToHost, t.s));
         if (h_vertices) NZ_CUDA(cudaMemcpyAsync((char*)h_vertices + (size_t)k * vbytes, t.vtx, vbytes, cudaMemcpyDeviceToHost, t.s));
@@ -1025,7 +1023,7 @@ NZ_API int32_t nz_tile_world_slot(int64_t world, int32_t slot, float** d_heights
     NZ_REQUIRE(slot >= 0 && slot < (int)w->slots.size(), "nz_tile_world_slot: slot %d out of range", slot);
     const TileSlot& t = w->slots[slot];
     if (d_heights) *d_heights = t.heights;
-    if (d_edges) *d_edges = t.edge;
+    if (d_edges) *d_edges = t.edges;
     if (d_vertices) *d_vertices = t.vtx;
     if (d_indices) *d_indices = t.idx;
     return NZ_OK;
