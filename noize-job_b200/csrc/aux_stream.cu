@@ -42,7 +42,14 @@ bool aux_disabled() {
 }  // namespace
 
 static thread_local int t_grid_edges = 3;
-int grid_edges() { return t_grid_edges; }
+int grid_edges() {
+    // NZ_GRID_EDGES=0..3 overrides the hint while profiling band-sized windows on one GPU (tools/band_scan.py)
+    static const int forced = [] {
+        const char* e = getenv("NZ_GRID_EDGES");
+        return e ? atoi(e) & 3 : -1;
+    }();
+    return forced >= 0 ? forced : t_grid_edges;
+}
 GridEdgesScope::GridEdgesScope(int edges) : prev(t_grid_edges) { t_grid_edges = edges; }
 GridEdgesScope::~GridEdgesScope() { t_grid_edges = prev; }
 
