@@ -988,7 +988,12 @@ NZ_API int32_t nz_tile_world_run(int64_t world, const int32_t* tiles_xz, int32_t
         if (rc != NZ_OK) return rc;
         float* other = cur == t.a ? t.b : t.a;
         float* edges = nullptr;
-        if (c.edge_filter_iterations > 0) {
+        if (c.edge_filter_iterations == 1 && c.edge_filter_type == NZ_FILTER_SOBEL3_2D) {
+            // one Sobel3_2D pass reads its input and writes its partner: straight from the heights into the edge buffer,
+            // no copy (a D2D copy between two kernels of a 70 us tile costs a copy-engine hand-off each way)
+            rc = launch_sobel2d(cur, t.edge, res, res, 1, &edges, t.s);
+            if (rc != NZ_OK) return rc;
+        } else if (c.edge_filter_iterations > 0) {
             NZ_CUDA(cudaMemcpyAsync(t.edge, cur, cells * sizeof(float), cudaMemcpyDeviceToDevice, t.s));
             if (c.edge_filter_type == NZ_FILTER_SOBEL3_2D) {
                 rc = launch_sobel2d(t.edge, other, res, res, c.edge_filter_iterations, &edges, t.s);
