@@ -261,7 +261,7 @@ struct WalkRanges {
 };
 
 template <int R, int T, bool SCALE, int PFR, bool BULK = false>
-__global__ void __launch_bounds__(WALK_WARPS * 32, 5)
+__global__ void __launch_bounds__(WALK_WARPS * 32, (2 * R + 1) * T > 20 ? 4 : 5)    // window of (2R+1)*T*4 registers: 5 CTAs/SM up to 80, else 4
 sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz,
                 int zc, WalkRanges g) {
     constexpr int HALO = (R * T + 3) & ~3;
@@ -365,7 +365,7 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
         zc = atoi(ez);
     } else {
         const int sms = sm_count();
-        const long long slots = 5LL * sms;               // 5 CTAs of 128 threads x 96 registers per SM
+        const long long slots = ((2 * R + 1) * T > 20 ? 4LL : 5LL) * sms;   // 5 CTAs of 128 threads x 96 registers per SM (4 x 128 for the deepest windows)
         const int warm = R * T + 2 * R + 1 + 3;
         double best = 1e300;
         for (int n = cdiv(irows, 448); n <= irows; n++) {
@@ -407,7 +407,13 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
 template <int R>
 int32_t launch_walk_r(float* d_data, float* d_tmp, int width, int rows, const float* kx, const float* kz, float factor,
                       int iterations, float** d_result, cudaStream_t s) {
-    constexpr int TMAX = R <= 2 ? 4 : 2;   // register windows: T*(2R+1)*4 floats per lane
+    // register windows: T*(2R+1)*4 floats per lane.  NZ_WALK_TMAX=5 (R <= 2 only) tries 5 stages per launch: 17 iterations in
+    // 4 launches (5,4,4,4) instead of 5 (4,4,3,3,3) — measured, see profiles/r2_walk_tmax_scan.txt
+    int TMAX = R <= 2 ? 4 : 2;
+    if (R <= 2) {
+        const char* et = getenv("NZ_WALK_TMAX");
+        if (et && atoi(et) == 5) TMAX = 5;
+    }
     const int launches = (iterations + TMAX - 1) / TMAX;
     float *cur = d_data, *other = d_tmp;
     int left = iterations;
@@ -418,6 +424,7 @@ int32_t launch_walk_r(float* d_data, float* d_tmp, int width, int rows, const fl
             case 1: rc = launch_walk_rt<R, 1>(cur, other, width, rows, kx, kz, factor, s); break;
             case 2: rc = launch_walk_rt<R, 2>(cur, other, width, rows, kx, kz, factor, s); break;
             case 3: rc = launch_walk_rt<R, 3>(cur, other, width, rows, kx, kz, factor, s); break;
+            case 5: rc = launch_walk_rt<(R <= 2 ? R : 1), 5>(cur, other, width, rows, kx, kz, factor, s); break;   // only reached with R <= 2
             default: rc = launch_walk_rt<R, 4>(cur, other, width, rows, kx, kz, factor, s); break;
         }
         if (rc != NZ_OK) return rc;

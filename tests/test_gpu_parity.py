@@ -742,3 +742,17 @@ def test_bulk_copy_row_feed_equals_cp_async_feed_bitwise(nz, torch_cuda, monkeyp
     bulk = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
     torch.cuda.synchronize()
     assert torch.equal(bulk, ref)
+
+
+@pytest.mark.parametrize("rows,width,ftype,iters", [(700, 600, 2, 17), (1300, 1000, 3, 5), (513, 472, 6, 10), (2200, 4096, 2, 17)])
+def test_five_stage_walk_launches_equal_generic_path_bitwise(nz, torch_cuda, monkeypatch, rows, width, ftype, iters):
+    """NZ_WALK_TMAX=5: five filter iterations per launch (17 = 5+4+4+4 instead of 4+4+3+3+3), a measured alternative."""
+    torch = torch_cuda
+    a = torch.from_numpy(rand_grid(rows, width)).cuda()
+    monkeypatch.setenv("NZ_SEP_PATH", "generic")
+    ref = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    monkeypatch.setenv("NZ_SEP_PATH", "walk")
+    monkeypatch.setenv("NZ_WALK_TMAX", "5")
+    five = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(five, ref)
