@@ -14,8 +14,7 @@ def t(fn, reps=5):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
 for I in (5, 4, 3):
-    for g in ("0", "4", "4L", "6"):
-        os.environ["NZ_FLOW_GROUP"] = g[0]
-        os.environ["NZ_FLOW_LAZY"] = "1" if g.endswith("L") else "0"
+    for g in ("0", "4", "6"):
+        os.environ["NZ_FLOW_GROUP"] = g
         a.copy_(src)
         print(f"I={I} group={g}: {t(lambda: d.flowmap(a, b, None, I, 0.0, 0.005)):.3f} ms", flush=True)
