@@ -16,4 +16,4 @@ from .stages import (FractalNoise, KernelFilterType, GaussSigma, MeshType, JobHa
                      StageGaussianBlur, StageSmoothBlur, ErosionFilterStage, FlowMapStage, MeshTileStage, BasePipeline,
                      ConstantOperationType, ReductionType, ReduceData, DownsampleData, StageThermalErosion, ErosionStageSubtractiveFlow,
                      ConstantStage, ReduceStage, CurveStage, CropStage, GpuStage, GpuResidency,
-                     PipelineStateManager, WriteGeneratorContextStage, ReadGeneratorContextStage)
+                     PipelineStateManager, WriteGeneratorContextStage, ReadGeneratorContextStage, ReducePipeline)

@@ -655,3 +655,81 @@ class ReadGeneratorContextStage(GpuStage):
         gd = requirements.data
         name = requirements.stageManager.GetBuffer(_context_buffer_name(gd, self.contextAlias), gd.resolution * gd.resolution)
         self._native(requirements, lambda: _h.context_read(name, gd.data))
+
+
+# ---- ReducePipeline: two upstream pipelines joined by a reduce pipeline ------------------------------------------------------
+class ReducePipeline(BasePipeline):
+    """Pipeline/Executable/ReducePipeline.cs:32-165: takes ONE work item, requests the same item (same uuid, position and
+    resolution; the right side on a buffer of its own) from both upstream pipelines, and when both have completed runs its
+    own stages on a ReduceData{data = left, rightData = right}.
+
+    On the GPU the join needs no host traffic: the reference gives both upstream items the SAME uuid (:104-112), and
+    GpuResidency keys the residency scope by uuid, so with `keepResident` on the last stage of each upstream pipeline both
+    operands are still in HBM when this pipeline's ReduceStage runs, and the scope closes (one download of the result) at
+    the end of THIS pipeline.  The C# ReducePipeline works unchanged with Gpu* stages for the same reason."""
+
+    def __init__(self, stages, upstreamPipelineLeft, upstreamPipelineRight, alias="reduce", contextManager=None):
+        super().__init__(stages, alias, contextManager)
+        self.upstreamPipelineLeft, self.upstreamPipelineRight = upstreamPipelineLeft, upstreamPipelineRight
+        self.upstreamsRunning = False
+        self.currentWorkItem = None
+        self.rightData = None
+        self.currentDataLength = 0
+
+    def GetDependencies(self):
+        deps = [self.upstreamPipelineLeft, self.upstreamPipelineRight, self]
+        for p in (self.upstreamPipelineLeft, self.upstreamPipelineRight):
+            if hasattr(p, "GetDependencies"):
+                deps += p.GetDependencies()
+        return deps
+
+    def Update(self):          # OnUpdate, :64-80
+        if not self.pipelineRunning and not self.pipelineQueued and not self.upstreamsRunning and self.queue:
+            self.upstreamsRunning = True
+            self.ScheduleUpstreams(self.queue.popleft())
+        for p in (self.upstreamPipelineLeft, self.upstreamPipelineRight):
+            p.Update()
+
+    def LateUpdate(self):
+        for p in (self.upstreamPipelineLeft, self.upstreamPipelineRight):
+            p.LateUpdate()
+        super().LateUpdate()
+
+    def ScheduleUpstreams(self, wi):     # :82-122
+        left = wi.data
+        if left.data.size != self.currentDataLength or self.rightData is None:
+            self.currentDataLength = left.data.size
+            self.rightData = np.empty(self.currentDataLength, np.float32)
+        right = GeneratorData(left.uuid, self.rightData, left.resolution, left.xpos, left.zpos)
+        self.currentWorkItem = {"status": {"L": False, "R": False}, "stages": {"L": left, "R": right}, "action": wi.completeAction}
+        self.upstreamPipelineLeft.Enqueue(left, completeAction=lambda res: self.OnCompleteUpstream(res, "L"))
+        self.upstreamPipelineRight.Enqueue(right, completeAction=lambda res: self.OnCompleteUpstream(res, "R"))
+
+    def OnCompleteUpstream(self, res, side):     # :124-150
+        w = self.currentWorkItem
+        w["status"][side] = True
+        w["stages"][side] = res
+        if all(w["status"].values()):
+            self.upstreamsRunning = False
+            d = res
+            rd = ReduceData(d.uuid, w["stages"]["L"].data, w["stages"]["R"].data, d.resolution, d.xpos, d.zpos)
+            self.Schedule(PipelineWorkItem(rd, w["action"], None, None, self.contextManager))
+
+    def Run(self, input, **kw):
+        """Enqueue and pump frames until the joined item has completed."""
+        done = []
+        user = kw.pop("completeAction", None)
+
+        def finished(d):
+            done.append(d)
+            if user is not None:
+                user(d)
+        self.Enqueue(input, completeAction=finished, **kw)
+        for _ in range(8):
+            self.Update()
+            self.LateUpdate()
+            if done:
+                break
+        if not done:
+            raise Exception(f"{self.alias}: the joined work item did not complete")
+        return done[0]

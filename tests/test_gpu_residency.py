@@ -175,3 +175,39 @@ def test_context_stages_keep_tiles_on_the_device_between_pipelines(nz, tmp_path)
     with pytest.raises(nz.NzError) as e:
         nz.host.context_read("no-such-buffer", out2)
     assert e.value.code == nz.lib.NZ_E_STATE
+
+
+def test_reduce_pipeline_joins_two_upstreams_on_the_device(nz):
+    """ReducePipeline (Pipeline/Executable/ReducePipeline.cs:32-165): both upstream items carry the same uuid, so with
+    keepResident on the upstreams' last stages the two operands meet in HBM — the host copies are poisoned before the reduce
+    runs, so a result that matches can only have come from the resident mirrors."""
+    left_stages = [nz.NoiseStage(nz.FractalNoise.Simplex, hurst=0.4, octaves=13, noiseSize=1700),
+                   nz.KernelFilterStage(nz.KernelFilterType.Gauss5_S1, iterations=4)]
+    right_stages = [nz.NoiseStage(nz.FractalNoise.Cellular, hurst=0.7, octaves=5, noiseSize=300),
+                    nz.ConstantStage(nz.ConstantOperationType.MULTIPLY, 0.5)]
+    left_stages[-1].keepResident = True
+    right_stages[-1].keepResident = True
+    left, right = nz.BasePipeline(left_stages, "left"), nz.BasePipeline(right_stages, "right")
+    poisoned = []
+
+    class Poison(nz.ReduceStage):          # first stage of the joined pipeline: both host operands are current, and get poisoned
+        def Schedule(self, requirements, dependency):
+            d = requirements.data
+            poisoned.append((d.data.copy(), d.rightData.copy(), nz.GpuResidency.IsOpen(d.uuid)))
+            d.data[:] = -5.0
+            d.rightData[:] = -7.0
+            super().Schedule(requirements, dependency)
+    rp = nz.ReducePipeline([Poison(nz.ReductionType.MAX), nz.ConstantStage(nz.ConstantOperationType.MULTIPLY, 2.0)], left, right)
+    data = np.zeros(N * N, np.float32)
+    out = rp.Run(nz.GeneratorData("joined", data, N, 0, 424))
+    a = np.zeros(N * N, np.float32)
+    nz.host.fractal(a, N, 3, 0.4, 1.0, 2.0, 0.0, 13, 0, 424, 1700)
+    nz.host.kernel_filter(a, None, 2, N, 4)
+    b = np.zeros(N * N, np.float32)
+    nz.host.fractal(b, N, 5, 0.7, 1.0, 2.0, 0.0, 5, 0, 424, 300)
+    nz.host.constant(b, None, 0, 0.5, N)
+    la, ra, was_open = poisoned[0]
+    assert was_open and np.array_equal(la, a) and np.array_equal(ra, b)          # keepResident flushed both, the scope stayed
+    assert np.array_equal(data, np.maximum(a, b) * np.float32(2.0))
+    assert isinstance(out, nz.GeneratorData)                                       # ReduceStage.TransformData (ReduceStage.cs:52-61)
+    assert not nz.GpuResidency.IsOpen("joined")
