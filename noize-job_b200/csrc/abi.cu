@@ -225,6 +225,8 @@ struct Mirror {
     // nz_set_bands: the mirror of a large square grid is a set of row bands, one per device, instead of d / d_tmp.  All
     // work on a banded mirror runs on the bands' own streams, so stages issued from different threads stay ordered.
     std::shared_ptr<BandSet> bands;
+    // element-wise stages issued inside a scope and not applied yet (see materialize()): d holds the values BEFORE them
+    std::vector<PointwiseOp> pending;
 };
 
 // A residency scope: the device mirrors of the host slices one chain of stages works on.  Scopes are process-wide
@@ -318,8 +320,31 @@ static int32_t upload(Mirror& m) {
     return rc;
 }
 
+// Element-wise stages (nz_constant, nz_normalize) called inside a residency scope are DEFERRED: the call appends a step to
+// the mirror's `pending` list and returns.  The list is applied as one pass (launch_pointwise_chain: 8 B of HBM traffic per
+// cell for the whole run instead of 8 B per stage) together with the next nz_curve, or when anything else needs the values:
+// another stage (acquire), the download at scope close / flush, a named-buffer write.  NZ_POINTWISE_FUSE=0 applies every
+// stage at once.  The values are those of the separate passes bit for bit.  Banded mirrors do not defer.
+static bool pointwise_defer_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("NZ_POINTWISE_FUSE");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+static int32_t materialize(Mirror& m, const PointwiseOp* last = nullptr) {
+    if (last) m.pending.push_back(*last);
+    if (m.pending.empty()) return NZ_OK;
+    int32_t rc = launch_pointwise_chain(m.d, m.n, m.pending.data(), (int)m.pending.size(), t_state.stream);
+    m.pending.clear();
+    m.dirty = true;
+    return rc;
+}
+
 static int32_t download(Mirror& m) {
     cudaStream_t s = t_state.stream;
+    int32_t prc = materialize(m);
+    if (prc != NZ_OK) return prc;
     if (m.host.stride_bytes == 4) {
         NZ_CUDA(cudaMemcpyAsync(m.host.ptr, m.d, m.n * sizeof(float), cudaMemcpyDeviceToHost, s));
     } else {
@@ -400,7 +425,7 @@ static void release_mirror(Mirror& m) {
 // Obtain the device mirror of a host slice.  `need_contents`: the stage reads the slice (H2D unless a resident mirror is
 // already newer than the host).  `band_res` > 0: the slice is a band_res^2 grid and the calling stage has a banded form
 // (nz_set_bands); 0: the stage needs an ordinary single-device mirror (a banded one is gathered first).
-static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out, int band_res = 0) {
+static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out, int band_res = 0, bool keep_pending = false) {
     Scope& sc = cur_scope();
     std::lock_guard<std::mutex> lk(sc.mu);
     auto& mirrors = sc.mirrors;
@@ -456,6 +481,13 @@ static int32_t acquire(const nz_slice_f32& s, bool need_contents, Mirror** out, 
         it = mirrors.emplace(s.ptr, m).first;
     } else if (it->second.bands && band_res == 0) {
         int32_t rc = unband(it->second);
+        if (rc != NZ_OK) return rc;
+    }
+    if (!keep_pending && !it->second.pending.empty()) {
+        // the caller reads (or overwrites) the values: apply the deferred element-wise run first (the stream already waits
+        // for the mirror's previous stage)
+        if (!need_contents) it->second.pending.clear();      // the caller overwrites every value
+        int32_t rc = materialize(it->second);
         if (rc != NZ_OK) return rc;
     }
     *out = &it->second;
@@ -1069,12 +1101,22 @@ static int band_cap_for(int resolution) {
     return BAND_GHOST_CAP < min_own ? BAND_GHOST_CAP : min_own;
 }
 
+// one element-wise step on an ordinary mirror: deferred inside a scope (see materialize()), applied at once outside
+static int32_t pointwise_step(Mirror& m, const PointwiseOp& op) {
+    if (in_scope() && pointwise_defer_enabled() && m.pending.size() + 1 < (size_t)PW_CHAIN_MAX) {
+        m.pending.push_back(op);
+        m.dirty = true;
+        return NZ_OK;
+    }
+    return materialize(m, &op);
+}
+
 // shared body of the in-place two-buffer stages.  `banded_body` (BandSet&) -> status is the stage's form on row bands
 // (nz_set_bands); pass can_band = false for a stage (or a parameter combination) that has none: a banded mirror is then
 // gathered onto the primary device first.
 template <typename F, typename B>
 static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const char* who, bool need_tmp, F&& body, bool can_band,
-                                 B&& banded_body) {
+                                 B&& banded_body, bool keep_pending = false) {
     NZ_REQUIRE(resolution > 0 && resolution <= 46340, "%s: resolution %d out of range", who, resolution);
     int32_t rc = check_slice(src, (long long)resolution * resolution, who);
     if (rc != NZ_OK) return rc;
@@ -1083,7 +1125,7 @@ static int32_t run_inplace_stage(nz_slice_f32 src, int32_t resolution, const cha
     struct Pop { ~Pop() { nvtxRangePop(); } } pop;
     if ((rc = begin_stage()) != NZ_OK) return rc;
     Mirror* m;
-    if ((rc = acquire(src, /*need_contents=*/true, &m, can_band ? resolution : 0)) != NZ_OK) return rc;
+    if ((rc = acquire(src, /*need_contents=*/true, &m, can_band ? resolution : 0, keep_pending)) != NZ_OK) return rc;
     if (m->bands) {
         if ((rc = mark_uploaded()) != NZ_OK) return rc;
         rc = banded_body(*m->bands);
@@ -1335,26 +1377,28 @@ NZ_API int32_t nz_subtractive_flow_erosion(nz_slice_f32 height, int32_t resoluti
 NZ_API int32_t nz_constant(nz_slice_f32 src, nz_slice_f32 tmp, int32_t operation, float constant_value, int32_t resolution) {
     (void)tmp;
     NZ_REQUIRE(operation >= 0 && operation < NZ_CONSTANT__COUNT, "nz_constant: operation %d out of range", operation);
+    const PointwiseOp op{operation == NZ_CONSTANT_MULTIPLY ? PW_MUL : PW_BINARIZE, constant_value, 0.0f, nullptr};
     return run_inplace_stage(src, resolution, "nz_constant", false, [&](Mirror& m, float**) {
-        return launch_constant(m.d, m.n, operation, constant_value, t_state.stream);
+        return pointwise_step(m, op);
     }, true, [&](BandSet& bs) {
         return bandset_stage(bs, 0, 0, [&](Band& bd, float* cur, float*, int rows, int, float**) {
             return launch_constant(cur, (size_t)rows * bs.width, operation, constant_value, bd.s);
         });
-    });
+    }, /*keep_pending=*/true);
 }
 
 NZ_API int32_t nz_normalize(nz_slice_f32 src, nz_slice_f32 tmp, const float* args3, int32_t resolution) {
     (void)tmp;
     NZ_REQUIRE(args3 != nullptr, "nz_normalize: args is null");
     const float vmin = args3[0], range = args3[2];
+    const PointwiseOp op{PW_NORMALIZE, vmin, range, nullptr};
     return run_inplace_stage(src, resolution, "nz_normalize", false, [&](Mirror& m, float**) {
-        return launch_normalize(m.d, m.n, vmin, range, t_state.stream);
+        return pointwise_step(m, op);
     }, true, [&](BandSet& bs) {
         return bandset_stage(bs, 0, 0, [&](Band& bd, float* cur, float*, int rows, int, float**) {
             return launch_normalize(cur, (size_t)rows * bs.width, vmin, range, bd.s);
         });
-    });
+    }, /*keep_pending=*/true);
 }
 
 NZ_API int32_t nz_reduce(nz_slice_f32 left, nz_slice_f32 right, nz_slice_f32 tmp, int32_t operation, int32_t resolution) {
@@ -1378,11 +1422,14 @@ NZ_API int32_t nz_curve(nz_slice_f32 src, nz_slice_f32 tmp, nz_slice_f32 curve, 
     NZ_REQUIRE(curve.ptr && curve.length >= 2 && curve.stride_bytes >= 4, "nz_curve: the curve needs at least 2 samples");
     NZ_REQUIRE(curve.ptr != src.ptr, "nz_curve: curve and data are the same slice");
     Mirror* c = nullptr;
+    // the curve closes a deferred run: its samples live in another mirror whose lifetime the data mirror does not control,
+    // so the run (with the curve as its last step) is applied now, in one pass
     int32_t rc = run_inplace_stage(src, resolution, "nz_curve", false, [&](Mirror& m, float**) {
         int32_t rr = acquire(curve, /*need_contents=*/true, &c);
         if (rr != NZ_OK) return rr;
-        return launch_curve(m.d, m.n, c->d, curve.length, t_state.stream);
-    });
+        const PointwiseOp op{PW_CURVE, (float)curve.length, 0.0f, c->d};
+        return materialize(m, &op);
+    }, false, [](BandSet&) { return (int32_t)NZ_E_UNSUPPORTED; }, /*keep_pending=*/true);
     return rc;
 }
 

@@ -104,6 +104,15 @@ int32_t launch_constant(float* d, size_t n, int op, float value, cudaStream_t s)
 int32_t launch_reduce(float* d_left, const float* d_right, size_t n, int op, cudaStream_t s);
 int32_t launch_curve(float* d, size_t n, const float* d_curve, int curve_size, cudaStream_t s);
 int32_t launch_normalize(float* d, size_t n, float vmin, float range, cudaStream_t s);
+// one pass applying up to PW_CHAIN_MAX element-wise steps in order (pointwise_kernels.cu: ChainF)
+enum { PW_MUL = 0, PW_BINARIZE = 1, PW_NORMALIZE = 2, PW_CURVE = 3 };
+constexpr int PW_CHAIN_MAX = 8;
+struct PointwiseOp {
+    int kind;
+    float a, b;          // MUL/BINARIZE: a = constant; NORMALIZE: a = min, b = range; CURVE: a = (float)curve size
+    const float* lut;    // CURVE: device pointer of the curve samples
+};
+int32_t launch_pointwise_chain(float* d, size_t n, const PointwiseOp* ops, int count, cudaStream_t s);
 int32_t launch_crop(const float* d_in, int in_res, float* d_out, int out_res, int offset, cudaStream_t s);
 size_t map_range_scratch_bytes();
 int32_t launch_map_range(const float* d, size_t n, float lim_min, float lim_max, float* d_res3, void* d_scratch, cudaStream_t s);

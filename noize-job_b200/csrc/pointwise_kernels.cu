@@ -145,6 +145,28 @@ __global__ void __launch_bounds__(PW_THREADS) range_final_kernel(const float2* _
     }
 }
 
+// A run of element-wise stages on the same grid as ONE pass (second half): the host layer defers
+// constant / normalize inside a residency scope and applies the run together with the next curve, or when another stage
+// (or the download) needs the values.  Each step is the functor the single-stage kernel uses, applied in call order to the
+// value in a register, so the result is the one the separate passes give bit for bit (--fmad=false: nothing contracts
+// across steps), for 8 B of HBM traffic per cell instead of 8 B per stage.
+struct ChainF {
+    PointwiseOp op[PW_CHAIN_MAX];
+    int count;
+    __device__ float operator()(float v) const {
+        for (int i = 0; i < count; i++) {
+            const PointwiseOp o = op[i];
+            switch (o.kind) {
+                case PW_MUL: v = MulC{o.a}(v); break;
+                case PW_BINARIZE: v = BinC{o.a}(v); break;
+                case PW_NORMALIZE: v = Norm{o.a, o.b}(v); break;
+                default: v = Curve{o.lut, o.a}(v); break;
+            }
+        }
+        return v;
+    }
+};
+
 inline int grid_for(size_t n) { return cdiv((long long)((n + 3) / 4), PW_THREADS); }
 
 }  // namespace
@@ -188,6 +210,21 @@ int32_t launch_curve(float* d, size_t n, const float* d_curve, int curve_size, c
 int32_t launch_normalize(float* d, size_t n, float vmin, float range, cudaStream_t s) {
     if (n == 0) return NZ_OK;
     map1_kernel<<<grid_for(n), PW_THREADS, 0, s>>>(d, n, Norm{vmin, range});
+    NZ_LAUNCHED();
+    return NZ_OK;
+}
+
+int32_t launch_pointwise_chain(float* d, size_t n, const PointwiseOp* ops, int count, cudaStream_t s) {
+    if (n == 0 || count == 0) return NZ_OK;
+    if (count < 0 || count > PW_CHAIN_MAX) {
+        set_error("pointwise chain: %d steps (at most %d)", count, PW_CHAIN_MAX);
+        return NZ_E_INVALID;
+    }
+    ChainF f;
+    for (int i = 0; i < count; i++) f.op[i] = ops[i];
+    for (int i = count; i < PW_CHAIN_MAX; i++) f.op[i] = PointwiseOp{PW_MUL, 1.0f, 0.0f, nullptr};
+    f.count = count;
+    map1_kernel<<<grid_for(n), PW_THREADS, 0, s>>>(d, n, f);
     NZ_LAUNCHED();
     return NZ_OK;
 }

@@ -186,3 +186,49 @@ def test_subtractive_flow_fused_cycles_equal_per_iteration_kernels_bitwise(nz, o
     assert torch.equal(a, b)
     if rows * width <= 300000:
         assert np.array_equal(bits(b.cpu().numpy()), bits(oracle.subtractive_flow_erosion(r, cycles, 0.1, 0.0, 0.05)))
+
+
+@pytest.mark.parametrize("res", [200, 1024])
+def test_deferred_pointwise_run_is_one_pass_and_bit_exact(nz, oracle, res):
+    """Inside a scope nz_constant / nz_normalize are deferred and applied as ONE pass with the next nz_curve (or when the
+    values are needed): fewer launches, the same bits as the oracle's stage-by-stage composition."""
+    v = rnd(res, 11, -0.3, 1.4)
+    curve = np.array([np.sqrt(i / 63) for i in range(64)], np.float32)
+    rng = oracle.map_range(v)
+    o = oracle
+    want = o.constant(o.curve(o.normalize(o.constant(v, 0, 0.9), rng), curve), 0, 0.5)
+    want_bin = o.constant(want, 1, 0.25)
+
+    got = v.copy().reshape(-1)
+    before = nz.host.kernel_launch_count()
+    with nz.host.pipeline():
+        nz.host.constant(got, None, 0, 0.9, res)
+        nz.host.normalize(got, None, rng, res)
+        nz.host.curve(got, None, curve, res)              # run of three -> one launch
+        nz.host.constant(got, None, 0, 0.5, res)          # deferred until ...
+        mid = nz.host.kernel_launch_count() - before
+        nz.host.flush_to_host(got)                        # ... the values are needed
+        assert np.array_equal(bits(got.reshape(res, res)), bits(want))
+        nz.host.constant(got, None, 1, 0.25, res)         # applied by the download at scope close
+    assert mid == 1, mid
+    assert nz.host.kernel_launch_count() - before == 3
+    assert np.array_equal(bits(got.reshape(res, res)), bits(want_bin))
+
+    # a stage that reads the values applies the run first; a stage that overwrites them drops it
+    a = v.copy().reshape(-1)
+    b = np.zeros(res * res, np.float32)
+    with nz.host.pipeline():
+        nz.host.constant(a, None, 0, 0.9, res)
+        nz.host.kernel_filter(a, None, 3, res, 1)
+        nz.host.constant(b, None, 0, 123.0, res)
+        nz.host.fractal(b, res, 3, 0.4, 1.0, 2.0, 0.0, 4, 0, 0, 300)
+    assert np.array_equal(bits(a.reshape(res, res)), bits(o.kernel_filter(o.constant(v, 0, 0.9), 3, 1)))
+    assert np.abs(b.reshape(res, res) - o.fractal(res, res, 3, 0.4, octaves=4, noise_size=300)).max() <= 1e-6
+    # more steps than one pass holds (PW_CHAIN_MAX = 8)
+    c = v.copy().reshape(-1)
+    wantc = v
+    with nz.host.pipeline():
+        for k in range(19):
+            nz.host.constant(c, None, 0, 1.0 + 0.01 * k, res)
+            wantc = o.constant(wantc, 0, 1.0 + 0.01 * k)
+    assert np.array_equal(bits(c.reshape(res, res)), bits(wantc))
