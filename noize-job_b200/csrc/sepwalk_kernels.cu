@@ -42,6 +42,9 @@ struct TapsW {
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -78,7 +81,12 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 
 // BORDER = false is the steady-state body for warps whose strip and chunk touch no grid border: no clamp logic.
 // BULK (interior body only): rows arrive by cp.async.bulk + mbarrier instead of per-lane cp.async (see above).
-template <int R, int T, bool SCALE, bool BORDER, int PFR, bool BULK = false>
+// SK = 1: SKEWED stages.  Unskewed, the T stages of one step form a serial chain (stage t+1 consumes what stage t has just
+// emitted: shuffle -> 2r+1 fmas -> 2r+1 fmas, T times).  Skewed, stage t+1 consumes what stage t emitted in the PREVIOUS
+// step (kept in pipe[t+1]), so the T stages of a step are independent instruction streams the scheduler can interleave; a
+// stage's rows arrive one step later per stage (row r0 - (R+1)t instead of r0 - R t), the chunk runs T-1 more steps, and
+// every cell sees the same operations in the same order: the bits do not change.
+template <int R, int T, bool SCALE, bool BORDER, int PFR, bool BULK = false, int SK = 0>
 __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor,
                                           const TapsW<R>& kx, const TapsW<R>& kz, int wx0, int zc0, int zc1, unsigned ring_base,
                                           unsigned bar_base = 0) {
@@ -91,34 +99,46 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     const bool interior = !has_left && !has_right;
     const int L0 = has_left ? (-wx0) / VW : 0;                 // lane whose element 0 is grid column 0
     const int L1 = has_right ? (W - 1 - wx0) / VW : 31;        // lane whose element 3 is grid column W-1
-    int rs = max(zc0 - R * T, 0);
+    constexpr int LAG = R * T + SK * (T - 1);                  // steps between a row's load and its store
+    int rs = max(zc0 - LAG, 0);
     rs -= rs % KS;                                             // first input row, phase 0
     // last (virtual) input row.  The clamp-free body never reads past the window: a chunk that ends at a window edge which
     // is not a grid edge (row bands, grid_edges()) simply stops there, leaving the last R*T rows unwritten — they are ghost rows
-    const int r_end = min(zc1 - 1 + R * T, BORDER ? H - 1 + R * T : H - 1);
-
-    auto load_row = [&](int r, float (&v)[VW]) {
-        const float* g = src + (size_t)(BORDER ? min(r, H - 1) : r) * W;
-        if (interior) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(g + gx));
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < VW; q++) v[q] = __ldg(g + min(max(gx + q, 0), W - 1));
-        }
-    };
+    // (skewed: the T-1 drain steps past the window's last row load nothing and push stale values through stage 0, whose
+    // emissions there are ghost rows anyway)
+    const int r_end = min(zc1 - 1 + LAG, BORDER ? H - 1 + LAG : H - 1 + SK * (T - 1));
+    const int r_load_end = (SK && !BORDER) ? min(r_end, H - 1) : r_end;
 
     float win[T][KS][VW];
+    float pipe[SK ? T + 1 : 1][VW];                            // skewed: pipe[t] = what stage t-1 emitted in the previous step
+    if (SK) {
+#pragma unroll
+        for (int t = 0; t <= T; t++)
+#pragma unroll
+            for (int q = 0; q < VW; q++) pipe[t][q] = 0.0f;
+    }
     // Memory-level parallelism.  One 512-byte row per step per warp is far too little in flight for HBM (Little's
-    // law: ~12 warps x 148 SMs x 512 B / ~2 us of loaded latency ~ 0.5 TB/s).  The steady-state body therefore
-    // requests rows PFR-1 steps ahead with cp.async into a per-lane private landing zone in shared memory (each
-    // lane writes and later reads its own 16 bytes per row, so no cross-lane synchronisation is needed); border
-    // warps (clamped addresses) keep the simple one-row register prefetch.
-    float nxt[VW];
+    // law: ~12 warps x 148 SMs x 512 B / ~2 us of loaded latency ~ 0.5 TB/s).  Rows are therefore requested PFR-1 steps
+    // ahead with cp.async into a per-lane private landing zone in shared memory (each lane writes and later reads its
+    // own 16 bytes per row, so no cross-lane synchronisation is needed).  Border warps do the same with clamped
+    // addresses — 4-byte copies where the strip overhangs the grid's first or last column; with a one-row register
+    // prefetch every step of a border walk waited a full memory latency (~0.85 us: 45 us per launch).
     const unsigned ring_lane = ring_base + (unsigned)(lane * VW * sizeof(float));   // shared-space byte address
-    if (BORDER) {
-        load_row(rs, nxt);
-    } else if (BULK) {
+    auto request = [&](int r) {
+        const unsigned slot = ring_lane + (r & (PFR - 1)) * (STRIP * 4);
+        if (!BORDER) {
+            cp_async16(slot, src + (size_t)r * W + gx);
+        } else {
+            const float* g = src + (size_t)min(r, H - 1) * W;
+            if (interior) {
+                cp_async16(slot, g + gx);
+            } else {
+#pragma unroll
+                for (int q = 0; q < VW; q++) cp_async4(slot + 4 * q, g + min(max(gx + q, 0), W - 1));
+            }
+        }
+    };
+    if (BULK) {
         if (lane == 0) {
 #pragma unroll 1
             for (int j = 0; j < PFR; j++) mbar_init(bar_base + j * 8, 1);
@@ -137,7 +157,7 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     } else {
 #pragma unroll 1
         for (int j = 0; j < PFR - 1; j++) {
-            if (rs + j <= r_end) cp_async16(ring_lane + ((rs + j) & (PFR - 1)) * (STRIP * 4), src + (size_t)(rs + j) * W + gx);
+            if (rs + j <= r_load_end) request(rs + j);
             cp_async_commit();
         }
     }
@@ -150,11 +170,7 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
             // chunk end compute rows that are never stored)
             if (!BORDER || r0 <= r_end) {
                 float v[VW];
-                if (BORDER) {
-#pragma unroll
-                    for (int q = 0; q < VW; q++) v[q] = nxt[q];
-                    if (r0 < r_end) load_row(r0 + 1, nxt);
-                } else if (BULK) {
+                if (BULK) {
                     const int ra = r0 + PFR - 1;                     // row requested now; its slot held row r0 - 1, read last step
                     __syncwarp();
                     if (lane == 0 && ra <= r_end) {
@@ -168,16 +184,29 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
                     v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
                 } else {
                     const int ra = r0 + PFR - 1;                     // row requested now, consumed PFR-1 steps later
-                    if (ra <= r_end) cp_async16(ring_lane + (ra & (PFR - 1)) * (STRIP * 4), src + (size_t)ra * W + gx);
+                    if (ra <= r_load_end) request(ra);
                     cp_async_commit();
                     cp_async_wait<PFR - 1>();                        // the group of row r0 has landed
                     const float4 t4 = ld_shared_f4(ring_lane + (r0 & (PFR - 1)) * (STRIP * 4));
                     v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
                 }
+                float vin[VW];
 #pragma unroll
-                for (int t = 0; t < T; t++) {
-                    const int rt = r0 - R * t;                  // row this stage receives; phase is static:
-                    const int P = ((u - R * t) % KS + KS) % KS;
+                for (int q = 0; q < VW; q++) vin[q] = v[q];
+                // stage order: ascending chains the stages within the step; descending (skewed) lets stage t read pipe[t] as
+                // stage t-1 left it in the previous step
+#pragma unroll
+                for (int tt = 0; tt < T; tt++) {
+                    const int t = SK ? T - 1 - tt : tt;
+                    const int rt = r0 - (R + SK) * t;           // row this stage receives; phase is static:
+                    const int P = ((u - (R + SK) * t) % KS + 4 * KS) % KS;
+                    if (SK && t > 0) {
+#pragma unroll
+                        for (int q = 0; q < VW; q++) v[q] = pipe[t][q];
+                    } else if (SK) {
+#pragma unroll
+                        for (int q = 0; q < VW; q++) v[q] = vin[q];
+                    }
                     if (!BORDER || rt >= 0) {
                         float xp[VW];
                         if (!BORDER || rt <= H - 1) {
@@ -241,9 +270,17 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
                                 for (int q = 0; q < VW; q++) v[q] = e;
                             }
                         }
+                        if (SK) {
+#pragma unroll
+                            for (int q = 0; q < VW; q++) pipe[t + 1][q] = v[q];
+                        }
                     }
                 }
-                const int rT = r0 - R * T;
+                if (SK) {
+#pragma unroll
+                    for (int q = 0; q < VW; q++) v[q] = pipe[T][q];
+                }
+                const int rT = r0 - LAG;
                 if (rT >= zc0 && rT < zc1 && VW * lane >= HALO && VW * lane < HALO + USE && gx < W)
                     *reinterpret_cast<float4*>(dst + (size_t)rT * W + gx) = make_float4(v[0], v[1], v[2], v[3]);
             }
@@ -258,32 +295,15 @@ struct WalkRanges {
     int s_lo, s_hi, r_lo, r_hi;   // interior launch: strips [s_lo, s_hi) x rows [r_lo, r_hi) in chunks of zc
     int ns, zcb;                  // border launch: flat (strip, chunk) items in chunks of zcb over the rest of the grid
     int n_top, n_bot, n_items;    //   all strips x [0, r_lo), all strips x [r_hi, H), border strips x [r_lo, r_hi)
+    int nb, ctas_x;               // merged launch: blocks [0, nb) take the border items, block nb + by * ctas_x + bx is interior CTA (bx, by)
 };
 
-template <int R, int T, bool SCALE, int PFR, bool BULK = false>
-__global__ void __launch_bounds__(WALK_WARPS * 32, (2 * R + 1) * T > 20 ? 4 : 5)    // window of (2R+1)*T*4 registers: 5 CTAs/SM up to 80, else 4
-sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz,
-                int zc, WalkRanges g) {
-    constexpr int HALO = (R * T + 3) & ~3;
-    constexpr int USE = STRIP - 2 * HALO;
-    const int strip = g.s_lo + blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
-    if (strip >= g.s_hi) return;                 // whole warp
-    const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
-    const int zc0 = g.r_lo + blockIdx.y * zc, zc1 = min(zc0 + zc, g.r_hi);
-    // the host chose the ranges so that the strip lies inside the grid and so does the chunk with its warm-up and drain rows
-    extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP] (+ [WALK_WARPS][PFR] mbarriers for the bulk feed)
-    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (PFR * STRIP));
-    const unsigned bar_base = (unsigned)__cvta_generic_to_shared(ring + WALK_WARPS * PFR * STRIP) + (threadIdx.x >> 5) * (PFR * 8);
-    walk_body<R, T, SCALE, false, PFR, BULK>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base, bar_base);
-}
-
+// one (strip, chunk) item of the border list, on the clamping body
 template <int R, int T, bool SCALE>
-__global__ void __launch_bounds__(WALK_WARPS * 32)
-sep_walk_border_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx,
-                       TapsW<R> kz, WalkRanges g) {
+__device__ __forceinline__ void border_item(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor,
+                                            const TapsW<R>& kx, const TapsW<R>& kz, const WalkRanges& g, int item, unsigned ring_base) {
     constexpr int HALO = (R * T + 3) & ~3;
     constexpr int USE = STRIP - 2 * HALO;
-    int item = blockIdx.x * WALK_WARPS + (threadIdx.x >> 5);
     if (item >= g.n_items) return;
     int strip, zc0, zc1;
     if (item < g.n_top) {
@@ -304,7 +324,47 @@ sep_walk_border_kernel(const float* __restrict__ src, float* __restrict__ dst, i
         zc1 = min(zc0 + g.zcb, g.r_hi);
     }
     const int wx0 = strip * USE - HALO;
-    walk_body<R, T, SCALE, true, 2>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, 0u);   // the border body does not use the ring
+    walk_body<R, T, SCALE, true, 16>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
+}
+
+// MERGED: one launch for the whole grid.  The first g.nb blocks (placed first by the block scheduler) walk the border
+// items on the clamping body, the others are the interior CTAs.  As two launches, even forked onto a side stream, the
+// border walk did not hide under the interior launch: it cost its full ~45 us per launch at every grid size
+// (tools/band_scan3.py: Gauss5 x4 on 2116 rows 135 us with the border launch, 96 us without; 16384 rows 581 / 535).
+template <int R, int T, bool SCALE, int PFR, bool BULK = false, int SK = 0, bool MERGED = false>
+__global__ void __launch_bounds__(WALK_WARPS * 32, ((2 * R + 1) * T > 20 || (SK && (2 * R + 1) * T > 15)) ? 4 : 5)    // window of (2R+1)*T*4 registers: 5 CTAs/SM up to 80, else 4
+sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx, TapsW<R> kz,
+                int zc, WalkRanges g) {
+    constexpr int HALO = (R * T + 3) & ~3;
+    constexpr int USE = STRIP - 2 * HALO;
+    int bx = blockIdx.x, by = blockIdx.y;
+    extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP] (+ [WALK_WARPS][PFR] mbarriers for the bulk feed)
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (PFR * STRIP));
+    if (MERGED) {
+        if (bx < g.nb) {
+            border_item<R, T, SCALE>(src, dst, W, H, factor, kx, kz, g, bx * WALK_WARPS + (threadIdx.x >> 5), ring_base);
+            return;
+        }
+        bx -= g.nb;
+        by = bx / g.ctas_x;
+        bx -= by * g.ctas_x;
+    }
+    const int strip = g.s_lo + bx * WALK_WARPS + (threadIdx.x >> 5);
+    if (strip >= g.s_hi) return;                 // whole warp
+    const int wx0 = strip * USE - HALO;          // grid column of this warp's column 0 (multiple of 4)
+    const int zc0 = g.r_lo + by * zc, zc1 = min(zc0 + zc, g.r_hi);
+    // the host chose the ranges so that the strip lies inside the grid and so does the chunk with its warm-up and drain rows
+    const unsigned bar_base = (unsigned)__cvta_generic_to_shared(ring + WALK_WARPS * PFR * STRIP) + (threadIdx.x >> 5) * (PFR * 8);
+    walk_body<R, T, SCALE, false, PFR, BULK, SK>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base, bar_base);
+}
+
+template <int R, int T, bool SCALE>
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+sep_walk_border_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, float factor, TapsW<R> kx,
+                       TapsW<R> kz, WalkRanges g) {
+    extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][16][STRIP]
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (16 * STRIP));
+    border_item<R, T, SCALE>(src, dst, W, H, factor, kx, kz, g, blockIdx.x * WALK_WARPS + (threadIdx.x >> 5), ring_base);
 }
 
 template <int R, int T>
@@ -318,8 +378,6 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     constexpr int HALO = (R * T + 3) & ~3;
     constexpr int USE = STRIP - 2 * HALO;
     const char* ez = getenv("NZ_WALK_ZC");
-    const char* ep = getenv("NZ_WALK_PFR");
-    const int pfr = ep ? atoi(ep) : 16;
     // ranges: strip k covers grid columns [k*USE - HALO, k*USE - HALO + 128); interior strips lie inside the grid, interior
     // rows leave a band of WB rows (> R*T + 2R + 1) at the top and the bottom to the border launch
     constexpr int WB = 32;
@@ -339,66 +397,82 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     g.n_top = g.ns * cdiv(g.r_lo, g.zcb);
     g.n_bot = g.ns * cdiv(rows - g.r_hi, g.zcb);
     g.n_items = g.n_top + g.n_bot + (g.s_lo + (g.ns - g.s_hi)) * cdiv(g.r_hi - g.r_lo, g.zcb);
-    // the border launch reads the same input and writes other cells than the interior launch: it runs underneath it on
-    // the side stream when there is an interior launch to hide it under
-    const bool forked = g.n_items > 0 && g.s_hi > g.s_lo;
-    if (g.n_items > 0) {
+    const bool has_interior = g.s_hi > g.s_lo;
+    const char* ef = getenv("NZ_WALK_FEED");      // bulk: the bulk-copy (TMA engine) row feed, kept as a MEASURED alternative (profiles/r2_walk_feed_scan.txt)
+    const bool bulk = ef && ef[0] == 'b' && factor == 1.0f;
+    const char* em = getenv("NZ_WALK_MERGE");     // 0: border and interior as two launches (the former form), for comparison
+    const bool merge = has_interior && !bulk && !(em && em[0] == '0');
+    const char* es = getenv("NZ_WALK_SKEW");      // 0: chained stages (the former form), for comparison
+    const bool skew = T > 1 && !bulk && !(es && es[0] == '0') && (merge || factor == 1.0f);
+    const bool forked = g.n_items > 0 && has_interior && !merge;
+    const size_t ring_bytes = (size_t)WALK_WARPS * 16 * STRIP * sizeof(float);
+    if (g.n_items > 0 && !merge) {
+        // two launches: the border launch reads the same input and writes other cells than the interior launch; it goes to
+        // the side stream when there is an interior launch to run beside
         cudaStream_t bs = s;
         if (forked) {
             int32_t rc = aux_fork(s, &bs);
             if (rc != NZ_OK) return rc;
         }
         if (factor == 1.0f)
-            sep_walk_border_kernel<R, T, false><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, 0, bs>>>(in, out, width, rows, factor, tx, tz, g);
+            sep_walk_border_kernel<R, T, false><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, ring_bytes, bs>>>(in, out, width, rows, factor, tx, tz, g);
         else
-            sep_walk_border_kernel<R, T, true><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, 0, bs>>>(in, out, width, rows, factor, tx, tz, g);
+            sep_walk_border_kernel<R, T, true><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, ring_bytes, bs>>>(in, out, width, rows, factor, tx, tz, g);
         NZ_LAUNCHED();
     }
-    if (g.s_hi <= g.s_lo) return NZ_OK;
+    if (!has_interior) return NZ_OK;
     const int irows = g.r_hi - g.r_lo;
     const int ctas_x = cdiv(g.s_hi - g.s_lo, WALK_WARPS);
-    // Rows per chunk.  A CTA walks its chunk serially and 5 CTAs are resident per SM, so the launch takes about
+    // Rows per chunk.  A CTA walks its chunk serially and 4-5 CTAs are resident per SM, so the launch takes about
     // waves x (zc + warm-up rows) steps: take the chunk count that minimises it, within [48, 448] rows.  Measured at
     // 16384^2 (Gauss5 x17, ms): 64 2.93, 96 2.77, 128 2.68, 192 2.66, 256 2.58, 408 2.57 (two whole waves), 544 2.70.
+    // (A merged launch counts its border blocks as whole CTAs: they are shorter, but a model that charges them by their
+    // length picks longer chunks, which measured slower on 2645..4232-row windows: 917 us against 726 at 4232.)
     int zc = WALK_ZC;
     if (ez) {
         zc = atoi(ez);
     } else {
         const int sms = sm_count();
-        const long long slots = ((2 * R + 1) * T > 20 ? 4LL : 5LL) * sms;   // 5 CTAs of 128 threads x 96 registers per SM (4 x 128 for the deepest windows)
-        const int warm = R * T + 2 * R + 1 + 3;
+        const int win_regs = (2 * R + 1) * T;
+        const long long slots = ((win_regs > 20 || (skew && win_regs > 15)) ? 4LL : 5LL) * sms;   // the kernel's __launch_bounds__
+        const int warm = R * T + 2 * R + 1 + 3 + (skew ? T - 1 : 0);
+        const long long nb = merge ? cdiv(g.n_items, WALK_WARPS) : 0;
         double best = 1e300;
         for (int n = cdiv(irows, 448); n <= irows; n++) {
             const int z = cdiv(irows, n);
             if (z < 48 && n > 1) break;
-            const long long ctas = (long long)ctas_x * cdiv(irows, z);
+            const long long ctas = nb + (long long)ctas_x * cdiv(irows, z);
             const long long waves = (ctas + slots - 1) / slots;
             const double cost = (double)waves * (z + warm);
             if (cost < best) { best = cost; zc = z; }
         }
     }
-    dim3 grid(ctas_x, cdiv(irows, zc));
-#define NZ_WALK_LAUNCH(SC, PF)                                                                                          \
-    do {                                                                                                               \
-        const size_t sm = (size_t)WALK_WARPS * PF * STRIP * sizeof(float);                                             \
-        if (sm > 48 * 1024)                                                                                            \
-            NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, SC, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-        sep_walk_kernel<R, T, SC, PF><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);  \
-    } while (0)
-    // NZ_WALK_FEED=bulk: the bulk-copy (TMA engine) row feed, kept as a MEASURED alternative (profiles/r2_walk_feed_scan.txt)
-    const char* ef = getenv("NZ_WALK_FEED");
-    if (ef && ef[0] == 'b' && factor == 1.0f) {
-        const size_t sm = (size_t)WALK_WARPS * 16 * STRIP * sizeof(float) + (size_t)WALK_WARPS * 16 * 8;
-        NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        sep_walk_kernel<R, T, false, 16, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
-    } else if (factor == 1.0f) {
-        if (pfr == 8) NZ_WALK_LAUNCH(false, 8);
-        else if (pfr == 32) NZ_WALK_LAUNCH(false, 32);
-        else NZ_WALK_LAUNCH(false, 16);
+    const size_t sm = ring_bytes;
+    if (merge) {
+        g.nb = cdiv(g.n_items, WALK_WARPS);
+        g.ctas_x = ctas_x;
+        const dim3 grid(g.nb + ctas_x * cdiv(irows, zc));
+        if (factor == 1.0f) {
+            if (skew) sep_walk_kernel<R, T, false, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+            else sep_walk_kernel<R, T, false, 16, false, 0, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        } else {
+            if (skew) sep_walk_kernel<R, T, true, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+            else sep_walk_kernel<R, T, true, 16, false, 0, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        }
     } else {
-        NZ_WALK_LAUNCH(true, 16);
+        const dim3 grid(ctas_x, cdiv(irows, zc));
+        if (bulk) {
+            const size_t smb = sm + (size_t)WALK_WARPS * 16 * 8;
+            NZ_CUDA(cudaFuncSetAttribute(sep_walk_kernel<R, T, false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+            sep_walk_kernel<R, T, false, 16, true><<<grid, WALK_WARPS * 32, smb, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        } else if (skew) {
+            sep_walk_kernel<R, T, false, 16, false, 1><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        } else if (factor == 1.0f) {
+            sep_walk_kernel<R, T, false, 16><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        } else {
+            sep_walk_kernel<R, T, true, 16><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        }
     }
-#undef NZ_WALK_LAUNCH
     NZ_LAUNCHED();
     if (forked) return aux_join(s);
     return NZ_OK;
