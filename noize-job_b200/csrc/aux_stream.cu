@@ -23,18 +23,9 @@ int32_t get_aux(Aux** out) {
     NZ_REQUIRE(dev >= 0 && dev < 64, "aux stream: device ordinal %d out of range", dev);
     Aux& a = t_aux[dev];
     if (!a.s) {
-        // highest priority: the border launch is short and the interior launch that follows on the caller's stream fills
-        // every SM slot; at equal priority the border CTAs are placed when the interior wave drains, i.e. the border walk
-        // (~45 us) runs as a tail AFTER it (tools/band_scan3.py: 135 us per band-sized Gauss5 x4 launch with the border
-        // launch, 96 without).  NZ_AUX_PRIORITY=0 keeps the default priority for comparison.
-        int least = 0, greatest = 0;
-        const char* ep = getenv("NZ_AUX_PRIORITY");
-        if (ep && ep[0] == '0') greatest = 0;
-        else if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) {
-            cudaGetLastError();
-            greatest = 0;
-        }
-        NZ_CUDA(cudaStreamCreateWithPriority(&a.s, cudaStreamNonBlocking, greatest));
+        // (a high-priority side stream was tried, to make the border CTAs win SM slots from the interior launch: no
+        // measurable change, tools/band_scan3.py)
+        NZ_CUDA(cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking));
         NZ_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
         NZ_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
     }

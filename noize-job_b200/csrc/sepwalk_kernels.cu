@@ -14,7 +14,7 @@
 // memory traffic is one coalesced 512-byte row load and one row store per step: 8 B/cell per T iterations.
 //
 // Redundancy: r*T halo columns each side of the strip (112 of 128 columns useful for Gauss5 x 4) and r*T
-// warm-up rows per chunk.  Against the shared-memory tile kernel this removes all LDS/STS, both tile phases
+// (+ T-1, skewed stages: see walk_body) warm-up rows per chunk.  Against the shared-memory tile kernel this removes all LDS/STS, both tile phases
 // and every __syncthreads; per cell-iteration it issues 2(2r+1) FFMA + ~2r/2 SHFL.
 //
 // Clamp-to-edge: input rows are loaded with clamped columns; after every stage the lanes outside the grid
@@ -288,9 +288,10 @@ __device__ __forceinline__ void walk_body(const float* __restrict__ src, float* 
     }
 }
 
-// Interior and border warps are separate LAUNCHES: the clamp logic of the border body raises the kernel from 96 to 128
-// registers, and in one kernel every warp pays for it in occupancy (Gauss5 x17 at 16384^2: 3.19 ms combined, 2.56 ms for
-// the interior body alone, with 3 % of the warps on a border).
+// Interior and border warps run different BODIES: as one body the clamp logic raised every warp from 96 to 128 registers
+// (Gauss5 x17 at 16384^2: 3.19 ms combined, 2.56 ms for the interior body alone, with 3 % of the warps on a border).
+// Round 1 made them two launches; since the skewed interior body holds 4 CTAs per SM at up to 128 registers anyway, they
+// are now two block ranges of ONE launch (sep_walk_kernel, MERGED).
 struct WalkRanges {
     int s_lo, s_hi, r_lo, r_hi;   // interior launch: strips [s_lo, s_hi) x rows [r_lo, r_hi) in chunks of zc
     int ns, zcb;                  // border launch: flat (strip, chunk) items in chunks of zcb over the rest of the grid

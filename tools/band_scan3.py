@@ -1,7 +1,6 @@
 """Fixed cost of a band-sized filter / flow launch: Gauss5 x4 (ONE sep_walk launch, T = 4) and flow x5 over windows of
 increasing height, window edges not grid edges (NZ_GRID_EDGES=0).  time(rows) = a + b * rows: `a` is what 8 bands pay 5x."""
 import os, sys
-os.environ.setdefault("NZ_GRID_EDGES", "0")
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import noize_job_b200 as nz
