@@ -18,8 +18,12 @@ LIB = os.path.join(ROOT, "noize-job_b200", "libnoize_b200.so")
 KERNELS = [
     ("fbm_simplex_pair_kernel", r"fbm_simplex_pair_kernel\("),
     ("fbm_psr_pair_kernel", r"fbm_psr_pair_kernel"),
-    ("sep_walk_kernel_R2_T4", r"sep_walk_kernel<2, 4, false, 16>"),
-    ("sep_walk_kernel_R2_T3", r"sep_walk_kernel<2, 3, false, 16>"),
+    # the default filter kernel holds two bodies (border items first, interior CTAs after: MERGED) whose blocks ptxas
+    # interleaves, so its largest backward-branch region spans both; the interior body alone is the unmerged instantiation
+    ("sep_walk_kernel_R2_T4_merged", r"sep_walk_kernel<2, 4, false, 16, false, 1, true>"),
+    ("sep_walk_kernel_R2_T4_skewed_interior", r"sep_walk_kernel<2, 4, false, 16, false, 1, false>"),
+    ("sep_walk_kernel_R2_T3_skewed_interior", r"sep_walk_kernel<2, 3, false, 16, false, 1, false>"),
+    ("sep_walk_kernel_R2_T4_chained_interior", r"sep_walk_kernel<2, 4, false, 16, false, 0, false>"),
     ("sep_ring_kernel_R2", r"sep_ring_kernel<2,"),
     ("flow_walk_kernel_I5", r"flow_walk_kernel<5,"),
     ("flow_group_kernel_I5_NW4", r"flow_group_kernel<5, 4,"),
@@ -70,18 +74,22 @@ def mnemonic(text):
     return t[0].split(".")[0] if t else ""
 
 
-def hottest_loop(ins):
-    """The backward branch that spans the most instructions: (first index, last index) or None."""
+def loops(ins):
+    """Backward-branch regions that are not nested in another one, largest first: [(first index, last index)]."""
     addr = {a: i for i, (a, _) in enumerate(ins)}
-    best = None
+    regs = []
     for i, (a, t) in enumerate(ins):
         if mnemonic(t) == "BRA":
             m = re.search(r"0x([0-9a-f]+)", t)
             if m and int(m.group(1), 16) in addr and int(m.group(1), 16) <= a:
-                j = addr[int(m.group(1), 16)]
-                if best is None or i - j > best[1] - best[0]:
-                    best = (j, i)
-    return best
+                regs.append((addr[int(m.group(1), 16)], i))
+    outer = [r for r in regs if not any(o != r and o[0] <= r[0] and r[1] <= o[1] for o in regs)]
+    return sorted(set(outer), key=lambda r: r[0] - r[1])
+
+
+def hottest_loop(ins):
+    ls = loops(ins)
+    return ls[0] if ls else None
 
 
 def mix(ins):
