@@ -561,6 +561,22 @@ static int32_t finish(Mirror* m) {
     return NZ_OK;
 }
 
+// A stage only READ this mirror (the right operand of a reduce, a curve's samples, the input of a crop, the heights of a
+// mesh): inside a scope whoever touches it next — possibly on another thread's stream, possibly to overwrite it — must wait
+// for that read as well.  The reader's stream already waited for the last writer (acquire), so re-recording `ready` here
+// keeps the order transitive.
+static void publish_read(Mirror* m) {
+    if (!m || !in_scope() || m->bands) return;
+    if (!m->ready && cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        m->ready = nullptr;
+        cudaStreamSynchronize(t_state.stream);      // no event to hand on: finish the read now
+        return;
+    }
+    cudaEventRecord(m->ready, t_state.stream);
+    m->last_stream = t_state.stream;
+}
+
 static int32_t begin_stage() {
     int32_t rc = thread_ready();
     if (rc != NZ_OK) return rc;
@@ -1412,7 +1428,9 @@ NZ_API int32_t nz_reduce(nz_slice_f32 left, nz_slice_f32 right, nz_slice_f32 tmp
     rc = run_inplace_stage(left, resolution, "nz_reduce", false, [&](Mirror& m, float**) {
         int32_t rr = acquire(right, /*need_contents=*/true, &r);
         if (rr != NZ_OK) return rr;
-        return launch_reduce(m.d, r->d, m.n, operation, t_state.stream);
+        rr = launch_reduce(m.d, r->d, m.n, operation, t_state.stream);
+        publish_read(r);
+        return rr;
     });
     return rc;              // outside a scope run_inplace_stage's cleanup guard has released the right operand's mirror
 }
@@ -1428,7 +1446,9 @@ NZ_API int32_t nz_curve(nz_slice_f32 src, nz_slice_f32 tmp, nz_slice_f32 curve, 
         int32_t rr = acquire(curve, /*need_contents=*/true, &c);
         if (rr != NZ_OK) return rr;
         const PointwiseOp op{PW_CURVE, (float)curve.length, 0.0f, c->d};
-        return materialize(m, &op);
+        rr = materialize(m, &op);
+        publish_read(c);
+        return rr;
     }, false, [](BandSet&) { return (int32_t)NZ_E_UNSUPPORTED; }, /*keep_pending=*/true);
     return rc;
 }
@@ -1448,6 +1468,7 @@ NZ_API int32_t nz_crop(nz_slice_f32 input, int32_t input_resolution, nz_slice_f3
     if ((rc = acquire(output, /*need_contents=*/false, &out)) != NZ_OK) return rc;
     if ((rc = mark_uploaded()) != NZ_OK) return rc;
     rc = launch_crop(in->d, input_resolution, out->d, output_resolution, offset, t_state.stream);
+    publish_read(in);
     if (rc == NZ_OK) out->dirty = true;
     int32_t rc2 = finish(out);
     return rc != NZ_OK ? rc : rc2;

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(TX) fill_norm_zero_kernel(float* __restrict__ 
 // scratch is only needed by the per-iteration path (water + 4 flow fields in HBM); the fused wavefront
 // kernel (flowwave_kernels.cu) keeps all state in shared memory and needs just an output buffer
 size_t flowmap_scratch_bytes(int width, int rows, int iterations) {
-    if (flow_wave_supported(width, rows, iterations, nullptr, nullptr)) return 0;
+    // (the same predicate launch_flowmap uses, minus the pointers: a caller with a null or misaligned tmp buffer is told so there)
+    if (!getenv("NZ_FLOW_UNFUSED") && flow_wave_supported(width, rows, iterations, nullptr, nullptr)) return 0;
     return (size_t)width * rows * sizeof(float) * 5;
 }
 

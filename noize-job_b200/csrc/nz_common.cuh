@@ -126,6 +126,18 @@ void dev_free(void* p);
 // side stream of the calling thread on the current device (aux_stream.cu)
 int32_t aux_fork(cudaStream_t main, cudaStream_t* aux);
 int32_t aux_join(cudaStream_t main);
+// joins the side stream when a launcher leaves early (an error return between aux_fork and its aux_join)
+struct AuxJoinGuard {
+    cudaStream_t main;
+    bool armed = false;
+    explicit AuxJoinGuard(cudaStream_t m) : main(m) {}
+    ~AuxJoinGuard() { if (armed) aux_join(main); }
+    int32_t join() {
+        if (!armed) return 0;
+        armed = false;
+        return aux_join(main);
+    }
+};
 
 // host-side table helpers (tables.cpp part of abi.cu)
 void gauss_table(double sigma, int width, float* out);

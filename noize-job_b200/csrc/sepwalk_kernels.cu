@@ -296,7 +296,9 @@ struct WalkRanges {
     int s_lo, s_hi, r_lo, r_hi;   // interior launch: strips [s_lo, s_hi) x rows [r_lo, r_hi) in chunks of zc
     int ns, zcb;                  // border launch: flat (strip, chunk) items in chunks of zcb over the rest of the grid
     int n_top, n_bot, n_items;    //   all strips x [0, r_lo), all strips x [r_hi, H), border strips x [r_lo, r_hi)
-    int nb, ctas_x;               // merged launch: blocks [0, nb) take the border items, block nb + by * ctas_x + bx is interior CTA (bx, by)
+    // merged launch: blocks [0, nb_first) and blocks from nb_first + n_int on take the border items (nb of them in all: either
+    // all first or all last), block nb_first + by * ctas_x + bx is interior CTA (bx, by)
+    int nb, nb_first, n_int, ctas_x;
 };
 
 // one (strip, chunk) item of the border list, on the clamping body
@@ -328,7 +330,7 @@ __device__ __forceinline__ void border_item(const float* __restrict__ src, float
     walk_body<R, T, SCALE, true, 16>(src, dst, W, H, factor, kx, kz, wx0, zc0, zc1, ring_base);
 }
 
-// MERGED: one launch for the whole grid.  The first g.nb blocks (placed first by the block scheduler) walk the border
+// MERGED: one launch for the whole grid.  g.nb blocks (the first ones by default: see the launch) walk the border
 // items on the clamping body, the others are the interior CTAs.  As two launches, even forked onto a side stream, the
 // border walk did not hide under the interior launch: it cost its full ~45 us per launch at every grid size
 // (tools/band_scan3.py: Gauss5 x4 on 2116 rows 135 us with the border launch, 96 us without; 16384 rows 581 / 535).
@@ -342,11 +344,13 @@ sep_walk_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, i
     extern __shared__ __align__(16) float ring[];   // [WALK_WARPS][PFR][STRIP] (+ [WALK_WARPS][PFR] mbarriers for the bulk feed)
     const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * (PFR * STRIP));
     if (MERGED) {
-        if (bx < g.nb) {
-            border_item<R, T, SCALE>(src, dst, W, H, factor, kx, kz, g, bx * WALK_WARPS + (threadIdx.x >> 5), ring_base);
+        int bitem = -1;
+        if (bx < g.nb_first) bitem = bx;
+        else if ((bx -= g.nb_first) >= g.n_int) bitem = bx - g.n_int;
+        if (bitem >= 0) {
+            border_item<R, T, SCALE>(src, dst, W, H, factor, kx, kz, g, bitem * WALK_WARPS + (threadIdx.x >> 5), ring_base);
             return;
         }
-        bx -= g.nb;
         by = bx / g.ctas_x;
         bx -= by * g.ctas_x;
     }
@@ -407,6 +411,7 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     const bool skew = T > 1 && !bulk && !(es && es[0] == '0') && (merge || factor == 1.0f);
     const bool forked = g.n_items > 0 && has_interior && !merge;
     const size_t ring_bytes = (size_t)WALK_WARPS * 16 * STRIP * sizeof(float);
+    AuxJoinGuard side(s);                          // an early (error) return joins the side stream too
     if (g.n_items > 0 && !merge) {
         // two launches: the border launch reads the same input and writes other cells than the interior launch; it goes to
         // the side stream when there is an interior launch to run beside
@@ -414,6 +419,7 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
         if (forked) {
             int32_t rc = aux_fork(s, &bs);
             if (rc != NZ_OK) return rc;
+            side.armed = true;
         }
         if (factor == 1.0f)
             sep_walk_border_kernel<R, T, false><<<cdiv(g.n_items, WALK_WARPS), WALK_WARPS * 32, ring_bytes, bs>>>(in, out, width, rows, factor, tx, tz, g);
@@ -450,9 +456,14 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     }
     const size_t sm = ring_bytes;
     if (merge) {
+        // Border blocks FIRST (the chunk height counts them into the waves).  Measured against border blocks last
+        // (NZ_WALK_BORDER_FIRST=0), Gauss5 x17, us: 2116 rows 417 / 447, 4232 rows 731 / 804, 16384 rows 2544 / 2603.
+        static const bool border_first = [] { const char* e = getenv("NZ_WALK_BORDER_FIRST"); return !(e && e[0] == '0'); }();
         g.nb = cdiv(g.n_items, WALK_WARPS);
+        g.nb_first = border_first ? g.nb : 0;
         g.ctas_x = ctas_x;
-        const dim3 grid(g.nb + ctas_x * cdiv(irows, zc));
+        g.n_int = ctas_x * cdiv(irows, zc);
+        const dim3 grid(g.nb + g.n_int);
         if (factor == 1.0f) {
             if (skew) sep_walk_kernel<R, T, false, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
             else sep_walk_kernel<R, T, false, 16, false, 0, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
@@ -475,7 +486,7 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
         }
     }
     NZ_LAUNCHED();
-    if (forked) return aux_join(s);
+    if (forked) return side.join();
     return NZ_OK;
 }
 
