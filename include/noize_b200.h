@@ -314,7 +314,7 @@ NZ_API int32_t nz_context_release(const char* name);
  *       exchanged by ncclSend/ncclRecv (nz_comm_*; libnccl.so.2 is bound at run time), or all bands in one process. */
 #define NZ_BANDS_MIN_RESOLUTION 4096
 #define NZ_COMM_ID_BYTES 128            /* sizeof(ncclUniqueId) */
-#define NZ_BANDS_EXCHANGE 0             /* ghost rows come from the neighbours, once per stage */
+#define NZ_BANDS_EXCHANGE 0             /* the ghost rows of the noise stage come from the neighbours, once per pass */
 #define NZ_BANDS_RECOMPUTE 1            /* the noise stage evaluates every ghost row the chain will consume: no communication */
 
 /* Host layer: split large grids over the first n_bands devices given to nz_init (0 or 1: off).  Devices may repeat

@@ -535,12 +535,8 @@ int32_t chain_setup(Chain& c, const nz_chain_config* cfg, int mode) {
     return NZ_OK;
 }
 
-int chain_cap(const Chain& c) {
-    const int above = c.h_filter + c.h_flow + c.h_erosion + c.h_mesh;
-    if (c.mode == NZ_BANDS_RECOMPUTE) return above;
-    const int merged = c.h_flow + c.h_erosion + c.h_mesh;     // the second exchange of a pass (see chain_run)
-    return c.h_filter > merged ? c.h_filter : merged;
-}
+// ghost rows a band holds on either side: everything the chain consumes below the noise stage (see chain_run)
+int chain_cap(const Chain& c) { return c.h_filter + c.h_flow + c.h_erosion + c.h_mesh; }
 
 int32_t chain_check_fit(const Chain& c) {
     const BandSet& bs = *c.bs;
@@ -566,32 +562,29 @@ int32_t chain_run(Chain& c, bool timed) {
     BandSet& bs = *c.bs;
     const bool exch = c.mode == NZ_BANDS_EXCHANGE;
     c.timed = timed;
-    // recompute mode: ghost rows still needed AFTER each stage (the window shrinks stage by stage)
-    const int rem_filter_a = exch ? 0 : c.h_flow + c.h_erosion + c.h_mesh, rem_filter_b = exch ? 0 : c.h_flow + c.h_mesh;
+    // Both modes run every stage below the noise on SHRINKING windows: a stage with r ghost rows of stencil reach leaves the
+    // outer r rows of its window wrong, which is fine as long as the stages after it need that many rows less.  Ghost rows
+    // still needed AFTER the filter (above / below): the flow map's 2I+1, the value erosion's (above only), the mesh's 1.
+    const int rem_filter_a = c.h_flow + c.h_erosion + c.h_mesh, rem_filter_b = c.h_flow + c.h_mesh;
+    const int noise_a = c.h_filter + rem_filter_a, noise_b = c.h_filter + rem_filter_b;
     int32_t rc;
     if ((rc = chain_mark(c, 0)) != NZ_OK) return rc;
-    {
-        const int ea = exch ? 0 : c.h_filter + rem_filter_a, eb = exch ? 0 : c.h_filter + rem_filter_b;
-        rc = bandset_fractal(bs, f.noise_type, f.hurst, f.starting_amplitude, f.stepdown, f.detune_rate, f.octaves, f.xpos, f.zpos,
-                             f.noise_size, ea, eb);
-        if (rc != NZ_OK) return rc;
-    }
+    // recompute mode: the noise stage evaluates the ghost rows itself (noise is a pure function of position)
+    rc = bandset_fractal(bs, f.noise_type, f.hurst, f.starting_amplitude, f.stepdown, f.detune_rate, f.octaves, f.xpos, f.zpos,
+                         f.noise_size, exch ? 0 : noise_a, exch ? 0 : noise_b);
+    if (rc != NZ_OK) return rc;
+    // Exchange mode moves ghost rows ONCE per pass: the noise rows everything downstream needs (51 above / 46 below at the
+    // C5 parameters, 3.3 MB each way).  Round 2 first exchanged twice (34 rows before the filter, 17 / 12 of filtered rows
+    // before the flow map) and round 1 once per stage; every NCCL round trip costs ~40 us on a band that takes 2.3 ms, the
+    // 17 extra rows through the filter 6 us.
+    if (exch && (rc = bandset_exchange(bs, noise_a, noise_b)) != NZ_OK) return rc;
     if ((rc = chain_mark(c, 1)) != NZ_OK) return rc;
     if (f.filter_iterations > 0) {
-        rc = c.ksize ? bandset_separable(bs, c.ksize, c.kx, c.kz, c.factor, f.filter_iterations, rem_filter_a, rem_filter_b, exch)
-                     : bandset_sobel2d(bs, f.filter_iterations, rem_filter_a, rem_filter_b, exch);
+        rc = c.ksize ? bandset_separable(bs, c.ksize, c.kx, c.kz, c.factor, f.filter_iterations, rem_filter_a, rem_filter_b, false)
+                     : bandset_sobel2d(bs, f.filter_iterations, rem_filter_a, rem_filter_b, false);
         if (rc != NZ_OK) return rc;
     }
     if ((rc = chain_mark(c, 2)) != NZ_OK) return rc;
-    if (exch) {
-        // Exchange mode moves ghost rows TWICE per pass: before the filter (r * iterations rows) and here, once, for
-        // everything downstream — the flow map's 2I+1 rows plus the rows the value erosion (above only) and the mesh (1)
-        // will still need from what the flow map and the erosion produce on those ghost rows.  Per-stage exchanges would
-        // cost two more NCCL round trips for a few rows of extra stencil work (17 above / 12 below at the C5 parameters).
-        const int a2 = c.h_flow + c.h_erosion + c.h_mesh, b2 = c.h_flow + c.h_mesh;
-        if ((rc = bandset_exchange(bs, a2, b2)) != NZ_OK) return rc;
-    }
-    // after the merged exchange both modes run the rest of the chain on shrinking windows
     const int xfa = c.h_erosion + c.h_mesh, xfb = c.h_mesh, xea = c.h_mesh, xeb = c.h_mesh;
     if (f.flow_iterations > 0) {
         rc = bandset_flowmap(bs, f.flow_iterations, f.norm_min, f.norm_max, xfa, xfb, false);
