@@ -42,5 +42,27 @@ R = n - 8
 v = torch.empty((R + 1) * (R + 1), 12, device="cuda"); i = torch.empty(6 * R * R, dtype=torch.int32, device="cuda")
 for mt in (0, 1):
     d.heightmap_mesh(mt, v, i, R, n, 4, 2000.0, 1500.0, b)
+# a grid above 4M cells takes the interior launches of the register-walk flow map (group strips at I = 5, independent strips
+# at I = 3) with the border launch beside them; the merged filter launch (border items + interior CTAs) on the same grid
+w2, h2 = 2304, 2048
+a2 = torch.rand(h2, w2, device="cuda") * 0.05; b2 = torch.empty_like(a2)
+d.kernel_filter(a2, b2, 2, 7)          # Gauss5: T = 4 + 3
+d.kernel_filter(a2, b2, 5, 2)          # a filter with a scale factor
+d.flowmap(a2.clone(), b2, None, 5, 0.0, 0.005)
+d.flowmap(a2.clone(), b2, None, 3, 0.0, 0.005)
+# row bands inside the library: two bands on this GPU, one exchange per pass, and the same chain in recompute mode
+from noize_job_b200 import bands
+cfg = bands.ChainConfig(N=512, noise_size=170, filter_iterations=6, flow_iterations=3, erosion_iterations=4)
+for mode in ("exchange", "recompute"):
+    ch = bands.LibBandChain(cfg, devices=[0, 0], mode=mode)
+    ch.run(); ch.sync() if hasattr(ch, "sync") else None
+    ch.release()
+# deferred element-wise run through the host layer
+h = np.random.rand(256 * 256).astype(np.float32)
+with nz.host.pipeline():
+    nz.host.constant(h, None, 0, 0.9, 256)
+    nz.host.normalize(h, None, np.array([0.0, 1.0, 1.0], np.float32), 256)
+    nz.host.curve(h, None, np.linspace(0, 1, 32).astype(np.float32), 256)
+    nz.host.constant(h, None, 1, 0.5, 256)
 torch.cuda.synchronize()
 print("sanitize_run ok")
