@@ -581,7 +581,8 @@ def run_ours(args):
 
     # facts about this rank's band that the report needs after the chain is gone
     env.own_rows, env.vz0, env.vz1 = chain.own, chain.vz0, chain.vz1
-    env.halo_bytes_per_step = chain.bytes_exchanged // max(1, chain.runs)
+    # ghost-row bytes RECEIVED per step, summed over the ranks (an inner band receives from both neighbours)
+    env.halo_bytes_per_step = int(env.sum_over_ranks([chain.bytes_exchanged // max(1, chain.runs)])[0])
     env.engine_name = chain.name
 
     # ---- end to end through the public API with host buffers ------------------------------------------------
