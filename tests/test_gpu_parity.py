@@ -730,6 +730,31 @@ def test_flow_group_strips_equal_wavefront_kernel_bitwise(nz, oracle, torch_cuda
     assert nz.device.flow_walk_reruns() == before
 
 
+@pytest.mark.parametrize("rows,width,ftype,iters", [(700, 600, 2, 17), (1300, 1000, 3, 7), (513, 472, 6, 4), (2200, 4096, 2, 17), (97, 2048, 7, 3),
+                                                      (3000, 236, 2, 9), (4096, 4096, 12, 2), (640, 1536, 8, 5), (1200, 2000, 0, 6)])
+def test_walk_filter_forms_agree_bitwise(nz, torch_cuda, monkeypatch, rows, width, ftype, iters):
+    """The register-walk filter's launch forms: border items inside the interior launch (default) or as a launch of their own
+    (NZ_WALK_MERGE=0), stages skewed by one step (default) or chained (NZ_WALK_SKEW=0).  Every cell sees the same operations in
+    the same order in all four, so the bits agree — also with the shared-memory tile kernel (NZ_SEP_PATH=fused)."""
+    torch = torch_cuda
+    a = torch.from_numpy(rand_grid(rows, width)).cuda()
+    monkeypatch.setenv("NZ_SEP_PATH", "walk")
+    ref = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+    for merge, skew in (("0", "1"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("NZ_WALK_MERGE", merge)
+        monkeypatch.setenv("NZ_WALK_SKEW", skew)
+        got = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref), (merge, skew)
+    monkeypatch.delenv("NZ_WALK_MERGE")
+    monkeypatch.delenv("NZ_WALK_SKEW")
+    if ftype != 11:
+        monkeypatch.setenv("NZ_SEP_PATH", "fused")
+        fused = nz.device.kernel_filter(a.clone(), torch.empty_like(a), ftype, iters).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(fused, ref)
+
+
 @pytest.mark.parametrize("rows,width,ftype,iters", [(700, 600, 2, 17), (1300, 1000, 3, 7), (513, 472, 6, 4), (2200, 4096, 2, 17)])
 def test_bulk_copy_row_feed_equals_cp_async_feed_bitwise(nz, torch_cuda, monkeypatch, rows, width, ftype, iters):
     """NZ_WALK_FEED=bulk: the separable walk fed by cp.async.bulk + mbarrier (the TMA engine, SASS UBLKCP) instead of per-lane
