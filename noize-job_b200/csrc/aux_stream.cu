@@ -1,7 +1,7 @@
-// aux_stream.cu — a side stream per (host thread, device) for launches that are independent of the next launch on the
-// caller's stream.  The register-walk kernels (flowwalk_kernels.cu, sepwalk_kernels.cu) run their border warps as a
-// separate, short launch; enqueued on the caller's stream it would serialise with the interior launch (one chunk walk of
-// latency, ~35-90 us, per launch); forked onto the side stream it runs underneath it.
+// aux_stream.cu — a side stream per (host thread, device, caller stream) for a launch that is independent of the next launch on
+// the caller's stream.  The register-walk flow map (flowwalk_kernels.cu) runs its border warps as a separate, short launch
+// beside the interior launch (the register-walk filter did too until its border items moved into the interior launch; its
+// two-launch form is still selectable).
 //   aux_fork(main, &aux): everything enqueued on `main` so far happens before what is enqueued on `aux` next
 //   aux_join(main)      : everything enqueued on `aux` so far happens before what is enqueued on `main` next
 // Both are event record/wait pairs (legal inside stream capture).  NZ_NO_AUX_STREAM=1 makes aux == main.
@@ -15,21 +15,59 @@ struct Aux {
     cudaStream_t s = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-thread_local Aux t_aux[64];
+// One side stream per (host thread, device, caller stream): a thread that drives several streams (the tile world's slots) gets
+// one side stream for each, so their border launches neither serialise on one stream nor make one slot's join wait for
+// another slot's work.  At most AUX_MAX live entries per thread: beyond that the oldest is recycled (its stream is idle by
+// then or will simply order a little more than necessary — fork and join on the same entry are always a matched pair).
+constexpr int AUX_MAX = 16;
+struct AuxEntry {
+    int dev = -1;
+    cudaStream_t main = nullptr;
+    Aux a;
+};
+thread_local AuxEntry t_aux[AUX_MAX];
+thread_local int t_aux_next = 0;
 
-int32_t get_aux(Aux** out) {
+int32_t get_aux(cudaStream_t main, Aux** out) {
     int dev = 0;
     NZ_CUDA(cudaGetDevice(&dev));
-    NZ_REQUIRE(dev >= 0 && dev < 64, "aux stream: device ordinal %d out of range", dev);
-    Aux& a = t_aux[dev];
-    if (!a.s) {
+    for (AuxEntry& e : t_aux)
+        if (e.a.s && e.dev == dev && e.main == main) {
+            *out = &e.a;
+            return NZ_OK;
+        }
+    AuxEntry* e = nullptr;
+    for (AuxEntry& c : t_aux)
+        if (!c.a.s) { e = &c; break; }
+    if (!e) {
+        // recycle: prefer an entry of this device (its stream and events can be reused as they are)
+        for (int k = 0; k < AUX_MAX && !e; k++) {
+            AuxEntry& c = t_aux[(t_aux_next + k) % AUX_MAX];
+            if (c.dev == dev) { e = &c; t_aux_next = (t_aux_next + k + 1) % AUX_MAX; }
+        }
+        if (!e) {
+            e = &t_aux[t_aux_next];
+            t_aux_next = (t_aux_next + 1) % AUX_MAX;
+            int prev = dev;
+            cudaSetDevice(e->dev);
+            cudaStreamSynchronize(e->a.s);
+            cudaStreamDestroy(e->a.s);
+            cudaEventDestroy(e->a.fork);
+            cudaEventDestroy(e->a.join);
+            cudaSetDevice(prev);
+            e->a = Aux{};
+        }
+    }
+    if (!e->a.s) {
         // (a high-priority side stream was tried, to make the border CTAs win SM slots from the interior launch: no
         // measurable change, tools/band_scan3.py)
-        NZ_CUDA(cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking));
-        NZ_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
-        NZ_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+        NZ_CUDA(cudaStreamCreateWithFlags(&e->a.s, cudaStreamNonBlocking));
+        NZ_CUDA(cudaEventCreateWithFlags(&e->a.fork, cudaEventDisableTiming));
+        NZ_CUDA(cudaEventCreateWithFlags(&e->a.join, cudaEventDisableTiming));
     }
-    *out = &a;
+    e->dev = dev;
+    e->main = main;
+    *out = &e->a;
     return NZ_OK;
 }
 
@@ -73,7 +111,7 @@ int32_t aux_fork(cudaStream_t main, cudaStream_t* aux) {
         return NZ_OK;
     }
     Aux* a;
-    int32_t rc = get_aux(&a);
+    int32_t rc = get_aux(main, &a);
     if (rc != NZ_OK) return rc;
     NZ_CUDA(cudaEventRecord(a->fork, main));
     NZ_CUDA(cudaStreamWaitEvent(a->s, a->fork, 0));
@@ -84,7 +122,7 @@ int32_t aux_fork(cudaStream_t main, cudaStream_t* aux) {
 int32_t aux_join(cudaStream_t main) {
     if (aux_disabled()) return NZ_OK;
     Aux* a;
-    int32_t rc = get_aux(&a);
+    int32_t rc = get_aux(main, &a);
     if (rc != NZ_OK) return rc;
     NZ_CUDA(cudaEventRecord(a->join, a->s));
     NZ_CUDA(cudaStreamWaitEvent(main, a->join, 0));
