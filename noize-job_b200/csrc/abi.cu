@@ -235,6 +235,10 @@ struct Mirror {
 struct Scope {
     std::mutex mu;
     std::unordered_map<const void*, Mirror> mirrors;
+    // A scope that is closed while another thread is still inside it can receive mirrors afterwards (that thread's stage
+    // calls keep working on the object it entered); they are released when the last thread leaves.  Their contents are not
+    // brought home: the scope was closed, the host was told so.
+    ~Scope();
 };
 static std::mutex g_scopes_mu;
 static std::unordered_map<long long, std::shared_ptr<Scope>> g_scopes;
@@ -420,6 +424,18 @@ static void release_mirror(Mirror& m) {
     m.bands.reset();        // ~BandSet synchronises its streams and frees its buffers
     if (m.ready) cudaEventDestroy(m.ready);
     m.ready = nullptr;
+}
+
+Scope::~Scope() {
+    if (mirrors.empty()) return;
+    // whatever still runs on these buffers (any stream of the primary device).  At process exit the runtime may already be
+    // unloading: then nothing is released (the process is going away with its memory)
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (auto& kv : mirrors) release_mirror(kv.second);
+    mirrors.clear();
 }
 
 // Obtain the device mirror of a host slice.  `need_contents`: the stage reads the slice (H2D unless a resident mirror is

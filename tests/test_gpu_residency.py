@@ -211,3 +211,40 @@ def test_reduce_pipeline_joins_two_upstreams_on_the_device(nz):
     assert np.array_equal(data, np.maximum(a, b) * np.float32(2.0))
     assert isinstance(out, nz.GeneratorData)                                       # ReduceStage.TransformData (ReduceStage.cs:52-61)
     assert not nz.GpuResidency.IsOpen("joined")
+
+
+def test_scope_closed_under_a_thread_still_inside_releases_late_mirrors(nz):
+    """A scope closed by one thread while another is still inside it: the second thread's later stage calls keep working on
+    the scope object it entered, and what they leave behind is released when that thread leaves (no device memory leak, and the
+    library keeps working)."""
+    import threading
+    import numpy as np
+    res = 256
+    sid = nz.host.scope_create()
+    entered, closed, done = threading.Event(), threading.Event(), threading.Event()
+    err = []
+
+    def worker():
+        try:
+            nz.host.scope_enter(sid)
+            entered.set()
+            closed.wait(10)
+            a = np.zeros(res * res, np.float32)
+            nz.host.fractal(a, res, 3, 0.4, 1.0, 2.0, 0.0, 3, 0, 0, 300)     # lands in the closed scope's object
+            nz.host.scope_leave()                                            # last reference: the mirror is released here
+        except Exception as e:                                               # noqa: BLE001
+            err.append(e)
+        finally:
+            done.set()
+
+    t = threading.Thread(target=worker)
+    t.start()
+    assert entered.wait(10)
+    nz.host.scope_close(sid)
+    closed.set()
+    assert done.wait(30)
+    t.join()
+    assert not err, err
+    b = np.zeros(res * res, np.float32)
+    nz.host.fractal(b, res, 3, 0.4, 1.0, 2.0, 0.0, 3, 0, 0, 300)
+    assert float(b.max()) > 0.0
