@@ -257,7 +257,23 @@ struct ThreadState {
     long long scope_id = 0;
     bool owns_scope = false;        // entered through nz_pipeline_begin: nz_pipeline_end closes it
     Scope local;                    // mirrors of a call made outside any scope (dropped when the call returns)
-    ~ThreadState() {}
+    // A host with a job system creates and retires worker threads: the thread's stream and events go with it.  (At process
+    // exit the runtime may be unloading already; the calls then fail harmlessly.)
+    ~ThreadState() {
+        if (!stream) return;
+        int prev = 0;
+        const bool have = cudaGetDevice(&prev) == cudaSuccess;
+        if (cudaSetDevice(device) == cudaSuccess) {
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+            for (auto& e : ev) if (e) cudaEventDestroy(e);
+            if (copy_stream) cudaStreamDestroy(copy_stream);
+            for (auto& e : mesh_ev) if (e) cudaEventDestroy(e);
+            if (have) cudaSetDevice(prev);
+        }
+        cudaGetLastError();
+        stream = nullptr;
+    }
 };
 static thread_local ThreadState t_state;
 static inline bool in_scope() { return (bool)t_state.scope; }

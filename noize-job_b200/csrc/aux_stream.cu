@@ -25,8 +25,28 @@ struct AuxEntry {
     cudaStream_t main = nullptr;
     Aux a;
 };
-thread_local AuxEntry t_aux[AUX_MAX];
-thread_local int t_aux_next = 0;
+struct AuxTable {
+    AuxEntry e[AUX_MAX];
+    int next = 0;
+    // worker threads come and go under a job system: their side streams go with them
+    ~AuxTable() {
+        int prev = 0;
+        const bool have = cudaGetDevice(&prev) == cudaSuccess;
+        for (AuxEntry& c : e)
+            if (c.a.s && cudaSetDevice(c.dev) == cudaSuccess) {
+                cudaStreamSynchronize(c.a.s);
+                cudaStreamDestroy(c.a.s);
+                cudaEventDestroy(c.a.fork);
+                cudaEventDestroy(c.a.join);
+                c.a = Aux{};
+            }
+        if (have) cudaSetDevice(prev);
+        cudaGetLastError();
+    }
+};
+thread_local AuxTable t_auxtab;
+#define t_aux t_auxtab.e
+#define t_aux_next t_auxtab.next
 
 int32_t get_aux(cudaStream_t main, Aux** out) {
     int dev = 0;
