@@ -406,9 +406,10 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
     const char* ef = getenv("NZ_WALK_FEED");      // bulk: the bulk-copy (TMA engine) row feed, kept as a MEASURED alternative (profiles/r2_walk_feed_scan.txt)
     const bool bulk = ef && ef[0] == 'b' && factor == 1.0f;
     const char* em = getenv("NZ_WALK_MERGE");     // 0: border and interior as two launches (the former form), for comparison
-    const bool merge = has_interior && !bulk && !(em && em[0] == '0');
-    const char* es = getenv("NZ_WALK_SKEW");      // 0: chained stages (the former form), for comparison
-    const bool skew = T > 1 && !bulk && !(es && es[0] == '0') && (merge || factor == 1.0f);
+    const char* es = getenv("NZ_WALK_SKEW");      // 0: chained stages (the former form, which is also two launches), for comparison
+    const bool chained = es && es[0] == '0';
+    const bool merge = has_interior && !bulk && !chained && !(em && em[0] == '0');
+    const bool skew = T > 1 && !bulk && !chained && (merge || factor == 1.0f);
     const bool forked = g.n_items > 0 && has_interior && !merge;
     const size_t ring_bytes = (size_t)WALK_WARPS * 16 * STRIP * sizeof(float);
     AuxJoinGuard side(s);                          // an early (error) return joins the side stream too
@@ -464,13 +465,9 @@ int32_t launch_walk_rt(const float* in, float* out, int width, int rows, const f
         g.ctas_x = ctas_x;
         g.n_int = ctas_x * cdiv(irows, zc);
         const dim3 grid(g.nb + g.n_int);
-        if (factor == 1.0f) {
-            if (skew) sep_walk_kernel<R, T, false, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
-            else sep_walk_kernel<R, T, false, 16, false, 0, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
-        } else {
-            if (skew) sep_walk_kernel<R, T, true, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
-            else sep_walk_kernel<R, T, true, 16, false, 0, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
-        }
+        // (T = 1 has nothing to skew: SK = 1 is the same body there)
+        if (factor == 1.0f) sep_walk_kernel<R, T, false, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
+        else sep_walk_kernel<R, T, true, 16, false, 1, true><<<grid, WALK_WARPS * 32, sm, s>>>(in, out, width, rows, factor, tx, tz, zc, g);
     } else {
         const dim3 grid(ctas_x, cdiv(irows, zc));
         if (bulk) {
@@ -509,9 +506,11 @@ int32_t launch_walk_r(float* d_data, float* d_tmp, int width, int rows, const fl
         switch (T) {
             case 1: rc = launch_walk_rt<R, 1>(cur, other, width, rows, kx, kz, factor, s); break;
             case 2: rc = launch_walk_rt<R, 2>(cur, other, width, rows, kx, kz, factor, s); break;
-            case 3: rc = launch_walk_rt<R, 3>(cur, other, width, rows, kx, kz, factor, s); break;
-            case 5: rc = launch_walk_rt<(R <= 2 ? R : 1), 5>(cur, other, width, rows, kx, kz, factor, s); break;   // only reached with R <= 2
-            default: rc = launch_walk_rt<R, 4>(cur, other, width, rows, kx, kz, factor, s); break;
+            // T >= 3 is only reached with R <= 2 (TMAX above): for R > 2 the template argument names an instantiation that
+            // exists anyway, so the deep register windows of (R = 3, 4; T = 3, 4) are not compiled at all
+            case 3: rc = launch_walk_rt<(R <= 2 ? R : 1), 3>(cur, other, width, rows, kx, kz, factor, s); break;
+            case 5: rc = launch_walk_rt<(R <= 2 ? R : 1), 5>(cur, other, width, rows, kx, kz, factor, s); break;
+            default: rc = launch_walk_rt<(R <= 2 ? R : 1), 4>(cur, other, width, rows, kx, kz, factor, s); break;
         }
         if (rc != NZ_OK) return rc;
         left -= T;
