@@ -120,3 +120,36 @@ def test_cpp_host_mirror_is_built_and_fails_loudly_without_a_gpu(nz):
         pytest.skip("GPU present: covered by the gpu tests")
     out = subprocess.run([exe, "64"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 1 and "no CPU fallback" in out.stderr
+
+
+def test_csharp_bindings_name_exported_symbols_and_mirror_the_structs(nz):
+    """The C# interop files cannot be compiled here (no Unity / mono), so keep them in step with the header mechanically:
+    every function behind a [DllImport] is a symbol the library exports, and the blittable structs have as many 32-bit /
+    pointer fields as their C counterparts."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = nz.load()
+    names = set()
+    for path in glob.glob(os.path.join(root, "noize-job_b200", "unity", "Interop", "*.cs")):
+        src = open(path).read()
+        names |= set(re.findall(r"\[DllImport\(LIB\)\]\s*public static extern [^;(]*?\b(nz_[a-z0-9_]+)\s*\(", src))
+    assert len(names) >= 45, sorted(names)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    header = open(os.path.join(root, "include", "noize_b200.h")).read()
+
+    def c_fields(struct_name):
+        end = header.index("} " + struct_name + ";")
+        body = header[header.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return sum(len(decl.split(",")) for decl in body.split(";") if decl.strip())
+
+    def cs_fields(struct_name):
+        src = open(os.path.join(root, "noize-job_b200", "unity", "Interop", "NoizeB200Worlds.cs")).read()
+        body = re.search(r"struct " + struct_name + r" \{(.*?)\n    \}", src, re.S).group(1)
+        body = re.sub(r"//.*", "", body)
+        return sum(len(decl.split(",")) for decl in body.split(";") if decl.strip())
+
+    for c, cs in (("nz_tile_config", "NzTileConfig"), ("nz_chain_config", "NzChainConfig"), ("nz_band_info", "NzBandInfo")):
+        assert c_fields(c) == cs_fields(cs), (c, c_fields(c), cs_fields(cs))
