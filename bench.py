@@ -561,6 +561,7 @@ def run_ours(args):
     barrier()
     names = ["noise", "filter", "flow", "erosion", "mesh", "end"]
     launches0 = nz.host.kernel_launch_count()
+    reruns0 = nz.device.flow_walk_reruns()
     if sampler:
         sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -583,6 +584,9 @@ def run_ours(args):
     env.own_rows, env.vz0, env.vz1 = chain.own, chain.vz0, chain.vz1
     # ghost-row bytes RECEIVED per step, summed over the ranks (an inner band receives from both neighbours)
     env.halo_bytes_per_step = int(env.sum_over_ranks([chain.bytes_exchanged // max(1, chain.runs)])[0])
+    # launches of the register-walk flow map that left its guarded fast paths and were redone on the wavefront kernel
+    # (exact either way; 0 on ordinary terrain, garbage ghost rows of a band included), summed over the ranks
+    env.flow_walk_reruns = int(env.sum_over_ranks([nz.device.flow_walk_reruns() - reruns0])[0])
     env.engine_name = chain.name
 
     # ---- end to end through the public API with host buffers ------------------------------------------------
@@ -678,6 +682,7 @@ def run_ours(args):
         "stages": stages, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
         "e2e_host_input": e2e_in, "band_check": check, "configs": configs, "gpu_launches": int(launches),
         "halo_bytes_per_step": int(env.halo_bytes_per_step),
+        "flow_walk_reruns": env.flow_walk_reruns,
         "parity": "GPU == oracle within the per-stage tolerances (tests/); oracle == Burst reference UNPINNED at bit level (no Unity here)",
         "clocks": sampler.report() if sampler else None,
     }
